@@ -1,0 +1,118 @@
+/*
+ * lowdin_it.h -- C ABI of liblowdin_itgpu.so, the B200 (sm_100a) four-index AO->MO
+ * two-particle integral transformation for openLOWDIN.
+ *
+ * This is the drop-in boundary for the reference's integral-transformation stage
+ * (src/integralsTransformation).  A Fortran host binds these entry points with
+ * ISO_C_BINDING exactly as TransformIntegralsD.f90:55-96 binds the reference's own
+ * C++ transformer (IntTransfD.h:57-82); see INTEGRATION.md for the shim.
+ *
+ * Conventions (identical to the reference's):
+ *   - coefficient matrices are COLUMN-MAJOR, C(mu,p), leading dimension ldc
+ *     (TransformIntegralsD.f90:192-196);
+ *   - windows are 1-based inclusive {p_l,p_u,q_l,q_u,r_l,r_u,s_l,s_u}
+ *     (TransformIntegralsC.f90:1456-1612, TransformIntegralsE.f90:1916-2062);
+ *   - AO integrals arrive in the reference's .ints stack layout
+ *     (int32 p[],q[],r[],s[]; double v[]; 1-based; terminator p=-1;
+ *     Libint2Iface.cpp:3414-3426, TransformIntegralsC.f90:251-298);
+ *   - pair ids are the 1-based row-wise upper-triangular numbering xy(p,q)
+ *     (TransformIntegralsC.f90:214-221 == IndexMap_tensorR2ToVectorB, IndexMap.f90:249-265).
+ *
+ * Every function returns 0 on success, non-zero on error; lowdin_it_last_error()
+ * gives the message (the Fortran shim raises Exception ERROR with it, mirroring
+ * TransformIntegralsC.f90:2030-2044).  All pointers are HOST pointers unless named d_*.
+ * The library has no CPU fallback: with no usable CUDA device every call fails.
+ */
+#ifndef LOWDIN_IT_H
+#define LOWDIN_IT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lowdin_it_ctx *lowdin_it_handle;
+
+/* Output convention of a transform. */
+#define LOWDIN_IT_CONV_C 0 /* transformer C: quads (p,q,r,s), `symmetric` skip rule  (TransformIntegralsC.f90:345-442) */
+#define LOWDIN_IT_CONV_E 1 /* transformer E: pair ids (ij,kl), j<=i, l<=k, half-drop (TransformIntegralsE.f90:1043-1260) */
+
+/* Synthetic AO generators (benchmark inputs). */
+#define LOWDIN_IT_GEN_HASH 1 /* value = 2u-1, u = (splitmix64(seed ^ key) >> 11) * 2^-53 */
+
+/* ---- lifetime --------------------------------------------------------------------- */
+/* Replaces the per-call malloc/free of IntTransfD.cpp:131-143: device buffers live in the handle. */
+int lowdin_it_create(int device, lowdin_it_handle *out);
+int lowdin_it_destroy(lowdin_it_handle h);
+const char *lowdin_it_last_error(lowdin_it_handle h); /* h may be NULL: last create() error */
+
+/* ---- inputs ----------------------------------------------------------------------- */
+/* Coefficients of one species into slot (0..7).  Replaces the coeff(nao,nao) copy +
+ * c_loc(coeff) hand-off of TransformIntegralsD.f90:189-196, :211-214. */
+int lowdin_it_set_species(lowdin_it_handle h, int slot, int nao, const double *C_colmajor, int ldc, int ncols);
+
+/* AO integrals of one species pair, pushed in the reference's stack layout.  Replaces the
+ * loaders TransformIntegralsC.f90:231-298 (intra), :852-972 (inter) and
+ * ReadIntegrals.f90:23-99.  slotB == slotA means intra-species.  `swapped` != 0 restates the
+ * reversed-pair branch TransformIntegralsC.f90:906-972: the stacks are (B B|A A). */
+int lowdin_it_ao_begin(lowdin_it_handle h, int slotA, int slotB, int swapped);
+int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int32_t *r,
+                             const int32_t *s, const double *v, int64_t n);
+int lowdin_it_ao_end(lowdin_it_handle h);
+/* Instead of an upload: slabs generated on the device on the fly (no N^4/8 array). */
+int lowdin_it_ao_set_generator(lowdin_it_handle h, int slotA, int slotB, int kind, uint64_t seed);
+
+/* ---- the transform ---------------------------------------------------------------- */
+/* One species (slotB==slotA) or species pair.  Replaces
+ * TransformIntegralsC_atomicToMolecularOfOneSpecie / OfTwoSpecies (TransformIntegralsC.f90:141, :728)
+ * and the E versions (TransformIntegralsE.f90:153, :1285) up to, not including, the file write.
+ * conv selects whose semantics are reproduced; `symmetric` is C's flag (ignored for E);
+ * drop_tol is the reference's 1e-10 (C.f90:418, E.f90:1113, :1242). */
+int lowdin_it_transform(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv, int symmetric,
+                        double drop_tol);
+int lowdin_it_result_count(lowdin_it_handle h, int64_t *count);
+/* E record content (TransformIntegralsE.f90:1244-1250): pair ids + value, reference loop order. */
+int lowdin_it_download_pairs(lowdin_it_handle h, int64_t *ij, int64_t *kl, double *v);
+/* C record content (TransformIntegralsC.f90:420-425): p,q,r,s + value, p,q,r,s loop order. */
+int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t *r, int32_t *s, double *v);
+
+/* Large-N streaming form: same transform, executed one occupied batch at a time
+ * (occ_batch values of the FIRST contracted index per pass, 0 = library picks from free HBM),
+ * results consumed on the device instead of being stored: sums[0]=count(|x|>tol),
+ * sums[1]=sum x, sums[2]=sum x^2, sums[3]=MP2-like pair energy sum_x x(lambda x - x_exch)/den
+ * when eps (host, length nao of species A then B) is given, else 0.
+ * first_pass/n_passes select a sub-range of the occupied batches (n_passes<=0: all). */
+int lowdin_it_transform_stream(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv,
+                               double drop_tol, int occ_batch, int first_pass, int n_passes,
+                               const double *epsA, const double *epsB, double lambda, double sums[4]);
+int lowdin_it_stream_num_passes(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv,
+                                int occ_batch, int *n_passes, int *occ_batch_used);
+
+/* ---- transformer-D compatible entry points ---------------------------------------- */
+/* Same arguments and in-place semantics as c_integrals_transform_all /
+ * c_integrals_transform_inter_all (IntTransfD.h:66-68, IntTransfD.cpp:125-181, :245-323):
+ * full transform of the lower-triangular 0-based packed tensor ERIS[ij(ij+1)/2+kl]
+ * (inter: ERIS[ij*om+kl]), but returning a status and using 64-bit sizes. */
+int lowdin_it_transform_all(const double *coeff, double *ints, int nao);
+int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, double *ints, int nao, int onao);
+
+/* ---- multi-GPU (one process per GPU; first half sharded over AO pair slabs,
+ *      NCCL all-to-all, second half sharded over MO pairs) ----------------------------- */
+int lowdin_it_comm_unique_id(char id[128]);
+int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]);
+
+/* ---- instrumentation -------------------------------------------------------------- */
+/* out[0]=AO upload+scatter, [1]=first half, [2]=exchange, [3]=second half, [4]=compaction/consume,
+ * [5]=download, [6]=algorithmic flops of the last transform, [7]=kernels launched by it.
+ * Times in seconds (CUDA events on the library's stream). */
+int lowdin_it_timers(lowdin_it_handle h, double out[8]);
+/* Stand-alone kernel entry points used by tests and bench.py to time one kernel on device
+ * buffers owned by the handle. kind: 0 = slab expansion, 1 = DGEMM (DMMA) m x n x k. */
+int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, int64_t k, int iters,
+                           double *ms_per_launch, double *check);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOWDIN_IT_H */

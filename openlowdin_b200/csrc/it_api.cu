@@ -1,0 +1,882 @@
+// it_api.cu -- C ABI (include/lowdin_it.h) of the B200 four-index AO->MO transformation.
+//
+// Host-side orchestration only: buffer management, the two-half plan, occupied batching,
+// kernel launches on one CUDA stream, result download.  The arithmetic lives in it_kernels.cuh.
+// Reference path being replaced: src/integralsTransformation/TransformIntegralsE.f90:821-1277,
+// :1285-1837 (two-half), TransformIntegralsC.f90:141-471, :728-1168 (window/skip semantics),
+// IntTransfD.cpp:125-181, :245-323 (full in-place transform behind the same style of C ABI).
+#include "it_kernels.cuh"
+#include "../../include/lowdin_it.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lowdin;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Species {
+  int n = 0, ncols = 0;
+  int64_t M = 0, ldc = 0;
+  DevBuf C, pi, pj;
+};
+
+struct AoSet {
+  bool valid = false;
+  AoSource src{};
+  DevBuf data;
+};
+
+// NCCL, resolved lazily so that single-GPU use has no link-time dependency on it.
+struct Id128 { char b[128]; };  // ncclUniqueId is passed by value (128 bytes)
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string &err) {
+  if (g_nccl.lib) return true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) { err = "NCCL not found (dlopen libnccl.so.2)"; return false; }
+#define NSYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+  NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank") NSYM(CommDestroy, "ncclCommDestroy")
+  NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv")
+  NSYM(GetErrorString, "ncclGetErrorString")
+#undef NSYM
+  g_nccl.lib = lib;
+  return true;
+}
+
+}  // namespace
+
+struct lowdin_it_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  Species sp[8];
+  AoSet ao[8][8];
+  // AO upload state
+  int up_a = -1, up_b = -1, up_swapped = 0;
+  DevBuf st_p, st_q, st_r, st_s, st_v;
+  // workspaces
+  DevBuf X, T1t, H, H2, OUT, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp;
+  // results of the last lowdin_it_transform
+  DevBuf r_i0, r_i1, r_i2, r_i3, r_v;
+  int64_t count = 0;
+  int res_conv = -1;
+  double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double launches = 0;
+  cudaEvent_t ev[6] = {};
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;
+  size_t workspace_bytes = (size_t)512 << 20;  // target size of the X / T1t batch buffers
+};
+
+namespace {
+
+int fail(lowdin_it_handle h, const std::string &msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return 1;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(h, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+inline int64_t npairs(int64_t n) { return n * (n + 1) / 2; }
+inline int64_t roundup2(int64_t x) { return (x + 1) & ~int64_t(1); }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- GEMM dispatch ----------------------------------------------------------------------------
+template <int BM, int BN, int WM, int WN, class Epi>
+cudaError_t launch_gemm_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
+  constexpr int ST = 3;
+  constexpr size_t smem = (size_t)ST * (BM + BN) * 20 * sizeof(double);
+  auto kern = dgemm_tn_kernel<BM, BN, WM, WN, ST, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), 1);
+  kern<<<grid, WM * WN * 32, smem, h->stream>>>(g, epi);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+template <class Epi>
+cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  const int n = g.N;
+  if (n <= 8) return launch_gemm_cfg<256, 8, 8, 1>(h, g, epi);
+  if (n <= 16) return launch_gemm_cfg<256, 16, 8, 1>(h, g, epi);
+  if (n <= 32) return launch_gemm_cfg<256, 32, 8, 1>(h, g, epi);
+  if (n <= 64) return launch_gemm_cfg<128, 64, 4, 2>(h, g, epi);
+  // pick the N tile with the least padding (ties -> the larger tile)
+  const int64_t p128 = ceil_div(n, 128) * 128, p80 = ceil_div(n, 80) * 80, p64 = ceil_div(n, 64) * 64;
+  if (p128 <= p80 && p128 <= p64) return launch_gemm_cfg<128, 128, 2, 4>(h, g, epi);
+  if (p80 <= p64) return launch_gemm_cfg<128, 80, 4, 2>(h, g, epi);
+  return launch_gemm_cfg<128, 64, 4, 2>(h, g, epi);
+}
+
+// ---- plan -------------------------------------------------------------------------------------
+struct Half {
+  int nc = 0;                 // basis size of the species contracted in this half
+  const double *C = nullptr;  // device coefficients, column-major, ldc
+  int64_t ldc = 0;
+  int lf = 1, nf = 0;         // first-contracted window (1-based start, count)
+  int ls = 1, ns = 0;         // second-contracted window
+  bool first_is_conv_second = true;  // first-contracted == the convention's second-listed index (q / s)
+};
+
+struct Plan {
+  int a = 0, b = 0, conv = 0, symmetric = 0;
+  bool intra = true;
+  int win[8];
+  Half h1, h2;
+  int64_t nslabs1 = 0;     // slabs of the first half (M of the non-contracted species)
+  AoSource src{};
+  std::vector<int> pairs_s, pairs_f;  // all needed first pairs in convention order: window-relative (second, first) indices
+  std::vector<int> pairs_a, pairs_b;  // orbital numbers in convention order ((i,j) or (p,q))
+};
+
+struct PassTables {
+  int f0 = 0, nfb = 0, nslots = 0;
+  std::vector<int32_t> table, sa, sb, ss, sf;
+};
+
+int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int symmetric, Plan &pl) {
+  if (a < 0 || a > 7 || b < 0 || b > 7) return fail(h, "species slot out of range");
+  if (!h->sp[a].n || !h->sp[b].n) return fail(h, "species not set");
+  if (!h->ao[a][b].valid) return fail(h, "AO integrals for this species pair were not uploaded");
+  if (conv != LOWDIN_IT_CONV_C && conv != LOWDIN_IT_CONV_E) return fail(h, "unknown output convention");
+  pl.a = a; pl.b = b; pl.conv = conv; pl.symmetric = symmetric; pl.intra = (a == b);
+  memcpy(pl.win, win, sizeof(int) * 8);
+  const Species &A = h->sp[a], &B = h->sp[b];
+  const int lim[4] = {A.ncols, A.ncols, B.ncols, B.ncols};
+  for (int w = 0; w < 4; ++w) {
+    if (win[2 * w] < 1) return fail(h, "window lower bound < 1");
+    if (win[2 * w + 1] > lim[w]) return fail(h, "window upper bound exceeds the number of orbitals");
+  }
+  auto cnt = [&](int w) { return std::max(0, win[2 * w + 1] - win[2 * w] + 1); };
+  // first pair (p|i , q|j) on species a; second pair (r|k , s|l) on species b.
+  // The smaller window is contracted first (ties: the convention's second index, as in E.f90:1081).
+  auto setup = [&](Half &hf, const Species &S, int w_first_listed, int w_second_listed) {
+    hf.nc = S.n; hf.C = S.C.as<double>(); hf.ldc = S.ldc;
+    const int n1 = cnt(w_first_listed), n2 = cnt(w_second_listed);
+    hf.first_is_conv_second = (n2 <= n1);
+    const int wf = hf.first_is_conv_second ? w_second_listed : w_first_listed;
+    const int ws = hf.first_is_conv_second ? w_first_listed : w_second_listed;
+    hf.lf = win[2 * wf]; hf.nf = cnt(wf); hf.ls = win[2 * ws]; hf.ns = cnt(ws);
+  };
+  setup(pl.h1, A, 0, 1);
+  setup(pl.h2, B, 2, 3);
+  pl.nslabs1 = B.M;
+  pl.src = h->ao[a][b].src;
+  // needed first pairs, convention order
+  pl.pairs_s.clear(); pl.pairs_f.clear(); pl.pairs_a.clear(); pl.pairs_b.clear();
+  for (int x = win[0]; x <= win[1]; ++x)
+    for (int y = win[2]; y <= win[3]; ++y) {
+      bool keep = (conv == LOWDIN_IT_CONV_E) ? (y <= x) : !(symmetric && y < x);
+      if (!keep) continue;
+      pl.pairs_a.push_back(x); pl.pairs_b.push_back(y);
+      if (pl.h1.first_is_conv_second) { pl.pairs_s.push_back(x - win[0]); pl.pairs_f.push_back(y - win[2]); }
+      else { pl.pairs_s.push_back(y - win[2]); pl.pairs_f.push_back(x - win[0]); }
+    }
+  return 0;
+}
+
+void build_pass(const Plan &pl, int f0, int nfb, PassTables &pt) {
+  pt.f0 = f0; pt.nfb = nfb;
+  pt.table.assign((size_t)pl.h1.ns * nfb, -1);
+  pt.sa.clear(); pt.sb.clear(); pt.ss.clear(); pt.sf.clear();
+  int slot = 0;
+  for (size_t k = 0; k < pl.pairs_s.size(); ++k) {
+    int f = pl.pairs_f[k] - f0;
+    if (f < 0 || f >= nfb) continue;
+    pt.table[(size_t)pl.pairs_s[k] * nfb + f] = slot++;
+    pt.sa.push_back(pl.pairs_a[k]); pt.sb.push_back(pl.pairs_b[k]);
+    pt.ss.push_back(pl.pairs_s[k]); pt.sf.push_back(f);
+  }
+  pt.nslots = slot;
+}
+
+int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
+  CK(buf.ensure(std::max<size_t>(v.size(), 1) * sizeof(int32_t)));
+  if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+// One half-transformation over `count` slabs starting at slab0 of `src`, batched.
+//   q_first: out = T1t ; q_second epilogue supplied by the caller through a functor factory.
+template <class MakeEpi>
+int run_half(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t count, const Half &hf, int f0, int nfb,
+             MakeEpi make_epi) {
+  const int nc = hf.nc;
+  const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
+  const size_t per_slab = std::max((size_t)nc * ldx, (size_t)nfb * ldt) * sizeof(double);
+  int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
+  B = std::min<int64_t>(B, count);
+  B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / nc)));  // gridDim.y limit of the stacked GEMM
+  B = std::min<int64_t>(B, 65535);                                                 // gridDim.y limit of the expansion
+  CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
+  for (int64_t s = 0; s < count; s += B) {
+    const int64_t bc = std::min<int64_t>(B, count - s);
+    {  // unpack (E.f90:1047-1063)
+      dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)bc);
+      if (bc > 65535) return fail(h, "slab batch exceeds gridDim.y");
+      expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, slab0 + s, nc, (int)ldx, h->X.as<double>());
+      h->launches += 1;
+      CK(cudaGetLastError());
+    }
+    {  // first quarter of this half (E.f90:1081-1090): T1t[z][f][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
+      GemmArgs g{h->X.as<double>(), hf.C + (int64_t)(hf.lf - 1 + f0) * hf.ldc, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
+      EpiQ1 epi{h->T1t.as<double>(), nc, nfb, ldt};
+      CK(launch_gemm(h, g, epi));
+    }
+    {  // second quarter (E.f90:1099-1110): T2[s][(z,f)] = sum_mu C(mu, ls+s) T1t[z][f][mu]
+      GemmArgs g{hf.C + (int64_t)(hf.ls - 1) * hf.ldc, h->T1t.as<double>(), hf.ns, (int)(bc * nfb), nc, hf.ldc, ldt, 0, 0};
+      CK(launch_gemm(h, g, make_epi(s, bc)));
+    }
+  }
+  return 0;
+}
+
+struct Consumer {
+  int mode = 0;  // 0: compaction (download), 1: streaming reduce
+  double tol = 1e-10;
+  const double *epsA = nullptr, *epsB = nullptr;  // device
+  double lambda = 2.0;
+};
+
+int exchange_h(lowdin_it_handle h, int nslots, int64_t ncols_local, int64_t ncols_total, const double **src_out, int64_t *ld_out,
+               int *slot_lo, int *slot_hi);
+
+int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass, int n_passes, const Consumer &cons,
+               double sums_out[4]) {
+  const Half &h1 = pl.h1, &h2 = pl.h2;
+  const int nf_total = h1.nf;
+  if (occ_batch <= 0 || occ_batch > nf_total) occ_batch = std::max(nf_total, 1);
+  const int total_passes = (int)ceil_div(std::max(nf_total, 1), occ_batch);
+  if (n_passes <= 0) { first_pass = 0; n_passes = total_passes; }
+  if (first_pass < 0 || first_pass + n_passes > total_passes) return fail(h, "pass range out of bounds");
+  for (int t = 0; t < 8; ++t) h->timers[t] = (t == 0 || t == 5) ? h->timers[t] : 0.0;
+  h->launches = 0;
+  if (cons.mode == 1) {
+    CK(h->sums.ensure(4 * sizeof(double)));
+    CK(cudaMemsetAsync(h->sums.p, 0, 4 * sizeof(double), h->stream));
+  }
+  h->count = 0;
+  double flops = 0.0;
+  // first-half slab range of this rank (contiguous blocks of equal width)
+  const int64_t wblk = ceil_div(pl.nslabs1, h->nranks);
+  const int64_t slab_lo = std::min<int64_t>(pl.nslabs1, wblk * h->rank), slab_hi = std::min<int64_t>(pl.nslabs1, slab_lo + wblk);
+  const int64_t nloc = slab_hi - slab_lo;
+
+  for (int pass = first_pass; pass < first_pass + n_passes; ++pass) {
+    PassTables pt;
+    const int f0 = pass * occ_batch, nfb = std::min(occ_batch, nf_total - f0);
+    if (nfb <= 0) continue;
+    build_pass(pl, f0, nfb, pt);
+    if (pt.nslots == 0) continue;
+    if (upload_i32(h, h->tab, pt.table) || upload_i32(h, h->sa, pt.sa) || upload_i32(h, h->sb, pt.sb) ||
+        upload_i32(h, h->ss, pt.ss) || upload_i32(h, h->sf, pt.sf))
+      return 1;
+    const int64_t ldh = (h->nranks > 1) ? std::max<int64_t>(wblk, 1) : pl.nslabs1;
+    CK(h->H.ensure((size_t)pt.nslots * ldh * sizeof(double)));
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    // ---------------- first half (E.f90:1043-1132), slabs [slab_lo, slab_hi) ----------------
+    {
+      const double half_tol = (pl.conv == LOWDIN_IT_CONV_E) ? cons.tol : -1.0;
+      double *Hp = h->H.as<double>();
+      const int32_t *tab = h->tab.as<int32_t>();
+      auto mk = [&](int64_t s, int64_t) { return EpiScatterH{Hp, ldh, s, tab, nfb, half_tol}; };
+      if (run_half(h, pl.src, slab_lo, nloc, h1, f0, nfb, mk)) return 1;
+      flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)nloc;
+    }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    // ---------------- exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203) -------
+    const double *H2 = h->H.as<double>();
+    int64_t ldh2 = ldh;
+    int slot_lo = 0, slot_hi = pt.nslots;
+    if (h->nranks > 1) {
+      if (exchange_h(h, pt.nslots, nloc, pl.nslabs1, &H2, &ldh2, &slot_lo, &slot_hi)) return 1;
+    }
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    // ---------------- second half (E.f90:1178-1260), slots [slot_lo, slot_hi) -----------------
+    const int nsl = slot_hi - slot_lo;
+    const int64_t per = (int64_t)h2.ns * h2.nf;
+    CK(h->OUT.ensure(std::max<size_t>((size_t)std::max(nsl, 1) * per, 1) * sizeof(double)));
+    if (nsl > 0) {
+      AoSource hsrc{SRC_RECT, H2, pl.nslabs1, ldh2, 0, 0};
+      double *OUT = h->OUT.as<double>();
+      const int ns2 = h2.ns, nf2 = h2.nf;
+      auto mk = [&](int64_t s, int64_t) { return EpiOut{OUT + s * per, ns2, nf2}; };
+      if (run_half(h, hsrc, 0, nsl, h2, 0, h2.nf, mk)) return 1;
+      flops += 2.0 * h2.nc * h2.nf * ((double)h2.nc + h2.ns) * (double)nsl;
+    }
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    // ---------------- consume ------------------------------------------------------------------
+    if (nsl > 0 && cons.mode == 0) {
+      SelectArgs sa{};
+      sa.OUT = h->OUT.as<double>(); sa.slot0 = slot_lo; sa.nslots_batch = nsl; sa.ns2 = h2.ns; sa.nf2 = h2.nf;
+      sa.swap2 = h2.first_is_conv_second ? 0 : 1;
+      sa.n_outer = std::max(0, pl.win[5] - pl.win[4] + 1); sa.n_inner = std::max(0, pl.win[7] - pl.win[6] + 1);
+      sa.lo_outer = pl.win[4]; sa.lo_inner = pl.win[6];
+      sa.conv = pl.conv; sa.symmetric = pl.symmetric; sa.intra = pl.intra ? 1 : 0;
+      sa.slot_a = h->sa.as<int32_t>(); sa.slot_b = h->sb.as<int32_t>();
+      sa.nA = h->sp[pl.a].n; sa.nB = h->sp[pl.b].n; sa.tol = cons.tol;
+      const int64_t ncand = (int64_t)nsl * sa.n_outer * sa.n_inner;
+      const int64_t nblk = ceil_div(ncand, SEL_CHUNK);
+      if (nblk > 0) {
+        if (nblk > 2147483647LL) return fail(h, "too many candidates for one download; use the streaming form");
+        CK(h->blockcount.ensure(nblk * sizeof(unsigned)));
+        CK(h->blockoff.ensure(nblk * sizeof(int64_t)));
+        CK(h->running.ensure(sizeof(unsigned long long)));
+        CK(h->overflow.ensure(sizeof(int)));
+        CK(cudaMemsetAsync(h->running.p, 0, sizeof(unsigned long long), h->stream));
+        CK(cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream));
+        select_count_kernel<<<(unsigned)nblk, SEL_THREADS, 0, h->stream>>>(sa, ncand, h->blockcount.as<unsigned>());
+        select_scan_kernel<<<1, 1024, 0, h->stream>>>(h->blockcount.as<unsigned>(), nblk, h->blockoff.as<int64_t>(),
+                                                      h->running.as<unsigned long long>());
+        h->launches += 2;
+        unsigned long long total = 0;
+        CK(cudaMemcpyAsync(&total, h->running.p, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->count = (int64_t)total;
+        const size_t n = std::max<size_t>(total, 1);
+        EmitArgs ea{};
+        CK(h->r_v.ensure(n * sizeof(double)));
+        ea.o_v = h->r_v.as<double>(); ea.capacity = (int64_t)total; ea.overflow = h->overflow.as<int>();
+        if (pl.conv == LOWDIN_IT_CONV_E) {
+          CK(h->r_i0.ensure(n * sizeof(int64_t))); CK(h->r_i1.ensure(n * sizeof(int64_t)));
+          ea.o_ij = h->r_i0.as<int64_t>(); ea.o_kl = h->r_i1.as<int64_t>();
+        } else {
+          CK(h->r_i0.ensure(n * sizeof(int32_t))); CK(h->r_i1.ensure(n * sizeof(int32_t)));
+          CK(h->r_i2.ensure(n * sizeof(int32_t))); CK(h->r_i3.ensure(n * sizeof(int32_t)));
+          ea.o_p = h->r_i0.as<int32_t>(); ea.o_q = h->r_i1.as<int32_t>(); ea.o_r = h->r_i2.as<int32_t>(); ea.o_s = h->r_i3.as<int32_t>();
+        }
+        select_emit_kernel<<<(unsigned)nblk, SEL_THREADS, 0, h->stream>>>(sa, ncand, h->blockoff.as<int64_t>(), ea);
+        h->launches += 1;
+        CK(cudaGetLastError());
+      }
+      h->res_conv = pl.conv;
+    } else if (nsl > 0) {
+      ReduceArgs ra{};
+      ra.OUT = h->OUT.as<double>(); ra.nslots = nsl; ra.ns2 = h2.ns; ra.nf2 = h2.nf;
+      ra.slot_s = h->ss.as<int32_t>() + slot_lo; ra.slot_f = h->sf.as<int32_t>() + slot_lo;
+      ra.slot_table = h->tab.as<int32_t>(); ra.nfb = nfb;
+      ra.orb_s1 = h1.ls; ra.orb_f1 = h1.lf + f0; ra.orb_s2 = h2.ls; ra.orb_f2 = h2.lf;
+      ra.epsA = cons.epsA; ra.epsB = cons.epsB;
+      ra.exchange = (pl.intra && h->nranks == 1 && h1.ls == h2.ls && h1.ns == h2.ns && h1.lf == h2.lf && h1.nf == h2.nf &&
+                     pl.win[0] == pl.win[4] && pl.win[2] == pl.win[6]) ? 1 : 0;
+      ra.lambda = cons.lambda; ra.tol = cons.tol;
+      reduce_block_kernel<<<148 * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
+      h->launches += 1;
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms;
+    for (int t = 0; t < 4; ++t) { CK(cudaEventElapsedTime(&ms, h->ev[t], h->ev[t + 1])); h->timers[1 + t] += ms * 1e-3; }
+  }
+  if (cons.mode == 1 && sums_out) {
+    CK(cudaMemcpyAsync(sums_out, h->sums.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->timers[6] = flops;
+  h->timers[7] = h->launches;
+  return 0;
+}
+
+// All-to-all of the half-transformed block between the halves.  Every rank holds
+// H[slot][its own AO-pair columns]; afterwards it holds, for its own block of slots, all columns,
+// as nranks column blocks H2[g][slot_local][col_local(g)] laid one after the other, which the
+// second-half unpack reads as a rectangular source with ld = total padded width by first
+// transposing the blocks into place with cudaMemcpy2DAsync.
+int exchange_h(lowdin_it_handle h, int nslots, int64_t ncols_local, int64_t ncols_total, const double **src_out, int64_t *ld_out,
+               int *slot_lo, int *slot_hi) {
+  const int G = h->nranks;
+  const int64_t wblk = ceil_div(ncols_total, G);
+  const int sblk = (int)ceil_div(nslots, G);
+  const int lo = std::min(nslots, sblk * h->rank), hi = std::min(nslots, lo + sblk);
+  *slot_lo = lo; *slot_hi = hi;
+  const int mine = hi - lo;
+  if (!h->comm) return fail(h, "multi-GPU transform without a communicator");
+  // receive staging: for peer g a [mine][wblk] block; final layout [mine][G*wblk]
+  CK(h->dtmp.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
+  CK(h->H2.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
+  int rc = g_nccl.GroupStart();
+  for (int g = 0; g < G && rc == 0; ++g) {
+    const int glo = std::min(nslots, sblk * g), ghi = std::min(nslots, glo + sblk);
+    const size_t send_n = (size_t)(ghi - glo) * wblk;   // rows glo..ghi of H (row stride wblk)
+    const size_t recv_n = (size_t)mine * wblk;
+    if (send_n) rc = g_nccl.Send(h->H.as<double>() + (size_t)glo * wblk, send_n * sizeof(double), /*ncclChar*/ 0, g, h->comm, h->stream);
+    if (rc == 0 && recv_n) rc = g_nccl.Recv(h->dtmp.as<double>() + (size_t)g * mine * wblk, recv_n * sizeof(double), 0, g, h->comm, h->stream);
+  }
+  if (rc == 0) rc = g_nccl.GroupEnd();
+  if (rc != 0) return fail(h, std::string("NCCL all-to-all failed: ") + g_nccl.GetErrorString(rc));
+  for (int g = 0; g < G; ++g)
+    if (mine)
+      CK(cudaMemcpy2DAsync(h->H2.as<double>() + (size_t)g * wblk, (size_t)G * wblk * sizeof(double),
+                           h->dtmp.as<double>() + (size_t)g * mine * wblk, (size_t)wblk * sizeof(double),
+                           (size_t)wblk * sizeof(double), (size_t)mine, cudaMemcpyDeviceToDevice, h->stream));
+  (void)ncols_local;
+  *src_out = h->H2.as<double>();
+  *ld_out = (int64_t)G * wblk;
+  return 0;
+}
+
+lowdin_it_handle g_dcompat = nullptr;  // context behind the transformer-D compatible entry points
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int lowdin_it_create(int device, lowdin_it_handle *out) {
+  lowdin_it_handle h = nullptr;
+  if (!out) return fail(nullptr, "null output handle");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) return fail(nullptr, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  h = new lowdin_it_ctx();
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, "cudaStreamCreate failed"); }
+  for (auto &ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return 0;
+}
+
+int lowdin_it_destroy(lowdin_it_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (auto &s : h->sp) { s.C.release(); s.pi.release(); s.pj.release(); }
+  for (auto &row : h->ao) for (auto &a : row) a.data.release();
+  DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->tab, &h->sa, &h->sb,
+                    &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp,
+                    &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char *lowdin_it_last_error(lowdin_it_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lowdin_it_set_species(lowdin_it_handle h, int slot, int nao, const double *C, int ldc, int ncols) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 7) return fail(h, "species slot out of range");
+  if (nao <= 0 || ncols <= 0 || ldc < nao || !C) return fail(h, "bad coefficient matrix arguments");
+  CK(cudaSetDevice(h->device));
+  Species &S = h->sp[slot];
+  S.n = nao; S.ncols = ncols; S.M = npairs(nao); S.ldc = roundup2(nao);
+  CK(S.C.ensure((size_t)S.ldc * ncols * sizeof(double)));
+  CK(cudaMemsetAsync(S.C.p, 0, (size_t)S.ldc * ncols * sizeof(double), h->stream));
+  CK(cudaMemcpy2DAsync(S.C.p, S.ldc * sizeof(double), C, (size_t)ldc * sizeof(double), (size_t)nao * sizeof(double), ncols,
+                       cudaMemcpyHostToDevice, h->stream));
+  std::vector<int32_t> pi(S.M), pj(S.M);
+  int64_t m = 0;
+  for (int i = 0; i < nao; ++i) for (int j = i; j < nao; ++j) { pi[m] = i; pj[m] = j; ++m; }
+  if (upload_i32(h, S.pi, pi) || upload_i32(h, S.pj, pj)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int o = 0; o < 8; ++o) { h->ao[slot][o].valid = false; h->ao[o][slot].valid = false; }
+  return 0;
+}
+
+int lowdin_it_ao_begin(lowdin_it_handle h, int a, int b, int swapped) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].n || !h->sp[b].n) return fail(h, "ao_begin: species not set");
+  CK(cudaSetDevice(h->device));
+  AoSet &S = h->ao[a][b];
+  const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  const size_t count = (a == b) ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb);
+  CK(S.data.ensure(count * sizeof(double)));
+  CK(cudaMemsetAsync(S.data.p, 0, count * sizeof(double), h->stream));  // C.f90:669-685 zero-initialises
+  S.src = (a == b) ? AoSource{SRC_SYM_PACKED, S.data.as<double>(), Ma, 0, 0, 0} : AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
+  S.valid = false;
+  h->up_a = a; h->up_b = b; h->up_swapped = swapped;
+  CK(cudaEventRecord(h->ev[5], h->stream));
+  h->timers[0] = 0;
+  return 0;
+}
+
+int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s,
+                             const double *v, int64_t n) {
+  if (!h) return 1;
+  if (h->up_a < 0) return fail(h, "ao_push_stacks without ao_begin");
+  int64_t m = 0;
+  while (m < n && p[m] != -1) ++m;  // terminator (C.f90:279-280)
+  if (m == 0) return 0;
+  const int na = h->sp[h->up_a].n, nb = h->sp[h->up_b].n;
+  const int lim_pq = (h->up_a == h->up_b) ? na : (h->up_swapped ? nb : na);
+  const int lim_rs = (h->up_a == h->up_b) ? na : (h->up_swapped ? na : nb);
+  for (int64_t k = 0; k < m; ++k)
+    if (p[k] < 1 || q[k] < 1 || r[k] < 1 || s[k] < 1 || p[k] > lim_pq || q[k] > lim_pq || r[k] > lim_rs || s[k] > lim_rs)
+      return fail(h, "AO stack entry " + std::to_string(k) + " has an index outside the basis");
+  CK(cudaSetDevice(h->device));
+  CK(h->st_p.ensure(m * 4)); CK(h->st_q.ensure(m * 4)); CK(h->st_r.ensure(m * 4)); CK(h->st_s.ensure(m * 4)); CK(h->st_v.ensure(m * 8));
+  CK(cudaMemcpyAsync(h->st_p.p, p, m * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->st_q.p, q, m * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->st_r.p, r, m * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->st_s.p, s, m * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->st_v.p, v, m * 8, cudaMemcpyHostToDevice, h->stream));
+  scatter_stacks_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, h->stream>>>(
+      h->st_p.as<int32_t>(), h->st_q.as<int32_t>(), h->st_r.as<int32_t>(), h->st_s.as<int32_t>(), h->st_v.as<double>(), m,
+      h->up_a == h->up_b, h->up_swapped, na, nb, h->ao[h->up_a][h->up_b].data.as<double>());
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+  return 0;
+}
+
+int lowdin_it_ao_end(lowdin_it_handle h) {
+  if (!h) return 1;
+  if (h->up_a < 0) return fail(h, "ao_end without ao_begin");
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[0]));
+  h->timers[0] = ms * 1e-3;
+  h->ao[h->up_a][h->up_b].valid = true;
+  h->up_a = h->up_b = -1;
+  return 0;
+}
+
+int lowdin_it_ao_set_generator(lowdin_it_handle h, int a, int b, int kind, uint64_t seed) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].n || !h->sp[b].n) return fail(h, "ao_set_generator: species not set");
+  if (kind != LOWDIN_IT_GEN_HASH) return fail(h, "unknown generator kind");
+  AoSet &S = h->ao[a][b];
+  S.data.release();
+  S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed};
+  S.valid = true;
+  return 0;
+}
+
+int lowdin_it_transform(lowdin_it_handle h, int a, int b, const int win[8], int conv, int symmetric, double drop_tol) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  Plan pl;
+  if (build_plan(h, a, b, win, conv, symmetric, pl)) return 1;
+  Consumer cons; cons.mode = 0; cons.tol = drop_tol;
+  if (h->nranks > 1) return fail(h, "lowdin_it_transform is single-GPU; use lowdin_it_transform_stream on a communicator");
+  // download mode keeps the whole dense result block: check that it fits
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const double need = ((double)pl.pairs_s.size() * ((double)pl.nslabs1 + (double)pl.h2.ns * pl.h2.nf)) * 8.0;
+  if (need > 0.9 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap))
+    return fail(h, "result block does not fit in device memory; use lowdin_it_transform_stream");
+  return run_passes(h, pl, 0, 0, 0, cons, nullptr);
+}
+
+int lowdin_it_result_count(lowdin_it_handle h, int64_t *count) {
+  if (!h || !count) return 1;
+  *count = h->count;
+  return 0;
+}
+
+int lowdin_it_download_pairs(lowdin_it_handle h, int64_t *ij, int64_t *kl, double *v) {
+  if (!h) return 1;
+  if (h->res_conv != LOWDIN_IT_CONV_E) return fail(h, "last transform did not use the E (pair id) convention");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (h->count) {
+    CK(cudaMemcpyAsync(ij, h->r_i0.p, h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(kl, h->r_i1.p, h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(v, h->r_v.p, h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timers[5] = ms * 1e-3;
+  int ov = 0; CK(cudaMemcpy(&ov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ov) return fail(h, "result buffer overflow");
+  return 0;
+}
+
+int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t *r, int32_t *s, double *v) {
+  if (!h) return 1;
+  if (h->res_conv != LOWDIN_IT_CONV_C) return fail(h, "last transform did not use the C (quad) convention");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (h->count) {
+    CK(cudaMemcpyAsync(p, h->r_i0.p, h->count * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(q, h->r_i1.p, h->count * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(r, h->r_i2.p, h->count * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(s, h->r_i3.p, h->count * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(v, h->r_v.p, h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timers[5] = ms * 1e-3;
+  return 0;
+}
+
+static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int *used) {
+  int nf = std::max(pl.h1.nf, 1);
+  if (requested > 0) { *used = std::min(requested, nf); return 0; }
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  double avail = 0.85 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->dtmp.cap) -
+                 3.0 * (double)h->workspace_bytes;
+  // bytes per first-window value: slots per value (<= ns1) x (H row + OUT block), H row split over the ranks
+  const double hrow = (double)ceil_div(pl.nslabs1, h->nranks) * (h->nranks > 1 ? 3.0 : 1.0);
+  const double per_f = (double)pl.h1.ns * (hrow + (double)pl.h2.ns * pl.h2.nf / h->nranks) * 8.0;
+  int qb = (int)std::max(1.0, std::min((double)nf, avail / std::max(per_f, 1.0)));
+  if (qb >= 8 && qb < nf) qb &= ~7;  // DMMA n-tile granularity
+  *used = qb;
+  return 0;
+}
+
+int lowdin_it_stream_num_passes(lowdin_it_handle h, int a, int b, const int win[8], int conv, int occ_batch, int *n_passes,
+                                int *occ_batch_used) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  Plan pl;
+  if (build_plan(h, a, b, win, conv, 0, pl)) return 1;
+  int used = 0;
+  if (pick_occ_batch(h, pl, occ_batch, &used)) return 1;
+  if (n_passes) *n_passes = (int)ceil_div(std::max(pl.h1.nf, 1), used);
+  if (occ_batch_used) *occ_batch_used = used;
+  return 0;
+}
+
+int lowdin_it_transform_stream(lowdin_it_handle h, int a, int b, const int win[8], int conv, double drop_tol, int occ_batch,
+                               int first_pass, int n_passes, const double *epsA, const double *epsB, double lambda, double sums[4]) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  Plan pl;
+  if (build_plan(h, a, b, win, conv, 0, pl)) return 1;
+  int used = 0;
+  if (pick_occ_batch(h, pl, occ_batch, &used)) return 1;
+  Consumer cons; cons.mode = 1; cons.tol = drop_tol; cons.lambda = lambda;
+  if (epsA) {
+    const int na = h->sp[a].ncols, nb = h->sp[b].ncols;
+    CK(h->epsA.ensure(na * sizeof(double)));
+    CK(cudaMemcpyAsync(h->epsA.p, epsA, na * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    cons.epsA = h->epsA.as<double>();
+    if (a != b) {
+      if (!epsB) return fail(h, "epsB required for an inter-species energy sum");
+      CK(h->epsB.ensure(nb * sizeof(double)));
+      CK(cudaMemcpyAsync(h->epsB.p, epsB, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      cons.epsB = h->epsB.as<double>();
+    } else cons.epsB = cons.epsA;
+  }
+  return run_passes(h, pl, used, first_pass, n_passes, cons, sums);
+}
+
+int lowdin_it_timers(lowdin_it_handle h, double out[8]) {
+  if (!h || !out) return 1;
+  memcpy(out, h->timers, sizeof(double) * 8);
+  return 0;
+}
+
+// ---- transformer-D compatible entry points --------------------------------------------------
+static int dcompat_ctx() {
+  if (g_dcompat) return 0;
+  return lowdin_it_create(0, &g_dcompat);
+}
+
+int lowdin_it_transform_all(const double *coeff, double *ints, int nao) {
+  if (dcompat_ctx()) return 1;
+  lowdin_it_handle h = g_dcompat;
+  if (!coeff || !ints || nao <= 0) return fail(h, "bad arguments");
+  if (lowdin_it_set_species(h, 0, nao, coeff, nao, nao)) return 1;
+  const int64_t M = npairs(nao), cnt = M * (M + 1) / 2;
+  CK(h->dtmp.ensure(cnt * sizeof(double)));
+  CK(cudaMemcpyAsync(h->dtmp.p, ints, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  AoSet &S = h->ao[0][0];
+  CK(S.data.ensure(cnt * sizeof(double)));
+  repack_d_intra_kernel<<<(unsigned)ceil_div(M * M, 256), 256, 0, h->stream>>>(S.data.as<double>(), h->dtmp.as<double>(),
+                                                                             h->sp[0].pi.as<int32_t>(), h->sp[0].pj.as<int32_t>(), M);
+  CK(cudaGetLastError());
+  S.src = AoSource{SRC_SYM_PACKED, S.data.as<double>(), M, 0, 0, 0};
+  S.valid = true;
+  const int win[8] = {1, nao, 1, nao, 1, nao, 1, nao};
+  // E convention with a negative tolerance keeps every (ij,kl), ij and kl in ijmap/klmap order,
+  // which for the full window is exactly D's lower-triangular pair numbering.
+  if (lowdin_it_transform(h, 0, 0, win, LOWDIN_IT_CONV_E, 0, -1.0)) return 1;
+  if (h->count != M * M) return fail(h, "internal: full transform did not produce M*M values");
+  pack_d_lower_kernel<<<(unsigned)ceil_div(M * M, 256), 256, 0, h->stream>>>(h->r_v.as<double>(), h->dtmp.as<double>(), M);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ints, h->dtmp.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, double *ints, int nao, int onao) {
+  if (dcompat_ctx()) return 1;
+  lowdin_it_handle h = g_dcompat;
+  if (!coeff || !ocoeff || !ints || nao <= 0 || onao <= 0) return fail(h, "bad arguments");
+  if (lowdin_it_set_species(h, 0, nao, coeff, nao, nao)) return 1;
+  if (lowdin_it_set_species(h, 1, onao, ocoeff, onao, onao)) return 1;
+  const int64_t Ma = npairs(nao), Mb = npairs(onao), cnt = Ma * Mb;
+  CK(h->dtmp.ensure(cnt * sizeof(double)));
+  CK(cudaMemcpyAsync(h->dtmp.p, ints, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  AoSet &S = h->ao[0][1];
+  CK(S.data.ensure(cnt * sizeof(double)));
+  repack_d_inter_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, h->stream>>>(S.data.as<double>(), h->dtmp.as<double>(),
+                                                                           h->sp[0].pi.as<int32_t>(), h->sp[0].pj.as<int32_t>(),
+                                                                           h->sp[1].pi.as<int32_t>(), h->sp[1].pj.as<int32_t>(), Ma, Mb);
+  CK(cudaGetLastError());
+  S.src = AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
+  S.valid = true;
+  const int win[8] = {1, nao, 1, nao, 1, onao, 1, onao};
+  if (lowdin_it_transform(h, 0, 1, win, LOWDIN_IT_CONV_E, 0, -1.0)) return 1;
+  if (h->count != cnt) return fail(h, "internal: full inter transform did not produce Ma*Mb values");
+  CK(cudaMemcpyAsync(ints, h->r_v.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------
+int lowdin_it_comm_unique_id(char id[128]) {
+  std::string err;
+  if (!load_nccl(err)) return fail(nullptr, err);
+  int rc = g_nccl.GetUniqueId(id);
+  if (rc) return fail(nullptr, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+  return 0;
+}
+
+int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]) {
+  if (!h) return 1;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, "bad rank / nranks");
+  CK(cudaSetDevice(h->device));
+  if (nranks == 1) { h->rank = 0; h->nranks = 1; return 0; }
+  std::string err;
+  if (!load_nccl(err)) return fail(h, err);
+  Id128 uid; memcpy(uid.b, id, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+  if (rc) return fail(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+  h->rank = rank; h->nranks = nranks;
+  return 0;
+}
+
+// ---- stand-alone kernel timing / debug --------------------------------------------------------
+int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, int64_t k, int iters, double *ms_per_launch, double *check) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0 = h->ev[0], e1 = h->ev[1];
+  float ms = 0;
+  if (kind == 0) {  // slab expansion of n slabs of an m-function hash tensor
+    const int nc = (int)m; const int64_t ldx = roundup2(nc);
+    CK(h->X.ensure((size_t)n * nc * ldx * sizeof(double)));
+    AoSource src{(int)k /* source kind */, nullptr, npairs(nc), npairs(nc), npairs(nc), 12345};
+    if (src.kind == SRC_SYM_PACKED || src.kind == SRC_RECT) {
+      const int64_t M = npairs(nc);
+      const size_t cnt = (src.kind == SRC_SYM_PACKED) ? (size_t)(M * (M + 1) / 2) : (size_t)(n * M);
+      CK(h->H.ensure(cnt * sizeof(double)));
+      CK(cudaMemsetAsync(h->H.p, 0, cnt * sizeof(double), h->stream));
+      src.data = h->H.as<double>();
+    }
+    dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)n);
+    expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, 0, nc, (int)ldx, h->X.as<double>());
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < iters; ++i) expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, 0, nc, (int)ldx, h->X.as<double>());
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (check) CK(cudaMemcpy(check, h->X.p, sizeof(double), cudaMemcpyDeviceToHost));
+  } else {  // DGEMM m x n x k on generated operands
+    const int64_t lda = roundup2(k);
+    CK(h->X.ensure((size_t)m * lda * sizeof(double)));
+    CK(h->T1t.ensure((size_t)n * lda * sizeof(double)));
+    CK(h->OUT.ensure((size_t)m * n * sizeof(double)));
+    CK(cudaMemsetAsync(h->X.p, 0x3f, (size_t)m * lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->T1t.p, 0x3f, (size_t)n * lda * sizeof(double), h->stream));
+    GemmArgs g{h->X.as<double>(), h->T1t.as<double>(), (int)m, (int)n, (int)k, lda, lda, 0, 0};
+    EpiPlain epi{h->OUT.as<double>(), n, 0};
+    CK(launch_gemm(h, g, epi));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < iters; ++i) CK(launch_gemm(h, g, epi));
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (check) CK(cudaMemcpy(check, h->OUT.p, sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (ms_per_launch) *ms_per_launch = ms / iters;
+  return 0;
+}
+
+// C[m][n] = sum_k A[m][k] B[n][k] on host arrays (row-major, K contiguous): parity tests of the DMMA kernel alone.
+int lowdin_it_debug_gemm(lowdin_it_handle h, const double *A, const double *B, double *C, int m, int n, int k) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  const int64_t ld = roundup2(k);
+  CK(h->X.ensure((size_t)m * ld * sizeof(double)));
+  CK(h->T1t.ensure((size_t)n * ld * sizeof(double)));
+  CK(h->OUT.ensure((size_t)m * n * sizeof(double)));
+  CK(cudaMemcpy2DAsync(h->X.p, ld * 8, A, (size_t)k * 8, (size_t)k * 8, m, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->T1t.p, ld * 8, B, (size_t)k * 8, (size_t)k * 8, n, cudaMemcpyHostToDevice, h->stream));
+  GemmArgs g{h->X.as<double>(), h->T1t.as<double>(), m, n, k, ld, ld, 0, 0};
+  EpiPlain epi{h->OUT.as<double>(), n, 0};
+  CK(launch_gemm(h, g, epi));
+  CK(cudaMemcpyAsync(C, h->OUT.p, (size_t)m * n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Dense N x N expansion of `nb` slabs starting at slab0 of the (a,b) AO set, to host X[nb][n][n].
+int lowdin_it_debug_expand(lowdin_it_handle h, int a, int b, int64_t slab0, int nb, double *X) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->ao[a][b].valid) return fail(h, "debug_expand: AO set not available");
+  CK(cudaSetDevice(h->device));
+  const int nc = h->sp[a].n; const int64_t ldx = roundup2(nc);
+  CK(h->X.ensure((size_t)nb * nc * ldx * sizeof(double)));
+  dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)nb);
+  expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(h->ao[a][b].src, slab0, nc, (int)ldx, h->X.as<double>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(X, (size_t)nc * 8, h->X.p, ldx * 8, (size_t)nc * 8, (size_t)nb * nc, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

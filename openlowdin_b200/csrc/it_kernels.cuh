@@ -1,0 +1,483 @@
+// it_kernels.cuh -- sm_100a device kernels of the four-index AO->MO transformation.
+//
+//   expand_slabs_kernel   packed / rectangular / generated AO slab  ->  dense symmetric N x N
+//                         (the "unpack" of TransformIntegralsE.f90:1047-1063, :1623-1630; HBM bound)
+//   dgemm_tn_kernel       C[m][n] = sum_k A[m][k] B[n][k]   FP64 tensor cores (DMMA.8x8x4 via
+//                         mma.sync.m8n8k4.f64), cp.async multi-stage shared-memory pipeline,
+//                         fused epilogues (plain / transposed / window-pair scatter + 1e-10 drop)
+//                         = the four quarter transforms (E.f90:1081-1110, :1213-1239)
+//   compaction kernels    dense MO block -> (ij,kl,v) / (p,q,r,s,v) lists, |v| > 1e-10, in the
+//                         reference's loop order (E.f90:1242-1257, C.f90:418-440)
+//   reduce_block_kernel   streaming consumer: count / sum / sum^2 / MP2-like pair energy
+//
+// Blackwell has no FP64 kind of tcgen05.mma: FP64 tensor throughput is reached through the
+// warp-level DMMA only (every mma.sync f64 shape lowers to DMMA.8x8x4 on sm_100a), so this
+// is a shared-memory-fed mma.sync kernel, not a TMEM kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lowdin {
+
+// ---------------------------------------------------------------------------------------------
+// AO sources
+// ---------------------------------------------------------------------------------------------
+enum SrcKind : int {
+  SRC_SYM_PACKED = 0,  // intra, C/E layout: row lo holds hi = lo..M-1 at lo*M - lo(lo+1)/2 + hi  (C.f90:223-226, :267-271)
+  SRC_RECT = 1,        // data[slab*ld + pair]   (inter AO storage (rs-1)*M_a+pq, C.f90:882; and the half-transformed H)
+  SRC_HASH_SYM = 2,    // generated, key = hi*M + lo
+  SRC_HASH_RECT = 3    // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
+};
+
+struct AoSource {
+  int kind;
+  const double *data;
+  int64_t M;    // pairs per slab vector
+  int64_t ld;   // SRC_RECT row stride
+  int64_t aux;  // SRC_HASH_RECT: number of slabs (M_b)
+  uint64_t seed;
+};
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ double hash_value(uint64_t seed, uint64_t key) {
+  return 2.0 * ((double)(splitmix64(seed ^ key) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+
+__device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, int64_t pair) {
+  switch (src.kind) {
+    case SRC_SYM_PACKED: {
+      int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
+      return __ldg(src.data + (lo * src.M - (lo * (lo + 1)) / 2 + hi));
+    }
+    case SRC_RECT:
+      return __ldg(src.data + (slab * src.ld + pair));
+    case SRC_HASH_SYM: {
+      int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
+      return hash_value(src.seed, (uint64_t)(hi * src.M + lo));
+    }
+    default:
+      return hash_value(src.seed, (uint64_t)(pair * src.aux + slab));
+  }
+}
+
+// 0-based row-wise upper-triangular pair id (== xy(p,q)-1, C.f90:214-221)
+__host__ __device__ __forceinline__ int64_t pair0(int64_t i, int64_t j, int64_t n) {
+  if (i > j) { int64_t t = i; i = j; j = t; }
+  return i * n - (i * (i - 1)) / 2 + (j - i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab expansion: X[b][mu][nu] = AO(slab_list[b] or slab0+b ; pair(mu,nu)),   ldx >= n
+// One thread per two adjacent nu (16-byte stores).  grid = (ceil(n*ldx/2 / 256), B)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expand_slabs_kernel(AoSource src, int64_t slab0, int n, int ldx, double *__restrict__ X) {
+  const int64_t b = blockIdx.y;
+  const int64_t slab = slab0 + b;
+  const int half = ldx >> 1;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * half) return;
+  const int mu = (int)(e / half);
+  const int nu = (int)(e % half) * 2;
+  double2 v;
+  v.x = (nu < n) ? ao_value(src, slab, pair0(mu, nu, n)) : 0.0;
+  v.y = (nu + 1 < n) ? ao_value(src, slab, pair0(mu, nu + 1, n)) : 0.0;
+  *reinterpret_cast<double2 *>(X + ((b * n + mu) * (int64_t)ldx + nu)) = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AO list scatter (C.f90:262-273 intra; :879-883 / :947-951 inter)
+// ---------------------------------------------------------------------------------------------
+__global__ void scatter_stacks_kernel(const int32_t *__restrict__ p, const int32_t *__restrict__ q,
+                                      const int32_t *__restrict__ r, const int32_t *__restrict__ s,
+                                      const double *__restrict__ v, int64_t n, int intra, int swapped, int na, int nb,
+                                      double *__restrict__ dst) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t Ma = (int64_t)na * (na + 1) / 2;
+  if (intra) {
+    int64_t pq = pair0(p[k] - 1, q[k] - 1, na), rs = pair0(r[k] - 1, s[k] - 1, na);
+    int64_t lo = pq < rs ? pq : rs, hi = pq < rs ? rs : pq;
+    dst[lo * Ma - (lo * (lo + 1)) / 2 + hi] = v[k];
+  } else if (!swapped) {
+    int64_t pq = pair0(p[k] - 1, q[k] - 1, na), rs = pair0(r[k] - 1, s[k] - 1, nb);
+    dst[rs * Ma + pq] = v[k];
+  } else {
+    int64_t pq = pair0(p[k] - 1, q[k] - 1, nb), rs = pair0(r[k] - 1, s[k] - 1, na);
+    dst[pq * Ma + rs] = v[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DGEMM on the FP64 tensor cores
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+struct GemmArgs {
+  const double *A;  // [M][K] row-major, lda   (K contiguous)
+  const double *B;  // [N][K] row-major, ldb   (K contiguous)
+  int M, N, K;
+  int64_t lda, ldb;
+  int64_t strideA, strideB;  // per blockIdx.z
+};
+
+// Epilogues -----------------------------------------------------------------------------------
+struct EpiPlain {  // C[z][m][n]
+  double *C; int64_t ldc, strideC;
+  __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { C[z * strideC + (int64_t)m * ldc + n] = v; }
+};
+// First quarter: m = (z, mu) over the stacked slabs of a batch, n = if (first-contracted window)
+//   T1t[z][if][mu]  (mu contiguous so the second quarter reads K-contiguous rows)
+struct EpiQ1 {
+  double *T1t; int nc; int nf; int64_t ldt;
+  __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
+    int zz = m / nc, mu = m - zz * nc;
+    T1t[((int64_t)zz * nf + n) * ldt + mu] = v;
+  }
+};
+// Second quarter of a first half: m = is (second-contracted window), n = (z, if).
+// T2 -> H[slot(is,if)][s0+z], keeping only window pairs (slot >= 0) and, for transformer E
+// semantics, zeroing |t| <= tol (E.f90:1113).  tol < 0 keeps everything.
+struct EpiScatterH {
+  double *H; int64_t ldh; int64_t col0; const int32_t *slot; int nf; double tol;
+  __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
+    int zz = n / nf, jf = n - zz * nf;
+    int sl = __ldg(slot + (int64_t)m * nf + jf);
+    if (sl >= 0) H[(int64_t)sl * ldh + col0 + zz] = (fabs(v) > tol) ? v : 0.0;
+  }
+};
+// Fourth quarter: m = ks, n = (z, kf)  ->  OUT[slot0+z][ks][kf]
+struct EpiOut {
+  double *OUT; int ns2, nf2;
+  __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
+    int zz = n / nf2, kf = n - zz * nf2;
+    OUT[((int64_t)zz * ns2 + m) * nf2 + kf] = v;
+  }
+};
+
+template <int BM, int BN, int WM, int WN, int STAGES, class Epi>
+__global__ void __launch_bounds__(WM *WN * 32) dgemm_tn_kernel(GemmArgs g, Epi epi) {
+  constexpr int BK = 16;        // doubles per k-tile
+  constexpr int LDS = BK + 4;   // padded smem row: 160 B -> conflict-free 64-bit fragment loads
+  constexpr int NT = WM * WN * 32;
+  constexpr int TM = BM / WM / 8, TN = BN / WN / 8;
+  static_assert(BM % (WM * 8) == 0 && BN % (WN * 8) == 0, "tile/warp mismatch");
+  extern __shared__ __align__(16) double smem[];
+  double *As = smem;                        // [STAGES][BM][LDS]
+  double *Bs = smem + STAGES * BM * LDS;    // [STAGES][BN][LDS]
+
+  const int z = blockIdx.z;
+  const double *__restrict__ A = g.A + z * g.strideA;
+  const double *__restrict__ B = g.B + z * g.strideB;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WN, wn = warp % WN;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int KT = (g.K + BK - 1) / BK;
+
+  auto load_tile = [&](int stage, int kt) {
+    const int k0 = kt * BK;
+    double *as = As + stage * BM * LDS, *bs = Bs + stage * BN * LDS;
+#pragma unroll
+    for (int c = tid; c < BM * (BK / 2); c += NT) {
+      int row = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+      int gm = m0 + row, gk = k0 + kc;
+      int valid = (gm < g.M) ? min(max(g.K - gk, 0), 2) : 0;
+      const double *src = A + (int64_t)(gm < g.M ? gm : 0) * g.lda + (valid ? gk : 0);
+      cp_async16(as + row * LDS + kc, src, valid * 8);
+    }
+#pragma unroll
+    for (int c = tid; c < BN * (BK / 2); c += NT) {
+      int row = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+      int gn = n0 + row, gk = k0 + kc;
+      int valid = (gn < g.N) ? min(max(g.K - gk, 0), 2) : 0;
+      const double *src = B + (int64_t)(gn < g.N ? gn : 0) * g.ldb + (valid ? gk : 0);
+      cp_async16(bs + row * LDS + kc, src, valid * 8);
+    }
+  };
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + STAGES - 1;
+      if (nk < KT) load_tile(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const double *as = As + (kt % STAGES) * BM * LDS + (wm * TM * 8 + grp) * LDS + tig;
+    const double *bs = Bs + (kt % STAGES) * BN * LDS + (wn * TN * 8 + grp) * LDS + tig;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = as[i * 8 * LDS + kk];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = bs[j * 8 * LDS + kk];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + wm * TM * 8 + i * 8 + grp;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
+      if (n < g.N) epi(z, m, n, acc[i][j][0]);
+      if (n + 1 < g.N) epi(z, m, n + 1, acc[i][j][1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Result selection / compaction.  Candidates are enumerated in the reference's loop order:
+// slot (the (i,j) or (p,q) pair, ijmap order), then the outer index of the second pair, then the inner.
+// ---------------------------------------------------------------------------------------------
+struct SelectArgs {
+  const double *OUT;    // [nslots_batch][ns2][nf2]
+  int64_t slot0;        // first slot of this batch
+  int nslots_batch;
+  int ns2, nf2;         // extents of OUT's two trailing dims (second-contracted, first-contracted window)
+  int swap2;            // 0: outer loop index of the convention == OUT's ns2 dim; 1: == nf2 dim
+  int n_outer, n_inner; // convention loop extents for the second pair (outer, inner)
+  int lo_outer, lo_inner;   // first orbital number of the outer / inner loop (1-based)
+  int conv;             // LOWDIN_IT_CONV_*
+  int symmetric, intra;
+  const int32_t *slot_a, *slot_b;   // orbital numbers of the first pair per slot: E: (i,j)  C: (p,q)
+  int nA, nB;           // basis sizes for pair ids
+  double tol;
+};
+
+__device__ __forceinline__ bool select_candidate(const SelectArgs &a, int64_t c, double &v, int &slot, int &o, int &in) {
+  const int64_t per = (int64_t)a.n_outer * a.n_inner;
+  slot = (int)(c / per);
+  const int rem = (int)(c % per);
+  o = rem / a.n_inner + a.lo_outer;
+  in = rem % a.n_inner + a.lo_inner;
+  const int64_t gs = a.slot0 + slot;
+  bool keep;
+  if (a.conv == 1) keep = (in <= o);  // klmap: l <= k   (E.f90:901-907)
+  else {
+    keep = !(a.symmetric && in < o);  // s < r skipped   (C.f90:409)
+    if (a.intra && a.symmetric && o < a.slot_a[gs]) keep = false;  // r < p skipped (C.f90:394)
+  }
+  if (!keep) return false;
+  const int io = o - a.lo_outer, ii = in - a.lo_inner;
+  const int64_t off = a.swap2 ? ((int64_t)ii * a.nf2 + io) : ((int64_t)io * a.nf2 + ii);
+  v = a.OUT[(int64_t)slot * a.ns2 * a.nf2 + off];
+  return fabs(v) > a.tol;
+}
+
+constexpr int SEL_CHUNK = 2048;  // candidates per block
+constexpr int SEL_THREADS = 256;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_count_kernel(SelectArgs a, int64_t ncand, unsigned *__restrict__ blockcount) {
+  __shared__ unsigned wsum[SEL_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SEL_CHUNK;
+  unsigned cnt = 0;
+  for (int t = threadIdx.x; t < SEL_CHUNK; t += SEL_THREADS) {
+    int64_t c = base + t;
+    double v; int s, o, in;
+    if (c < ncand && select_candidate(a, c, v, s, o, in)) ++cnt;
+  }
+  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) t += wsum[w];
+    blockcount[blockIdx.x] = t;
+  }
+}
+
+// Single-block exclusive scan of the block counts; *running is the number of entries already emitted
+// by earlier batches and is advanced by this batch's total.
+__global__ void __launch_bounds__(1024) select_scan_kernel(const unsigned *__restrict__ blockcount, int64_t nblk,
+                                                           int64_t *__restrict__ blockoff, unsigned long long *running) {
+  __shared__ unsigned long long part[1024];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = *running;
+  __syncthreads();
+  for (int64_t base = 0; base < nblk; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    unsigned long long v = (i < nblk) ? blockcount[i] : 0ull;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      unsigned long long t = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0ull;
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nblk) blockoff[i] = (int64_t)(carry + part[threadIdx.x] - v);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *running = carry;
+}
+
+struct EmitArgs {
+  int64_t *o_ij, *o_kl;                 // conv E
+  int32_t *o_p, *o_q, *o_r, *o_s;       // conv C
+  double *o_v;
+  int64_t capacity;
+  int *overflow;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(SelectArgs a, int64_t ncand, const int64_t *__restrict__ blockoff, EmitArgs e) {
+  __shared__ unsigned wbase[SEL_THREADS / 32];
+  __shared__ unsigned round_base;
+  const int64_t base = (int64_t)blockIdx.x * SEL_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) round_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < SEL_CHUNK; t0 += SEL_THREADS) {
+    const int64_t c = base + t0 + threadIdx.x;
+    double v = 0.0; int s = 0, o = 0, in = 0;
+    const bool keep = (c < ncand) && select_candidate(a, c, v, s, o, in);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wbase[warp] = __popc(bal);
+    __syncthreads();
+    unsigned pre = 0, tot = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) { if (w < warp) pre += wbase[w]; tot += wbase[w]; }
+    const unsigned rb = round_base;
+    if (keep) {
+      const int64_t pos = blockoff[blockIdx.x] + rb + pre + __popc(bal & ((1u << lane) - 1u));
+      if (pos < e.capacity) {
+        const int64_t gs = a.slot0 + s;
+        e.o_v[pos] = v;
+        if (a.conv == 1) {
+          e.o_ij[pos] = pair0(a.slot_a[gs] - 1, a.slot_b[gs] - 1, a.nA) + 1;
+          e.o_kl[pos] = pair0(o - 1, in - 1, a.nB) + 1;
+        } else {
+          e.o_p[pos] = a.slot_a[gs]; e.o_q[pos] = a.slot_b[gs]; e.o_r[pos] = o; e.o_s[pos] = in;
+        }
+      } else *e.overflow = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) round_base = rb + tot;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming consumer: count / sum / sum of squares / pair energy of one OUT batch.
+//   energy term (intra, E convention, P==R and Q==S windows): x (lambda x - x_exch) / den with
+//   x = (a i|b j) = OUT[slot(a,i)][b][j], x_exch = (b i|a j) = OUT[slot(b,i)][a][j]
+//   (closed form of src/MBPT/MPFunctions.f90:450-512); inter: x^2/den (MPFunctions.f90:750-765).
+// sums: [0]=count, [1]=sum, [2]=sum sq, [3]=energy   (double atomics, order non-deterministic)
+// ---------------------------------------------------------------------------------------------
+struct ReduceArgs {
+  const double *OUT;                // [nslots][ns2][nf2], all slots of the pass
+  int nslots, ns2, nf2;
+  const int32_t *slot_s, *slot_f;   // per pass-local slot: index in the second / first window of the first pair
+  const int32_t *slot_table;        // [ns1][nfb] -> pass-local slot or -1
+  int nfb;
+  int orb_s1, orb_f1, orb_s2, orb_f2;  // 1-based orbital number of index 0 along each of the four dims
+  const double *epsA, *epsB;        // device orbital energies (null: no energy term)
+  int exchange;                     // 1: intra, identical windows -> exchange partner is in OUT
+  double lambda, tol;
+};
+
+__global__ void __launch_bounds__(256) reduce_block_kernel(ReduceArgs a, double *__restrict__ sums) {
+  const int64_t per = (int64_t)a.ns2 * a.nf2;
+  const int64_t total = (int64_t)a.nslots * per;
+  double cnt = 0, s1 = 0, s2 = 0, en = 0;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a.OUT[c];
+    if (fabs(x) > a.tol) { cnt += 1.0; s1 += x; s2 += x * x; }
+    if (a.epsA) {
+      const int slot = (int)(c / per);
+      const int rem = (int)(c - (int64_t)slot * per);
+      const int k2 = rem / a.nf2, k1 = rem - k2 * a.nf2;
+      const int i2 = a.slot_s[slot], i1 = a.slot_f[slot];
+      const int o1s = a.orb_s1 + i2, o1f = a.orb_f1 + i1, o2s = a.orb_s2 + k2, o2f = a.orb_f2 + k1;
+      const double den = a.epsA[min(o1s, o1f) - 1] + a.epsB[min(o2s, o2f) - 1] - a.epsA[max(o1s, o1f) - 1] - a.epsB[max(o2s, o2f) - 1];
+      if (a.exchange) {
+        const int xs = a.slot_table[(int64_t)k2 * a.nfb + i1];   // slot of (second=k2, first=i1)
+        const double xe = (xs >= 0) ? a.OUT[(int64_t)xs * per + (int64_t)i2 * a.nf2 + k1] : 0.0;
+        en += x * (a.lambda * x - xe) / den;
+      } else {
+        en += x * x / den;
+      }
+    }
+  }
+  __shared__ double sh[4][8];
+  for (int d = 16; d; d >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d); s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);   en += __shfl_xor_sync(0xffffffffu, en, d);
+  }
+  if ((threadIdx.x & 31) == 0) { int w = threadIdx.x >> 5; sh[0][w] = cnt; sh[1][w] = s1; sh[2][w] = s2; sh[3][w] = en; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+// D-layout -> internal layout (IntTransfD.cpp:25-65 Multi_Index / Multi_Index_Inter).
+// pairD(i,j) = i(i+1)/2 + j, i>=j (0-based).  pi/pj: (i,j) of each xy-numbered pair (i<=j).
+__device__ __forceinline__ int64_t pairD(int64_t i, int64_t j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+__global__ void repack_d_intra_kernel(double *__restrict__ packed /*SRC_SYM_PACKED*/, const double *__restrict__ dpacked,
+                                      const int32_t *__restrict__ pi, const int32_t *__restrict__ pj, int64_t M) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * M) return;
+  int64_t a = e / M, b = e % M;
+  if (b < a) return;
+  int64_t da = pairD(pi[a], pj[a]), db = pairD(pi[b], pj[b]);
+  int64_t hi = da >= db ? da : db, lo = da >= db ? db : da;
+  packed[a * M - (a * (a + 1)) / 2 + b] = dpacked[hi * (hi + 1) / 2 + lo];
+}
+
+__global__ void repack_d_inter_kernel(double *__restrict__ rect /*[Mb][Ma] xy numbering*/, const double *__restrict__ d_rect /*[ij*om+kl]*/,
+                                      const int32_t *__restrict__ pia, const int32_t *__restrict__ pja,
+                                      const int32_t *__restrict__ pib, const int32_t *__restrict__ pjb, int64_t Ma, int64_t Mb) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Ma * Mb) return;
+  int64_t b = e / Ma, a = e % Ma;
+  rect[e] = d_rect[pairD(pia[a], pja[a]) * Mb + pairD(pib[b], pjb[b])];
+}
+
+// v[ij*M + kl] (dense pair matrix in D numbering) -> ERIS[ij(ij+1)/2 + kl], kl <= ij
+__global__ void pack_d_lower_kernel(const double *__restrict__ v, double *__restrict__ dpacked, int64_t M) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * M) return;
+  int64_t ij = e / M, kl = e % M;
+  if (kl <= ij) dpacked[ij * (ij + 1) / 2 + kl] = v[e];
+}
+
+}  // namespace lowdin
