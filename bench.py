@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- four-index AO->MO transform throughput on B200 (BASELINE.json metric).
+
+Workload (config.workload): synthetic kind-H AO integrals (generated on the device from a counter
+hash) + random orthonormal coefficients, N_bf basis functions (default 1500),
+O = N/10 occupied, MP2 window in transformer-E roles (p,r in virt; q,s in occ).  The (i a|mu nu)
+half-transformed block of N=1500 is 1.8 TB, so the transform runs one OCCUPIED BATCH at a time
+(lowdin_it_transform_stream); a "step" is one such pass: first half over all M AO-pair slabs for
+`occ_batch` occupied orbitals, second half over the resulting MO pairs, results consumed on the
+device (count / sums / MP2 pair energy).  GFLOP/s uses the ALGORITHMIC two-half flop count
+F = 2 N Qb (N+P) n_pq + 2 N S (N+R) n_ij of SURVEY.md 8d -- no credit for padding or redundancy.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--nbf 1500] [--occ-batch 0] [--impl reference]
+
+N>1: launched by torchrun, one rank per GPU; first half sharded over AO pair slabs, one NCCL
+all-to-all, second half sharded over MO pairs (strong scaling: the job is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261017
+
+
+def mp2_window_e(n, occ):
+    # TransformIntegralsE.f90:1938-1949: p,r in [occ+1,N]; q,s in [1,occ]
+    return [occ + 1, n, 1, occ, occ + 1, n, 1, occ]
+
+
+def algorithmic_flops_pass(n, occ, qb, nslabs_frac=1.0):
+    P = n - occ
+    M = n * (n + 1) // 2
+    first = 2.0 * n * qb * (n + P) * M * nslabs_frac
+    second = 2.0 * n * occ * (n + P) * (P * qb) * nslabs_frac
+    return first + second
+
+
+def random_orthonormal(n, seed):
+    q, _ = np.linalg.qr(np.random.default_rng(seed).standard_normal((n, n)))
+    return np.asfortranarray(q)
+
+
+def synthetic_eps(occ, n):
+    return np.concatenate([np.linspace(-2.0, -0.5, occ), np.linspace(0.2, 3.0, n - occ)])
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        # "under load" = samples drawing more than half of the max power seen
+        load = [s for s, p in zip(sm, pw) if pw and p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(n, occ, nslabs, nthreads):
+    """The oracle's restatement of transformer E's first half (E.f90:1043-1132) on `nslabs` slabs."""
+    from oracle import oracle as O
+    Cm = O.random_orthonormal(n, n)
+    win = mp2_window_e(n, occ)
+    t0 = time.perf_counter()
+    chk = O.e_first_half_sample(SEED, Cm, win, 0, nslabs, nthreads)
+    dt = time.perf_counter() - t0
+    flops = 2.0 * n * occ * (n + (n - occ)) * nslabs
+    return flops / dt / 1e9, dt, chk
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU transformer (oracle port of transformer E: the reference's
+    Fortran cannot be compiled here and its C++ transformer D overflows 32-bit indices past N~300)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, occ = args.nbf, args.nbf // 10
+    nthreads = os.cpu_count() or 1
+    per_step = max(1, nthreads)  # one slab per thread per step
+    for _ in range(args.warmup):
+        cpu_sample(n, occ, per_step, nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(n, occ, per_step, nthreads)
+    dt = time.perf_counter() - t0
+    flops = 2.0 * n * occ * (n + (n - occ)) * per_step * args.steps
+    val = flops / dt / 1e9
+    sample = (f"first half of transformer E (E.f90:1043-1132, oracle port), {per_step} of {n*(n+1)//2} AO-pair slabs per step, "
+              f"full occupied window, {nthreads} threads over independent slabs")
+    line = {"impl": "reference", "metric": "4-index transform FP64 GFLOP/s", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"N_bf={n} MP2 window O={occ}, kind-H synthetic AO, random orthonormal C", "nbf": n, "occ": occ},
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cublas_fp64_peak(torch, dev, n=4096, iters=6):
+    a = torch.rand(n, n, dtype=torch.float64, device=dev)
+    b = torch.rand(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--nbf", type=int, default=1500)
+    ap.add_argument("--occ-batch", type=int, default=0)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import openlowdin_b200 as ol
+    from openlowdin_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, occ = args.nbf, args.nbf // 10
+    win = mp2_window_e(n, occ)
+    Cm = random_orthonormal(n, n)
+    eps = synthetic_eps(occ, n)
+
+    fp64_peak = cublas_fp64_peak(torch, dev)  # the FP64 roofline denominator, measured live (cuBLAS DGEMM)
+
+    T = ol.Transformer(local)
+    if world > 1:
+        uid = [capi.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        T.comm_init(rank, world, uid[0])
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, SEED)
+    npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_pass(i, with_eps=True):
+        return T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, first_pass=i % npass, n_passes=1,
+                                  epsA=eps if with_eps else None)
+
+    for i in range(args.warmup):
+        one_pass(i)
+
+    # ---------------- timed region: `value` (inputs resident in HBM) ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    T.set_profiling(True)
+    barrier()
+    t0 = time.perf_counter()
+    dev_s, flops, launches = 0.0, 0.0, 0
+    for i in range(args.steps):
+        one_pass(args.warmup + i)
+        tm = T.timers()
+        dev_s += tm["first_half"] + tm["exchange"] + tm["second_half"] + tm["consume"]
+        flops += tm["flops"]
+        launches += tm["launches"]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    stats = T.kernel_stats()
+    T.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- e2e: through the C ABI with host buffers every step ----------------
+    pinned = torch.from_numpy(np.ascontiguousarray(Cm.T)).pin_memory()  # column-major C(mu,p) == row-major C^T
+    Cpin = pinned.numpy().T
+    barrier()
+    t1 = time.perf_counter()
+    e2e_flops = 0.0
+    for i in range(args.steps):
+        T.set_species(0, Cpin)           # H2D: coefficients
+        T.set_generator(0, 0, SEED)
+        s = one_pass(args.warmup + i)    # H2D: orbital energies; D2H: sums
+        e2e_flops += T.timers()["flops"]
+    barrier()
+    e2e_s = time.perf_counter() - t1
+
+    if dist is not None:
+        t = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall_s, e2e_s = t.tolist()
+        f = torch.tensor([flops, e2e_flops, float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+        flops, e2e_flops, launches = f.tolist()
+
+    if rank == 0:
+        value = flops / dev_s / 1e9
+        gemm_cats = ("q1", "q2", "q3", "q4")
+        dom = max(stats, key=lambda c: stats[c]["ms"])
+        st = stats[dom]
+        if dom in gemm_cats:
+            achieved = st["work"] / (st["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": f"dgemm_tn_kernel ({dom})", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak, "traffic": None, "launches": st["launches"],
+                    "avg_launch_ms": st["ms"] / max(st["launches"], 1),
+                    "peak_source": "cuBLAS DGEMM 4096^3 best of 6, measured live by bench.py (MEASURED_PEAKS.json has no FP64 entry)"}
+        else:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except (OSError, ValueError):
+                pass
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            achieved = st["work"] / (st["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": f"{dom}", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    "traffic": None, "launches": st["launches"], "avg_launch_ms": st["ms"] / max(st["launches"], 1),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
+        kernels = {}
+        for c, s_ in stats.items():
+            if s_["launches"] == 0:
+                continue
+            rate = s_["work"] / (s_["ms"] * 1e-3)
+            kernels[c] = {"ms": round(s_["ms"], 3), "launches": s_["launches"],
+                          ("TFLOP/s" if c in gemm_cats else "GB/s"): rate / (1e12 if c in gemm_cats else 1e9)}
+        line = {"metric": "4-index transform FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"N_bf={n} MP2 window O={occ} (transformer-E roles), kind-H synthetic AO generated on device, "
+                                       f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
+                                       f"({npass} passes = the whole transform)",
+                           "nbf": n, "occ": occ, "occ_batch": qb, "passes_per_transform": npass,
+                           "l2": "inputs larger than L2 (each pass streams >100 GB of generated slabs / half-transformed data)",
+                           "flops_per_step": flops / args.steps, "fp64_pct_of_cublas_dgemm": 100.0 * value / 1e3 / fp64_peak,
+                           "fp64_pct_of_nominal_37tf": 100.0 * value / 37000.0, "wall_ms_per_step": wall_s / args.steps * 1e3},
+                "roofline": roof, "kernels": kernels,
+                "e2e": {"value": e2e_flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(n * n * 8 + n * 8),
+                        "d2h_bytes_per_step": 32},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            nthreads = os.cpu_count() or 1
+            nsl = max(1, nthreads) * (2 if n >= 1000 else 8)
+            v, dt, _ = cpu_sample(n, occ, nsl, nthreads)
+            line["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": nthreads, "kind": "port",
+                                    "sample": f"first half of transformer E (oracle port of E.f90:1043-1132) on {nsl} of {n*(n+1)//2} "
+                                              f"AO-pair slabs, full occupied window, {dt:.1f} s"}
+        print(json.dumps(line))
+    T.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

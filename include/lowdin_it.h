@@ -107,10 +107,20 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
  * [5]=download, [6]=algorithmic flops of the last transform, [7]=kernels launched by it.
  * Times in seconds (CUDA events on the library's stream). */
 int lowdin_it_timers(lowdin_it_handle h, double out[8]);
+/* Per-kernel-category device timing of the transforms that follow (CUDA event pairs around every
+ * launch on the library's stream).  Categories: 0 slab expansion (1st half), 1 first quarter,
+ * 2 second quarter + H scatter, 3 slab expansion (2nd half), 4 third quarter, 5 fourth quarter,
+ * 6 consumer, 7 exchange.  work[] = algorithmic flops (GEMMs) or bytes (expansion, consumer). */
+int lowdin_it_set_profiling(lowdin_it_handle h, int on);
+int lowdin_it_kernel_stats(lowdin_it_handle h, double ms[8], double launches[8], double work[8]);
 /* Stand-alone kernel entry points used by tests and bench.py to time one kernel on device
  * buffers owned by the handle. kind: 0 = slab expansion, 1 = DGEMM (DMMA) m x n x k. */
 int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, int64_t k, int iters,
                            double *ms_per_launch, double *check);
+/* Parity-test access to single kernels: C[m][n] = sum_k A[m][k] B[n][k] on host arrays through the
+ * DMMA kernel; dense expansion of nb slabs of an uploaded / generated AO set to host X[nb][n][n]. */
+int lowdin_it_debug_gemm(lowdin_it_handle h, const double *A, const double *B, double *C, int m, int n, int k);
+int lowdin_it_debug_expand(lowdin_it_handle h, int slotA, int slotB, int64_t slab0, int nb, double *X);
 
 #ifdef __cplusplus
 }

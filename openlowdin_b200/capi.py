@@ -22,6 +22,7 @@ ABI_SYMBOLS = [
     "lowdin_it_result_count", "lowdin_it_download_pairs", "lowdin_it_download_quads", "lowdin_it_transform_stream",
     "lowdin_it_stream_num_passes", "lowdin_it_transform_all", "lowdin_it_transform_inter_all",
     "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_timers", "lowdin_it_kernel_bench",
+    "lowdin_it_set_profiling", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
 ]
 
 
@@ -71,6 +72,8 @@ def load():
     L.lowdin_it_timers.argtypes = [H, _f64p]
     L.lowdin_it_kernel_bench.argtypes = [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
+    L.lowdin_it_set_profiling.argtypes = [H, C.c_int]
+    L.lowdin_it_kernel_stats.argtypes = [H, _f64p, _f64p, _f64p]
     L.lowdin_it_debug_gemm.argtypes = [H, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_int]
     L.lowdin_it_debug_expand.argtypes = [H, C.c_int, C.c_int, C.c_int64, C.c_int, _f64p]
     _lib = L
@@ -164,6 +167,16 @@ class Transformer:
         self._ck(self.L.lowdin_it_timers(self.h, t))
         return dict(ao_upload=t[0], first_half=t[1], exchange=t[2], second_half=t[3], consume=t[4], download=t[5],
                     flops=t[6], launches=int(t[7]))
+
+    CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
+
+    def set_profiling(self, on=True):
+        self._ck(self.L.lowdin_it_set_profiling(self.h, int(on)))
+
+    def kernel_stats(self):
+        ms, cnt, work = np.zeros(8), np.zeros(8), np.zeros(8)
+        self._ck(self.L.lowdin_it_kernel_stats(self.h, ms, cnt, work))
+        return {c: dict(ms=ms[i], launches=int(cnt[i]), work=work[i]) for i, c in enumerate(self.CATEGORIES)}
 
     def kernel_bench(self, kind, m, n, k, iters=10):
         ms, chk = C.c_double(), C.c_double()

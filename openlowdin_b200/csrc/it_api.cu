@@ -101,7 +101,14 @@ struct lowdin_it_ctx {
   // multi-GPU
   int rank = 0, nranks = 1;
   void *comm = nullptr;
-  size_t workspace_bytes = (size_t)512 << 20;  // target size of the X / T1t batch buffers
+  size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
+  // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  struct ProfRec { int cat, e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  int prof_used = 0;
+  double prof_ms[8] = {0}, prof_cnt[8] = {0}, prof_work[8] = {0};
 };
 
 namespace {
@@ -119,6 +126,33 @@ int fail(lowdin_it_handle h, const std::string &msg) {
 inline int64_t npairs(int64_t n) { return n * (n + 1) / 2; }
 inline int64_t roundup2(int64_t x) { return (x + 1) & ~int64_t(1); }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- per-category kernel timing ---------------------------------------------------------------
+// categories: 0 expand(1st half) 1 Q1 2 Q2 3 expand(2nd half) 4 Q3 5 Q4 6 consume 7 exchange
+void prof_drain(lowdin_it_handle h) {
+  if (h->prof_recs.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  for (auto &r : h->prof_recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->prof_pool[r.e0], h->prof_pool[r.e1]) == cudaSuccess) { h->prof_ms[r.cat] += ms; h->prof_cnt[r.cat] += 1; }
+  }
+  h->prof_recs.clear();
+  h->prof_used = 0;
+}
+struct ProfScope {
+  lowdin_it_handle h; int idx = -1;
+  ProfScope(lowdin_it_handle h_, int cat, double work) : h(h_) {
+    if (!h->prof_on) return;
+    if (h->prof_used + 2 > 8192) prof_drain(h);
+    while ((int)h->prof_pool.size() < h->prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); h->prof_pool.push_back(e); }
+    idx = (int)h->prof_recs.size();
+    h->prof_recs.push_back({cat, h->prof_used, h->prof_used + 1});
+    h->prof_used += 2;
+    h->prof_work[cat] += work;
+    cudaEventRecord(h->prof_pool[h->prof_recs[idx].e0], h->stream);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_pool[h->prof_recs[idx].e1], h->stream); }
+};
 
 // ---- GEMM dispatch ----------------------------------------------------------------------------
 template <int BM, int BN, int WM, int WN, class Epi>
@@ -245,7 +279,7 @@ int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
 //   q_first: out = T1t ; q_second epilogue supplied by the caller through a functor factory.
 template <class MakeEpi>
 int run_half(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t count, const Half &hf, int f0, int nfb,
-             MakeEpi make_epi) {
+             MakeEpi make_epi, int cat) {
   const int nc = hf.nc;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
   const size_t per_slab = std::max((size_t)nc * ldx, (size_t)nfb * ldt) * sizeof(double);
@@ -258,6 +292,7 @@ int run_half(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t cou
   for (int64_t s = 0; s < count; s += B) {
     const int64_t bc = std::min<int64_t>(B, count - s);
     {  // unpack (E.f90:1047-1063)
+      ProfScope ps(h, cat, (double)bc * 8.0 * ((double)src.M + (double)nc * nc));
       dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)bc);
       if (bc > 65535) return fail(h, "slab batch exceeds gridDim.y");
       expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, slab0 + s, nc, (int)ldx, h->X.as<double>());
@@ -267,10 +302,12 @@ int run_half(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t cou
     {  // first quarter of this half (E.f90:1081-1090): T1t[z][f][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
       GemmArgs g{h->X.as<double>(), hf.C + (int64_t)(hf.lf - 1 + f0) * hf.ldc, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
       EpiQ1 epi{h->T1t.as<double>(), nc, nfb, ldt};
+      ProfScope ps(h, cat + 1, 2.0 * bc * nc * (double)nc * nfb);
       CK(launch_gemm(h, g, epi));
     }
     {  // second quarter (E.f90:1099-1110): T2[s][(z,f)] = sum_mu C(mu, ls+s) T1t[z][f][mu]
       GemmArgs g{hf.C + (int64_t)(hf.ls - 1) * hf.ldc, h->T1t.as<double>(), hf.ns, (int)(bc * nfb), nc, hf.ldc, ldt, 0, 0};
+      ProfScope ps(h, cat + 2, 2.0 * bc * nc * (double)hf.ns * nfb);
       CK(launch_gemm(h, g, make_epi(s, bc)));
     }
   }
@@ -326,7 +363,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       double *Hp = h->H.as<double>();
       const int32_t *tab = h->tab.as<int32_t>();
       auto mk = [&](int64_t s, int64_t) { return EpiScatterH{Hp, ldh, s, tab, nfb, half_tol}; };
-      if (run_half(h, pl.src, slab_lo, nloc, h1, f0, nfb, mk)) return 1;
+      if (run_half(h, pl.src, slab_lo, nloc, h1, f0, nfb, mk, 0)) return 1;
       flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)nloc;
     }
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -347,7 +384,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       double *OUT = h->OUT.as<double>();
       const int ns2 = h2.ns, nf2 = h2.nf;
       auto mk = [&](int64_t s, int64_t) { return EpiOut{OUT + s * per, ns2, nf2}; };
-      if (run_half(h, hsrc, 0, nsl, h2, 0, h2.nf, mk)) return 1;
+      if (run_half(h, hsrc, 0, nsl, h2, 0, h2.nf, mk, 3)) return 1;
       flops += 2.0 * h2.nc * h2.nf * ((double)h2.nc + h2.ns) * (double)nsl;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
@@ -406,12 +443,14 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       ra.exchange = (pl.intra && h->nranks == 1 && h1.ls == h2.ls && h1.ns == h2.ns && h1.lf == h2.lf && h1.nf == h2.nf &&
                      pl.win[0] == pl.win[4] && pl.win[2] == pl.win[6]) ? 1 : 0;
       ra.lambda = cons.lambda; ra.tol = cons.tol;
+      ProfScope ps(h, 6, (double)nsl * per * 8.0);
       reduce_block_kernel<<<148 * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
       h->launches += 1;
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    prof_drain(h);
     float ms;
     for (int t = 0; t < 4; ++t) { CK(cudaEventElapsedTime(&ms, h->ev[t], h->ev[t + 1])); h->timers[1 + t] += ms * 1e-3; }
   }
@@ -710,6 +749,19 @@ int lowdin_it_transform_stream(lowdin_it_handle h, int a, int b, const int win[8
     } else cons.epsB = cons.epsA;
   }
   return run_passes(h, pl, used, first_pass, n_passes, cons, sums);
+}
+
+int lowdin_it_set_profiling(lowdin_it_handle h, int on) {
+  if (!h) return 1;
+  h->prof_on = on != 0;
+  for (int c = 0; c < 8; ++c) h->prof_ms[c] = h->prof_cnt[c] = h->prof_work[c] = 0;
+  return 0;
+}
+
+int lowdin_it_kernel_stats(lowdin_it_handle h, double ms[8], double launches[8], double work[8]) {
+  if (!h) return 1;
+  for (int c = 0; c < 8; ++c) { ms[c] = h->prof_ms[c]; launches[c] = h->prof_cnt[c]; work[c] = h->prof_work[c]; }
+  return 0;
 }
 
 int lowdin_it_timers(lowdin_it_handle h, double out[8]) {

@@ -512,28 +512,36 @@ void orc_fill_hash_inter(uint64_t seed, int na, int nb, double *rect) {
 /* First half of transformer E (E.f90:1043-1132) on slabs [pq0, pq0+npq) of a
  * kind-H synthetic intra tensor generated on the fly (so N=500..1500 samples
  * need no N^4/8 array).  Returns a checksum so the work cannot be elided.
- * Single thread, as in the reference (its OMP directives are commented out:
- * E.f90:1078-1080). */
+ * The reference's compute loops are serial (its OMP directives are commented
+ * out: E.f90:1078-1080); nthreads > 1 spreads the independent slabs over
+ * threads, which is the most the reference's structure would allow. */
 double orc_e_first_half_sample(uint64_t seed, int n, const double *C, int ldc, const int *win, int64_t pq0,
-                               int64_t npq) {
+                               int64_t npq, int nthreads) {
   int64_t M = (int64_t)n * (n + 1) / 2;
   int32_t *x1 = malloc(sizeof(int32_t) * M), *x2 = malloc(sizeof(int32_t) * M);
   build_xypair(n, x1, x2);
   int64_t nij = build_pairmap(win[0], win[1], win[2], win[3], n, NULL);
   int64_t *ijmap = malloc(sizeof(int64_t) * (nij + 1));
   build_pairmap(win[0], win[1], win[2], win[3], n, ijmap);
-  double *slab = malloc(sizeof(double) * M), *tB = malloc(sizeof(double) * n * n),
-         *tBC = calloc((size_t)n * n, sizeof(double)), *res = malloc(sizeof(double) * (nij + 1));
   double chk = 0.0;
-  for (int64_t pq = pq0 + 1; pq <= pq0 + npq && pq <= M; ++pq) {
-    for (int64_t rs = 1; rs <= M; ++rs) {
-      int64_t hi = pq >= rs ? pq : rs, lo = pq >= rs ? rs : pq;
-      slab[rs - 1] = orc_hash_value(seed, (uint64_t)((hi - 1) * M + (lo - 1)));
+  if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads) reduction(+ : chk)
+  {
+    double *slab = malloc(sizeof(double) * M), *tB = malloc(sizeof(double) * n * n),
+           *tBC = calloc((size_t)n * n, sizeof(double)), *res = malloc(sizeof(double) * (nij + 1));
+#pragma omp for schedule(dynamic)
+    for (int64_t pq = pq0 + 1; pq <= pq0 + npq; ++pq) {
+      if (pq > M) continue;
+      for (int64_t rs = 1; rs <= M; ++rs) {
+        int64_t hi = pq >= rs ? pq : rs, lo = pq >= rs ? rs : pq;
+        slab[rs - 1] = orc_hash_value(seed, (uint64_t)((hi - 1) * M + (lo - 1)));
+      }
+      e_half_slab(n, C, ldc, slab, x1, x2, win[2], win[3], ijmap, nij, tB, tBC, res);
+      for (int64_t ij = 0; ij < nij; ++ij)
+        if (fabs(res[ij]) > 1e-10) chk += res[ij];
     }
-    e_half_slab(n, C, ldc, slab, x1, x2, win[2], win[3], ijmap, nij, tB, tBC, res);
-    for (int64_t ij = 0; ij < nij; ++ij)
-      if (fabs(res[ij]) > 1e-10) chk += res[ij];
+    free(slab); free(tB); free(tBC); free(res);
   }
-  free(x1); free(x2); free(ijmap); free(slab); free(tB); free(tBC); free(res);
+  free(x1); free(x2); free(ijmap);
   return chk;
 }

@@ -87,7 +87,7 @@ def lib():
         L.orc_fill_hash_inter.restype = None
         L.orc_fill_hash_inter.argtypes = [C.c_uint64, C.c_int, C.c_int, _f64p]
         L.orc_e_first_half_sample.restype = C.c_double
-        L.orc_e_first_half_sample.argtypes = [C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64]
+        L.orc_e_first_half_sample.argtypes = [C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int]
         L.orc_reader_pairs_intra.restype = None
         L.orc_reader_pairs_intra.argtypes = [_i64p, _i64p, _f64p, C.c_int64, C.c_int, _f64p]
         L.orc_reader_quads_intra.restype = None
@@ -594,3 +594,9 @@ def mp2_inter_from_quads(p, q, r, s, v, na, nb, occ_a, occ_b, eps_a, eps_b, char
     lib().orc_reader_quads_inter(p, q, r, s, np.ascontiguousarray(v), len(v), na, nb, rect)
     return lib().orc_mp2_inter(rect, na, nb, occ_a, occ_b, 0, 0, na, nb, charge_a, charge_b, lam_a, lam_b,
                                np.ascontiguousarray(eps_a), np.ascontiguousarray(eps_b))
+
+
+def e_first_half_sample(seed, Cm, win, pq0, npq, nthreads=1):
+    """CPU baseline sample: first half of transformer E on npq slabs of the kind-H tensor."""
+    n = Cm.shape[0]
+    return lib().orc_e_first_half_sample(seed, n, np.asfortranarray(Cm), n, _win(win), pq0, npq, nthreads)
