@@ -102,6 +102,11 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
 int lowdin_it_comm_unique_id(char id[128]);
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]);
 
+/* ---- tuning ----------------------------------------------------------------------- */
+#define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
+#define LOWDIN_IT_OPT_CHUNK_COLS 2      /* cap on AO-pair columns per chunk of the half-transformed block (0 = from free HBM) */
+int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
+
 /* ---- instrumentation -------------------------------------------------------------- */
 /* out[0]=AO upload+scatter, [1]=first half, [2]=exchange, [3]=second half, [4]=compaction/consume,
  * [5]=download, [6]=algorithmic flops of the last transform, [7]=kernels launched by it.

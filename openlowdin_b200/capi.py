@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "lowdin_it_result_count", "lowdin_it_download_pairs", "lowdin_it_download_quads", "lowdin_it_transform_stream",
     "lowdin_it_stream_num_passes", "lowdin_it_transform_all", "lowdin_it_transform_inter_all",
     "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_timers", "lowdin_it_kernel_bench",
-    "lowdin_it_set_profiling", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
+    "lowdin_it_set_profiling", "lowdin_it_set_option", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
 ]
 
 
@@ -73,6 +73,7 @@ def load():
     L.lowdin_it_kernel_bench.argtypes = [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
     L.lowdin_it_set_profiling.argtypes = [H, C.c_int]
+    L.lowdin_it_set_option.argtypes = [H, C.c_int, C.c_int64]
     L.lowdin_it_kernel_stats.argtypes = [H, _f64p, _f64p, _f64p]
     L.lowdin_it_debug_gemm.argtypes = [H, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_int]
     L.lowdin_it_debug_expand.argtypes = [H, C.c_int, C.c_int, C.c_int64, C.c_int, _f64p]
@@ -169,6 +170,11 @@ class Transformer:
                     flops=t[6], launches=int(t[7]))
 
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
+
+    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS = 1, 2
+
+    def set_option(self, option, value):
+        self._ck(self.L.lowdin_it_set_option(self.h, option, int(value)))
 
     def set_profiling(self, on=True):
         self._ck(self.L.lowdin_it_set_profiling(self.h, int(on)))

@@ -90,7 +90,7 @@ struct lowdin_it_ctx {
   int up_a = -1, up_b = -1, up_swapped = 0;
   DevBuf st_p, st_q, st_r, st_s, st_v;
   // workspaces
-  DevBuf X, T1t, H, H2, OUT, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp;
+  DevBuf X, T1t, H, H2, OUT, T3, order, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp;
   // results of the last lowdin_it_transform
   DevBuf r_i0, r_i1, r_i2, r_i3, r_v;
   int64_t count = 0;
@@ -102,6 +102,7 @@ struct lowdin_it_ctx {
   int rank = 0, nranks = 1;
   void *comm = nullptr;
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
+  int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_pool;
@@ -204,13 +205,19 @@ struct Plan {
   Half h1, h2;
   int64_t nslabs1 = 0;     // slabs of the first half (M of the non-contracted species)
   AoSource src{};
-  std::vector<int> pairs_s, pairs_f;  // all needed first pairs in convention order: window-relative (second, first) indices
-  std::vector<int> pairs_a, pairs_b;  // orbital numbers in convention order ((i,j) or (p,q))
+  // all needed first pairs in convention order: window-relative (second, first) indices and orbital numbers ((i,j) or (p,q))
+  std::vector<int> pairs_s, pairs_f, pairs_a, pairs_b;
+  int max_slots_per_f = 0;  // largest number of needed pairs sharing one first-contracted index
 };
 
+// One occupied-batch pass: first-contracted indices [f0, f0+nfb).  Slots (the needed window pairs of the
+// pass) are numbered f-major, so that the pairs sharing one first-contracted index are consecutive: they
+// are finished together (fourth quarter + consumer), owned by one rank, and contain each other's
+// exchange partners.  `order` lists the slots in the reference's loop order for the download.
 struct PassTables {
   int f0 = 0, nfb = 0, nslots = 0;
-  std::vector<int32_t> table, sa, sb, ss, sf;
+  std::vector<int32_t> table, sa, sb, ss, sf, order;
+  std::vector<int> fbeg;  // [nfb+1] first slot of each f
 };
 
 int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int symmetric, Plan &pl) {
@@ -243,6 +250,7 @@ int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int
   pl.src = h->ao[a][b].src;
   // needed first pairs, convention order
   pl.pairs_s.clear(); pl.pairs_f.clear(); pl.pairs_a.clear(); pl.pairs_b.clear();
+  std::vector<int> per_f(std::max(pl.h1.nf, 1), 0);
   for (int x = win[0]; x <= win[1]; ++x)
     for (int y = win[2]; y <= win[3]; ++y) {
       bool keep = (conv == LOWDIN_IT_CONV_E) ? (y <= x) : !(symmetric && y < x);
@@ -250,23 +258,43 @@ int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int
       pl.pairs_a.push_back(x); pl.pairs_b.push_back(y);
       if (pl.h1.first_is_conv_second) { pl.pairs_s.push_back(x - win[0]); pl.pairs_f.push_back(y - win[2]); }
       else { pl.pairs_s.push_back(y - win[2]); pl.pairs_f.push_back(x - win[0]); }
+      per_f[pl.pairs_f.back()]++;
     }
+  pl.max_slots_per_f = 0;
+  for (int c : per_f) pl.max_slots_per_f = std::max(pl.max_slots_per_f, c);
   return 0;
 }
 
 void build_pass(const Plan &pl, int f0, int nfb, PassTables &pt) {
   pt.f0 = f0; pt.nfb = nfb;
-  pt.table.assign((size_t)pl.h1.ns * nfb, -1);
-  pt.sa.clear(); pt.sb.clear(); pt.ss.clear(); pt.sf.clear();
-  int slot = 0;
+  const int ns = pl.h1.ns;
+  pt.table.assign((size_t)std::max(ns, 1) * nfb, -1);
+  std::vector<int> conv_of((size_t)std::max(ns, 1) * nfb, -1);  // (s,f) -> index in convention order
   for (size_t k = 0; k < pl.pairs_s.size(); ++k) {
     int f = pl.pairs_f[k] - f0;
     if (f < 0 || f >= nfb) continue;
-    pt.table[(size_t)pl.pairs_s[k] * nfb + f] = slot++;
-    pt.sa.push_back(pl.pairs_a[k]); pt.sb.push_back(pl.pairs_b[k]);
-    pt.ss.push_back(pl.pairs_s[k]); pt.sf.push_back(f);
+    conv_of[(size_t)pl.pairs_s[k] * nfb + f] = (int)k;
   }
+  pt.sa.clear(); pt.sb.clear(); pt.ss.clear(); pt.sf.clear(); pt.order.clear();
+  pt.fbeg.assign(nfb + 1, 0);
+  std::vector<std::pair<int, int>> byconv;  // (convention index, slot)
+  int slot = 0;
+  for (int f = 0; f < nfb; ++f) {
+    pt.fbeg[f] = slot;
+    for (int s_ = 0; s_ < ns; ++s_) {
+      const int k = conv_of[(size_t)s_ * nfb + f];
+      if (k < 0) continue;
+      pt.table[(size_t)s_ * nfb + f] = slot;
+      pt.sa.push_back(pl.pairs_a[k]); pt.sb.push_back(pl.pairs_b[k]);
+      pt.ss.push_back(s_); pt.sf.push_back(f);
+      byconv.push_back({k, slot});
+      ++slot;
+    }
+  }
+  pt.fbeg[nfb] = slot;
   pt.nslots = slot;
+  std::sort(byconv.begin(), byconv.end());
+  for (auto &e : byconv) pt.order.push_back(e.second);
 }
 
 int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
@@ -275,40 +303,140 @@ int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
   return 0;
 }
 
-// One half-transformation over `count` slabs starting at slab0 of `src`, batched.
-//   q_first: out = T1t ; q_second epilogue supplied by the caller through a functor factory.
-template <class MakeEpi>
-int run_half(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t count, const Half &hf, int f0, int nfb,
-             MakeEpi make_epi, int cat) {
-  const int nc = hf.nc;
+// ---- kernel launch helpers --------------------------------------------------------------------
+int launch_expand(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_t bc, int n, int r0, int nrows, int c0, int ncols,
+                  int64_t colbase, int ldx, double *X) {
+  if (bc <= 0 || nrows <= 0 || ncols <= 0) return 0;
+  if (bc > 65535) return fail(h, "slab batch exceeds gridDim.z");
+  dim3 grid((unsigned)ceil_div(ldx, 32), (unsigned)ceil_div(nrows, 32), (unsigned)bc);
+  expand_block_kernel<<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int TN>
+cudaError_t launch_q1_gen_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
+                              int nfb, double *T1t, int64_t ldt) {
+  constexpr int ST = 4;
+  constexpr size_t smem = (size_t)ST * (TN * 8) * 20 * sizeof(double);
+  auto kern = q1_gen_kernel<TN, ST>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(nc, 128), (unsigned)bc);
+  kern<<<grid, 256, smem, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
+// fused generation + first quarter; window columns in groups of at most 64
+int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb,
+                  double *T1t, int64_t ldt) {
+  for (int f = 0; f < nfb; f += 64) {
+    const int w = std::min(64, nfb - f);
+    const int tn = (int)ceil_div(w, 8);
+    const double *cf = Cf + (int64_t)f * ldc;
+    double *out = T1t + (int64_t)f * bc * ldt;
+    cudaError_t e = cudaSuccess;
+    switch (tn) {
+      case 1: e = launch_q1_gen_cfg<1>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 2: e = launch_q1_gen_cfg<2>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 3: e = launch_q1_gen_cfg<3>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 4: e = launch_q1_gen_cfg<4>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 5: e = launch_q1_gen_cfg<5>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 6: e = launch_q1_gen_cfg<6>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 7: e = launch_q1_gen_cfg<7>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      default: e = launch_q1_gen_cfg<8>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+    }
+    CK(e);
+  }
+  return 0;
+}
+
+// First half (E.f90:1043-1132) of `count` AO-pair slabs starting at slab `slab0`:
+//   Hc[slot][col0 + (slab - slab0)] for every slot of the pass.
+int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t slab0, int64_t count, double *Hc, int64_t ldh,
+               int64_t col0, double tol) {
+  const Half &hf = pl.h1;
+  const int nc = hf.nc, nfb = pt.nfb;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const size_t per_slab = std::max((size_t)nc * ldx, (size_t)nfb * ldt) * sizeof(double);
+  const bool generated = (pl.src.kind == SRC_HASH_SYM || pl.src.kind == SRC_HASH_RECT);
+  const size_t per_slab = std::max(generated ? (size_t)0 : (size_t)nc * ldx, (size_t)nfb * ldt) * sizeof(double);
   int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
   B = std::min<int64_t>(B, count);
   B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / nc)));  // gridDim.y limit of the stacked GEMM
-  B = std::min<int64_t>(B, 65535);                                                 // gridDim.y limit of the expansion
-  CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  B = std::min<int64_t>(B, 65535);                                                 // gridDim limits of expansion / fused kernel
+  if (!generated) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
+  const double *Cf = hf.C + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc;
   for (int64_t s = 0; s < count; s += B) {
     const int64_t bc = std::min<int64_t>(B, count - s);
-    {  // unpack (E.f90:1047-1063)
-      ProfScope ps(h, cat, (double)bc * 8.0 * ((double)src.M + (double)nc * nc));
-      dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)bc);
-      if (bc > 65535) return fail(h, "slab batch exceeds gridDim.y");
-      expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, slab0 + s, nc, (int)ldx, h->X.as<double>());
-      h->launches += 1;
-      CK(cudaGetLastError());
-    }
-    {  // first quarter of this half (E.f90:1081-1090): T1t[z][f][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
-      GemmArgs g{h->X.as<double>(), hf.C + (int64_t)(hf.lf - 1 + f0) * hf.ldc, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
-      EpiQ1 epi{h->T1t.as<double>(), nc, nfb, ldt};
-      ProfScope ps(h, cat + 1, 2.0 * bc * nc * (double)nc * nfb);
+    if (generated) {
+      // slab generation + first quarter in one kernel: the dense slab never exists
+      ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
+      if (launch_q1_gen(h, pl.src, slab0 + s, (int)bc, nc, Cf, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+    } else {
+      {  // unpack (E.f90:1047-1063)
+        ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
+        if (launch_expand(h, pl.src, slab0 + s, bc, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
+      }
+      // first quarter (E.f90:1081-1090): T1t[f][z][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
+      GemmArgs g{h->X.as<double>(), Cf, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
+      EpiQ1 epi{h->T1t.as<double>(), nc, (int)bc, ldt};
+      ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
       CK(launch_gemm(h, g, epi));
     }
-    {  // second quarter (E.f90:1099-1110): T2[s][(z,f)] = sum_mu C(mu, ls+s) T1t[z][f][mu]
+    {  // second quarter (E.f90:1099-1110): T2[s][(f,z)] = sum_mu C(mu, ls+s) T1t[f][z][mu]  ->  Hc[slot(s,f)][col0+s'+z]
       GemmArgs g{hf.C + (int64_t)(hf.ls - 1) * hf.ldc, h->T1t.as<double>(), hf.ns, (int)(bc * nfb), nc, hf.ldc, ldt, 0, 0};
-      ProfScope ps(h, cat + 2, 2.0 * bc * nc * (double)hf.ns * nfb);
-      CK(launch_gemm(h, g, make_epi(s, bc)));
+      EpiScatterH epi{Hc, ldh, col0 + s, h->tab.as<int32_t>(), nfb, (int)bc, tol};
+      ProfScope ps(h, 2, 2.0 * bc * nc * (double)hf.ns * nfb);
+      CK(launch_gemm(h, g, epi));
+    }
+  }
+  return 0;
+}
+
+// A chunk of AO-pair slabs = the pairs (p,q>=p) of rows p in [p0,p1) of the second-half species' pair triangle.
+struct Chunk { int p0, p1; int64_t base, width; };
+
+// Partial second half (E.f90:1178-1239, third quarter only) of one chunk for slots [s_lo, s_hi):
+//   T3[slot][kf][mu] += sum_nu Y_chunk(mu,nu) C(nu, kf),  Y_chunk = the symmetric N x N matrix of the slot's
+//   half-transformed row restricted to pairs whose smaller index lies in [p0,p1).
+// Two dense blocks carry it: W = Y[p0.., p0..p1) (all rows below, chunk columns) and V = Y[p0..p1), p1..) .
+int second_half_partial(lowdin_it_handle h, const Plan &pl, const AoSource &hsrc, const Chunk &ck, int s_lo, int s_hi, double *T3,
+                        int64_t ldt2) {
+  const Half &h2 = pl.h2;
+  const int n2 = h2.nc, nf2 = h2.nf;
+  const int pc = ck.p1 - ck.p0, nrw = n2 - ck.p0, ncv = n2 - ck.p1;
+  const int64_t ldw = roundup2(pc), ldv = roundup2(std::max(ncv, 1));
+  const size_t per_slot = std::max((size_t)nrw * ldw, (size_t)pc * ldv) * sizeof(double);
+  int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slot));
+  B = std::min<int64_t>(B, s_hi - s_lo);
+  B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / std::max(nrw, 1))));
+  B = std::min<int64_t>(B, 65535);
+  CK(h->X.ensure((size_t)B * nrw * ldw * sizeof(double)));
+  if (ncv > 0) CK(h->T1t.ensure((size_t)B * pc * ldv * sizeof(double)));
+  const double *C2f = h2.C + (int64_t)(h2.lf - 1) * h2.ldc;
+  for (int64_t s = s_lo; s < s_hi; s += B) {
+    const int64_t bs = std::min<int64_t>(B, s_hi - s);
+    double *T3s = T3 + (int64_t)(s - s_lo) * nf2 * ldt2;
+    {
+      ProfScope ps(h, 3, (double)bs * 8.0 * ((double)ck.width + (double)nrw * pc + (double)pc * ncv));
+      if (launch_expand(h, hsrc, s, bs, n2, ck.p0, nrw, ck.p0, pc, ck.base, (int)ldw, h->X.as<double>())) return 1;
+      if (ncv > 0 && launch_expand(h, hsrc, s, bs, n2, ck.p0, pc, ck.p1, ncv, ck.base, (int)ldv, h->T1t.as<double>())) return 1;
+    }
+    {
+      ProfScope ps(h, 4, 2.0 * bs * (double)nf2 * ((double)nrw * pc + (double)pc * ncv));
+      GemmArgs g{h->X.as<double>(), C2f + ck.p0, (int)(bs * nrw), nf2, pc, ldw, h2.ldc, 0, 0};
+      CK(launch_gemm(h, g, EpiAccT{T3s, nrw, ck.p0, nf2, ldt2}));
+      if (ncv > 0) {
+        GemmArgs g2{h->T1t.as<double>(), C2f + ck.p1, (int)(bs * pc), nf2, ncv, ldv, h2.ldc, 0, 0};
+        CK(launch_gemm(h, g2, EpiAccT{T3s, pc, ck.p0, nf2, ldt2}));
+      }
     }
   }
   return 0;
@@ -321,13 +449,13 @@ struct Consumer {
   double lambda = 2.0;
 };
 
-int exchange_h(lowdin_it_handle h, int nslots, int64_t ncols_local, int64_t ncols_total, const double **src_out, int64_t *ld_out,
-               int *slot_lo, int *slot_hi);
+int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out);
 
 int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass, int n_passes, const Consumer &cons,
                double sums_out[4]) {
   const Half &h1 = pl.h1, &h2 = pl.h2;
   const int nf_total = h1.nf;
+  const int G = h->nranks;
   if (occ_batch <= 0 || occ_batch > nf_total) occ_batch = std::max(nf_total, 1);
   const int total_passes = (int)ceil_div(std::max(nf_total, 1), occ_batch);
   if (n_passes <= 0) { first_pass = 0; n_passes = total_passes; }
@@ -340,10 +468,10 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
   }
   h->count = 0;
   double flops = 0.0;
-  // first-half slab range of this rank (contiguous blocks of equal width)
-  const int64_t wblk = ceil_div(pl.nslabs1, h->nranks);
-  const int64_t slab_lo = std::min<int64_t>(pl.nslabs1, wblk * h->rank), slab_hi = std::min<int64_t>(pl.nslabs1, slab_lo + wblk);
-  const int64_t nloc = slab_hi - slab_lo;
+  const int n2 = h2.nc, nf2 = h2.nf, ns2 = h2.ns;
+  const int64_t ldt2 = roundup2(n2);
+  const int64_t per_out = (int64_t)ns2 * nf2;
+  const double half_tol = (pl.conv == LOWDIN_IT_CONV_E) ? cons.tol : -1.0;
 
   for (int pass = first_pass; pass < first_pass + n_passes; ++pass) {
     PassTables pt;
@@ -352,53 +480,132 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     build_pass(pl, f0, nfb, pt);
     if (pt.nslots == 0) continue;
     if (upload_i32(h, h->tab, pt.table) || upload_i32(h, h->sa, pt.sa) || upload_i32(h, h->sb, pt.sb) ||
-        upload_i32(h, h->ss, pt.ss) || upload_i32(h, h->sf, pt.sf))
+        upload_i32(h, h->ss, pt.ss) || upload_i32(h, h->sf, pt.sf) || upload_i32(h, h->order, pt.order))
       return 1;
-    const int64_t ldh = (h->nranks > 1) ? std::max<int64_t>(wblk, 1) : pl.nslabs1;
-    CK(h->H.ensure((size_t)pt.nslots * ldh * sizeof(double)));
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    // ---------------- first half (E.f90:1043-1132), slabs [slab_lo, slab_hi) ----------------
-    {
-      const double half_tol = (pl.conv == LOWDIN_IT_CONV_E) ? cons.tol : -1.0;
-      double *Hp = h->H.as<double>();
-      const int32_t *tab = h->tab.as<int32_t>();
-      auto mk = [&](int64_t s, int64_t) { return EpiScatterH{Hp, ldh, s, tab, nfb, half_tol}; };
-      if (run_half(h, pl.src, slab_lo, nloc, h1, f0, nfb, mk, 0)) return 1;
-      flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)nloc;
+    // slot ownership: rank r owns the slots of a contiguous block of first-contracted indices
+    std::vector<int> own(G + 1, 0);
+    for (int r = 0; r <= G; ++r) own[r] = pt.fbeg[(int)((int64_t)nfb * r / G)];
+    const int s_lo = own[h->rank], s_hi = own[h->rank + 1], nmine = s_hi - s_lo;
+    // ---- device memory of the pass: T3 accumulators (own slots) + one chunk of half-transformed rows ----
+    const size_t t3_bytes = std::max<size_t>((size_t)std::max(nmine, 1) * nf2 * ldt2, 1) * sizeof(double);
+    CK(h->T3.ensure(t3_bytes));
+    CK(cudaMemsetAsync(h->T3.p, 0, t3_bytes, h->stream));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const bool download = (cons.mode == 0);
+    double out_need = download ? (double)std::max(nmine, 1) * per_out * 8.0
+                               : std::min(4.0e9, (double)std::max(nmine, 1) * per_out * 8.0);
+    out_need = std::max(out_need, (double)pl.max_slots_per_f * per_out * 8.0);
+    double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->OUT.cap + (double)h->X.cap + (double)h->T1t.cap) -
+                   out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
+    const double per_col = (double)pt.nslots * 8.0 + (G > 1 ? 2.0 * (double)nmine * 8.0 : 0.0);
+    int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
+    if (h->chunk_cols_limit > 0) max_cols = std::min<int64_t>(max_cols, h->chunk_cols_limit);
+    if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
+    // chunks: rows [p0,p1) of the pair triangle, even boundaries, as many rows as fit
+    std::vector<Chunk> chunks;
+    for (int p0 = 0; p0 < n2;) {
+      int p1 = p0;
+      int64_t width = 0;
+      while (p1 < n2) {
+        int step = std::min(2, n2 - p1);
+        int64_t add = 0;
+        for (int t = 0; t < step; ++t) add += n2 - (p1 + t);
+        if (p1 > p0 && width + add > max_cols) break;
+        width += add; p1 += step;
+      }
+      chunks.push_back({p0, p1, (int64_t)pair0(p0, p0, n2), width});
+      p0 = p1;
     }
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    float ms_first = 0, ms_exch = 0, ms_second = 0;
+    for (const Chunk &ck : chunks) {
+      // ---------------- first half (E.f90:1043-1132) over this rank's share of the chunk's slabs ----------------
+      const int64_t wblk = ceil_div(ck.width, G);
+      const int64_t c_lo = std::min<int64_t>(ck.width, wblk * h->rank), c_hi = std::min<int64_t>(ck.width, c_lo + wblk);
+      const int64_t ldh = (G > 1) ? wblk : ck.width;
+      CK(h->H.ensure(std::max<size_t>((size_t)pt.nslots * ldh, 1) * sizeof(double)));
+      CK(cudaEventRecord(h->ev[1], h->stream));
+      if (first_half(h, pl, pt, ck.base + c_lo, c_hi - c_lo, h->H.as<double>(), ldh, 0, half_tol)) return 1;
+      flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)(c_hi - c_lo);
+      CK(cudaEventRecord(h->ev[2], h->stream));
+      // ---------------- exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203) ----------------
+      AoSource hsrc{SRC_RECT, h->H.as<double>(), ck.width, ldh, 0, 0};
+      if (G > 1) {
+        ProfScope ps(h, 7, (double)pt.nslots * (double)(c_hi - c_lo) * 8.0);
+        if (exchange_chunk(h, own, wblk, &hsrc)) return 1;
+      }
+      CK(cudaEventRecord(h->ev[3], h->stream));
+      // ---------------- third quarter of the chunk, accumulated into T3 (own slots) ----------------
+      if (nmine > 0) {
+        // rows of hsrc are numbered from this rank's first slot when the data came through the exchange
+        AoSource src2 = hsrc;
+        int lo = s_lo, hi = s_hi;
+        if (G > 1) { lo = 0; hi = nmine; }
+        if (second_half_partial(h, pl, src2, ck, lo, hi, h->T3.as<double>() + (G > 1 ? 0 : 0), ldt2)) return 1;
+        const double nrw = n2 - ck.p0, pc = ck.p1 - ck.p0, ncv = n2 - ck.p1;
+        flops += 2.0 * (double)nmine * nf2 * (nrw * pc + pc * ncv);
+      }
+      CK(cudaEventRecord(h->ev[4], h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      prof_drain(h);
+      float ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_first += ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); ms_exch += ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); ms_second += ms;
+    }
+    // ---------------- fourth quarter (E.f90:1230-1239) + consumer, in groups of whole f-blocks ----------------
     CK(cudaEventRecord(h->ev[1], h->stream));
-    // ---------------- exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203) -------
-    const double *H2 = h->H.as<double>();
-    int64_t ldh2 = ldh;
-    int slot_lo = 0, slot_hi = pt.nslots;
-    if (h->nranks > 1) {
-      if (exchange_h(h, pt.nslots, nloc, pl.nslabs1, &H2, &ldh2, &slot_lo, &slot_hi)) return 1;
+    float ms_consume = 0;
+    if (nmine > 0) {
+      const int fr_lo = (int)((int64_t)nfb * h->rank / G), fr_hi = (int)((int64_t)nfb * (h->rank + 1) / G);
+      const int64_t out_slots_cap = download ? nmine : std::max<int64_t>(pl.max_slots_per_f, (int64_t)(out_need / (per_out * 8.0)));
+      CK(h->OUT.ensure(std::max<size_t>((size_t)out_slots_cap * per_out, 1) * sizeof(double)));
+      for (int fa = fr_lo; fa < fr_hi;) {
+        int fb = fa + 1;
+        while (fb < fr_hi && pt.fbeg[fb + 1] - pt.fbeg[fa] <= out_slots_cap) ++fb;
+        const int g_lo = pt.fbeg[fa], g_hi = pt.fbeg[fb], gn = g_hi - g_lo;
+        fa = fb;
+        if (gn <= 0) continue;
+        const double *T3g = h->T3.as<double>() + (int64_t)(g_lo - s_lo) * nf2 * ldt2;
+        double *OUT = h->OUT.as<double>();
+        // batches bounded by the GEMM grid (N dimension = slots * nf2)
+        const int64_t Bq = std::max<int64_t>(1, std::min<int64_t>(gn, (int64_t)2000000000 / std::max(nf2, 1) / 64));
+        for (int64_t s = 0; s < gn; s += Bq) {
+          const int64_t bs = std::min<int64_t>(Bq, gn - s);
+          GemmArgs g{h2.C + (int64_t)(h2.ls - 1) * h2.ldc, T3g + s * nf2 * ldt2, ns2, (int)(bs * nf2), n2, h2.ldc, ldt2, 0, 0};
+          ProfScope ps(h, 5, 2.0 * bs * n2 * (double)ns2 * nf2);
+          CK(launch_gemm(h, g, EpiOut{OUT + s * per_out, ns2, nf2}));
+        }
+        flops += 2.0 * (double)gn * n2 * (double)ns2 * nf2;
+        if (!download) {
+          ReduceArgs ra{};
+          ra.OUT = OUT; ra.nslots = gn; ra.ns2 = ns2; ra.nf2 = nf2; ra.slot_base = g_lo;
+          ra.slot_s = h->ss.as<int32_t>() + g_lo; ra.slot_f = h->sf.as<int32_t>() + g_lo;
+          ra.slot_table = h->tab.as<int32_t>(); ra.nfb = nfb;
+          ra.orb_s1 = h1.ls; ra.orb_f1 = h1.lf + f0; ra.orb_s2 = h2.ls; ra.orb_f2 = h2.lf;
+          ra.epsA = cons.epsA; ra.epsB = cons.epsB;
+          ra.exchange = (pl.intra && h1.ls == h2.ls && h1.ns == h2.ns && h1.lf == h2.lf && h1.nf == h2.nf &&
+                         pl.win[0] == pl.win[4] && pl.win[2] == pl.win[6]) ? 1 : 0;
+          ra.lambda = cons.lambda; ra.tol = cons.tol;
+          ProfScope ps(h, 6, (double)gn * per_out * 8.0);
+          reduce_block_kernel<<<148 * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
+          h->launches += 1;
+          CK(cudaGetLastError());
+        }
+      }
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
-    // ---------------- second half (E.f90:1178-1260), slots [slot_lo, slot_hi) -----------------
-    const int nsl = slot_hi - slot_lo;
-    const int64_t per = (int64_t)h2.ns * h2.nf;
-    CK(h->OUT.ensure(std::max<size_t>((size_t)std::max(nsl, 1) * per, 1) * sizeof(double)));
-    if (nsl > 0) {
-      AoSource hsrc{SRC_RECT, H2, pl.nslabs1, ldh2, 0, 0};
-      double *OUT = h->OUT.as<double>();
-      const int ns2 = h2.ns, nf2 = h2.nf;
-      auto mk = [&](int64_t s, int64_t) { return EpiOut{OUT + s * per, ns2, nf2}; };
-      if (run_half(h, hsrc, 0, nsl, h2, 0, h2.nf, mk, 3)) return 1;
-      flops += 2.0 * h2.nc * h2.nf * ((double)h2.nc + h2.ns) * (double)nsl;
-    }
-    CK(cudaEventRecord(h->ev[3], h->stream));
-    // ---------------- consume ------------------------------------------------------------------
-    if (nsl > 0 && cons.mode == 0) {
+    if (nmine > 0 && download) {
       SelectArgs sa{};
-      sa.OUT = h->OUT.as<double>(); sa.slot0 = slot_lo; sa.nslots_batch = nsl; sa.ns2 = h2.ns; sa.nf2 = h2.nf;
+      sa.OUT = h->OUT.as<double>(); sa.order = h->order.as<int32_t>(); sa.nslots_batch = nmine; sa.ns2 = ns2; sa.nf2 = nf2;
       sa.swap2 = h2.first_is_conv_second ? 0 : 1;
       sa.n_outer = std::max(0, pl.win[5] - pl.win[4] + 1); sa.n_inner = std::max(0, pl.win[7] - pl.win[6] + 1);
       sa.lo_outer = pl.win[4]; sa.lo_inner = pl.win[6];
       sa.conv = pl.conv; sa.symmetric = pl.symmetric; sa.intra = pl.intra ? 1 : 0;
       sa.slot_a = h->sa.as<int32_t>(); sa.slot_b = h->sb.as<int32_t>();
       sa.nA = h->sp[pl.a].n; sa.nB = h->sp[pl.b].n; sa.tol = cons.tol;
-      const int64_t ncand = (int64_t)nsl * sa.n_outer * sa.n_inner;
+      const int64_t ncand = (int64_t)nmine * sa.n_outer * sa.n_inner;
       const int64_t nblk = ceil_div(ncand, SEL_CHUNK);
       if (nblk > 0) {
         if (nblk > 2147483647LL) return fail(h, "too many candidates for one download; use the streaming form");
@@ -433,26 +640,16 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         CK(cudaGetLastError());
       }
       h->res_conv = pl.conv;
-    } else if (nsl > 0) {
-      ReduceArgs ra{};
-      ra.OUT = h->OUT.as<double>(); ra.nslots = nsl; ra.ns2 = h2.ns; ra.nf2 = h2.nf;
-      ra.slot_s = h->ss.as<int32_t>() + slot_lo; ra.slot_f = h->sf.as<int32_t>() + slot_lo;
-      ra.slot_table = h->tab.as<int32_t>(); ra.nfb = nfb;
-      ra.orb_s1 = h1.ls; ra.orb_f1 = h1.lf + f0; ra.orb_s2 = h2.ls; ra.orb_f2 = h2.lf;
-      ra.epsA = cons.epsA; ra.epsB = cons.epsB;
-      ra.exchange = (pl.intra && h->nranks == 1 && h1.ls == h2.ls && h1.ns == h2.ns && h1.lf == h2.lf && h1.nf == h2.nf &&
-                     pl.win[0] == pl.win[4] && pl.win[2] == pl.win[6]) ? 1 : 0;
-      ra.lambda = cons.lambda; ra.tol = cons.tol;
-      ProfScope ps(h, 6, (double)nsl * per * 8.0);
-      reduce_block_kernel<<<148 * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
-      h->launches += 1;
-      CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     prof_drain(h);
-    float ms;
-    for (int t = 0; t < 4; ++t) { CK(cudaEventElapsedTime(&ms, h->ev[t], h->ev[t + 1])); h->timers[1 + t] += ms * 1e-3; }
+    {
+      float ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_second += ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); ms_consume += ms;
+    }
+    h->timers[1] += ms_first * 1e-3; h->timers[2] += ms_exch * 1e-3; h->timers[3] += ms_second * 1e-3; h->timers[4] += ms_consume * 1e-3;
   }
   if (cons.mode == 1 && sums_out) {
     CK(cudaMemcpyAsync(sums_out, h->sums.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -463,41 +660,25 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
   return 0;
 }
 
-// All-to-all of the half-transformed block between the halves.  Every rank holds
-// H[slot][its own AO-pair columns]; afterwards it holds, for its own block of slots, all columns,
-// as nranks column blocks H2[g][slot_local][col_local(g)] laid one after the other, which the
-// second-half unpack reads as a rectangular source with ld = total padded width by first
-// transposing the blocks into place with cudaMemcpy2DAsync.
-int exchange_h(lowdin_it_handle h, int nslots, int64_t ncols_local, int64_t ncols_total, const double **src_out, int64_t *ld_out,
-               int *slot_lo, int *slot_hi) {
+// All-to-all of one chunk of the half-transformed block between the halves.  Every rank holds
+// H[slot][its own wblk columns of the chunk] for ALL slots; afterwards it holds, for ITS slots, all columns as G
+// blocks [g][slot_local][wblk], which the chunk expansion reads in place (SRC_RECT_BLOCKED).
+int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out) {
   const int G = h->nranks;
-  const int64_t wblk = ceil_div(ncols_total, G);
-  const int sblk = (int)ceil_div(nslots, G);
-  const int lo = std::min(nslots, sblk * h->rank), hi = std::min(nslots, lo + sblk);
-  *slot_lo = lo; *slot_hi = hi;
-  const int mine = hi - lo;
   if (!h->comm) return fail(h, "multi-GPU transform without a communicator");
-  // receive staging: for peer g a [mine][wblk] block; final layout [mine][G*wblk]
-  CK(h->dtmp.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
+  const int mine = own[h->rank + 1] - own[h->rank];
   CK(h->H2.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
   int rc = g_nccl.GroupStart();
   for (int g = 0; g < G && rc == 0; ++g) {
-    const int glo = std::min(nslots, sblk * g), ghi = std::min(nslots, glo + sblk);
-    const size_t send_n = (size_t)(ghi - glo) * wblk;   // rows glo..ghi of H (row stride wblk)
+    const size_t send_n = (size_t)(own[g + 1] - own[g]) * wblk;   // rows own[g]..own[g+1] of H (row stride wblk)
     const size_t recv_n = (size_t)mine * wblk;
-    if (send_n) rc = g_nccl.Send(h->H.as<double>() + (size_t)glo * wblk, send_n * sizeof(double), /*ncclChar*/ 0, g, h->comm, h->stream);
-    if (rc == 0 && recv_n) rc = g_nccl.Recv(h->dtmp.as<double>() + (size_t)g * mine * wblk, recv_n * sizeof(double), 0, g, h->comm, h->stream);
+    if (send_n) rc = g_nccl.Send(h->H.as<double>() + (size_t)own[g] * wblk, send_n * sizeof(double), /*ncclChar*/ 0, g, h->comm, h->stream);
+    if (rc == 0 && recv_n) rc = g_nccl.Recv(h->H2.as<double>() + (size_t)g * mine * wblk, recv_n * sizeof(double), 0, g, h->comm, h->stream);
   }
   if (rc == 0) rc = g_nccl.GroupEnd();
   if (rc != 0) return fail(h, std::string("NCCL all-to-all failed: ") + g_nccl.GetErrorString(rc));
-  for (int g = 0; g < G; ++g)
-    if (mine)
-      CK(cudaMemcpy2DAsync(h->H2.as<double>() + (size_t)g * wblk, (size_t)G * wblk * sizeof(double),
-                           h->dtmp.as<double>() + (size_t)g * mine * wblk, (size_t)wblk * sizeof(double),
-                           (size_t)wblk * sizeof(double), (size_t)mine, cudaMemcpyDeviceToDevice, h->stream));
-  (void)ncols_local;
-  *src_out = h->H2.as<double>();
-  *ld_out = (int64_t)G * wblk;
+  h->launches += 1;
+  *src_out = AoSource{SRC_RECT_BLOCKED, h->H2.as<double>(), src_out->M, wblk, (int64_t)mine, 0};
   return 0;
 }
 
@@ -539,7 +720,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.pi.release(); s.pj.release(); }
   for (auto &row : h->ao) for (auto &a : row) a.data.release();
-  DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->tab, &h->sa, &h->sb,
+  DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
@@ -647,11 +828,11 @@ int lowdin_it_transform(lowdin_it_handle h, int a, int b, const int win[8], int 
   if (build_plan(h, a, b, win, conv, symmetric, pl)) return 1;
   Consumer cons; cons.mode = 0; cons.tol = drop_tol;
   if (h->nranks > 1) return fail(h, "lowdin_it_transform is single-GPU; use lowdin_it_transform_stream on a communicator");
-  // download mode keeps the whole dense result block: check that it fits
+  // download mode keeps the dense result block of every window pair and the third-quarter accumulators: check that they fit
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const double need = ((double)pl.pairs_s.size() * ((double)pl.nslabs1 + (double)pl.h2.ns * pl.h2.nf)) * 8.0;
-  if (need > 0.9 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap))
+  const double need = (double)pl.pairs_s.size() * ((double)pl.h2.ns * pl.h2.nf + (double)pl.h2.nf * roundup2(pl.h2.nc)) * 8.0;
+  if (need > 0.8 * ((double)free_b + (double)h->T3.cap + (double)h->OUT.cap + (double)h->H.cap))
     return fail(h, "result block does not fit in device memory; use lowdin_it_transform_stream");
   return run_passes(h, pl, 0, 0, 0, cons, nullptr);
 }
@@ -699,18 +880,25 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
 }
 
 static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int *used) {
-  int nf = std::max(pl.h1.nf, 1);
+  const int nf = std::max(pl.h1.nf, 1);
   if (requested > 0) { *used = std::min(requested, nf); return 0; }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  double avail = 0.85 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->dtmp.cap) -
-                 3.0 * (double)h->workspace_bytes;
-  // bytes per first-window value: slots per value (<= ns1) x (H row + OUT block), H row split over the ranks
-  const double hrow = (double)ceil_div(pl.nslabs1, h->nranks) * (h->nranks > 1 ? 3.0 : 1.0);
-  const double per_f = (double)pl.h1.ns * (hrow + (double)pl.h2.ns * pl.h2.nf / h->nranks) * 8.0;
-  int qb = (int)std::max(1.0, std::min((double)nf, avail / std::max(per_f, 1.0)));
-  if (qb >= 8 && qb < nf) qb &= ~7;  // DMMA n-tile granularity
-  *used = qb;
+  const int G = h->nranks;
+  const double spf = std::max(pl.max_slots_per_f, 1);
+  const double per_out = (double)pl.h2.ns * pl.h2.nf * 8.0;
+  const double out_need = std::max(std::min(4.0e9, spf * per_out * nf), spf * per_out);
+  const double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->T3.cap +
+                               (double)h->X.cap + (double)h->T1t.cap) - 2.0 * (double)h->workspace_bytes - out_need - (double)((size_t)1 << 30);
+  // per first-window value: third-quarter accumulators of its slots (own share) + a chunk of at least 8 pair rows of H
+  const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
+  const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
+  const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
+  int qmax = (int)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f)));
+  const int passes = (int)ceil_div(nf, qmax);
+  int qb = (int)ceil_div(nf, passes);
+  if (qb > 8 && qb < nf) { const int q8 = (qb + 7) & ~7; if (q8 <= qmax) qb = q8; }  // DMMA n-tile granularity
+  *used = std::min(qb, nf);
   return 0;
 }
 
@@ -749,6 +937,19 @@ int lowdin_it_transform_stream(lowdin_it_handle h, int a, int b, const int win[8
     } else cons.epsB = cons.epsA;
   }
   return run_passes(h, pl, used, first_pass, n_passes, cons, sums);
+}
+
+int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
+  if (!h) return 1;
+  switch (option) {
+    case LOWDIN_IT_OPT_WORKSPACE_BYTES:
+      if (value < (1 << 16)) return fail(h, "workspace too small");
+      h->workspace_bytes = (size_t)value; return 0;
+    case LOWDIN_IT_OPT_CHUNK_COLS:
+      if (value < 0) return fail(h, "negative chunk column limit");
+      h->chunk_cols_limit = value; return 0;
+    default: return fail(h, "unknown option");
+  }
 }
 
 int lowdin_it_set_profiling(lowdin_it_handle h, int on) {
@@ -869,10 +1070,10 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
       CK(cudaMemsetAsync(h->H.p, 0, cnt * sizeof(double), h->stream));
       src.data = h->H.as<double>();
     }
-    dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)n);
-    expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, 0, nc, (int)ldx, h->X.as<double>());
+    if (launch_expand(h, src, 0, n, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
     CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < iters; ++i) expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(src, 0, nc, (int)ldx, h->X.as<double>());
+    for (int i = 0; i < iters; ++i)
+      if (launch_expand(h, src, 0, n, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -923,9 +1124,7 @@ int lowdin_it_debug_expand(lowdin_it_handle h, int a, int b, int64_t slab0, int 
   CK(cudaSetDevice(h->device));
   const int nc = h->sp[a].n; const int64_t ldx = roundup2(nc);
   CK(h->X.ensure((size_t)nb * nc * ldx * sizeof(double)));
-  dim3 grid((unsigned)ceil_div((int64_t)nc * (ldx / 2), 256), (unsigned)nb);
-  expand_slabs_kernel<<<grid, 256, 0, h->stream>>>(h->ao[a][b].src, slab0, nc, (int)ldx, h->X.as<double>());
-  CK(cudaGetLastError());
+  if (launch_expand(h, h->ao[a][b].src, slab0, nb, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
   CK(cudaMemcpy2DAsync(X, (size_t)nc * 8, h->X.p, ldx * 8, (size_t)nc * 8, (size_t)nb * nc, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

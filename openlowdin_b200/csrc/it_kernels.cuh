@@ -1,6 +1,7 @@
 // it_kernels.cuh -- sm_100a device kernels of the four-index AO->MO transformation.
 //
-//   expand_slabs_kernel   packed / rectangular / generated AO slab  ->  dense symmetric N x N
+//   expand_block_kernel   packed / rectangular / generated AO slab  ->  dense symmetric N x N (or a block of it)
+//   q1_gen_kernel         generated AO slab x coefficient window, the slab produced in registers (no HBM, no smem)
 //                         (the "unpack" of TransformIntegralsE.f90:1047-1063, :1623-1630; HBM bound)
 //   dgemm_tn_kernel       C[m][n] = sum_k A[m][k] B[n][k]   FP64 tensor cores (DMMA.8x8x4 via
 //                         mma.sync.m8n8k4.f64), cp.async multi-stage shared-memory pipeline,
@@ -26,7 +27,9 @@ enum SrcKind : int {
   SRC_SYM_PACKED = 0,  // intra, C/E layout: row lo holds hi = lo..M-1 at lo*M - lo(lo+1)/2 + hi  (C.f90:223-226, :267-271)
   SRC_RECT = 1,        // data[slab*ld + pair]   (inter AO storage (rs-1)*M_a+pq, C.f90:882; and the half-transformed H)
   SRC_HASH_SYM = 2,    // generated, key = hi*M + lo
-  SRC_HASH_RECT = 3    // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
+  SRC_HASH_RECT = 3,   // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
+  SRC_RECT_BLOCKED = 4 // data[((pair/ld)*aux + slab)*ld + pair%ld]: the half-transformed chunk as it arrives from the
+                       // all-to-all, one [slots][ld] block per sending rank (aux = slots per block)
 };
 
 struct AoSource {
@@ -56,6 +59,10 @@ __device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, in
     }
     case SRC_RECT:
       return __ldg(src.data + (slab * src.ld + pair));
+    case SRC_RECT_BLOCKED: {
+      int64_t blk = pair / src.ld;
+      return __ldg(src.data + ((blk * src.aux + slab) * src.ld + (pair - blk * src.ld)));
+    }
     case SRC_HASH_SYM: {
       int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
       return hash_value(src.seed, (uint64_t)(hi * src.M + lo));
@@ -72,21 +79,53 @@ __host__ __device__ __forceinline__ int64_t pair0(int64_t i, int64_t j, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Slab expansion: X[b][mu][nu] = AO(slab_list[b] or slab0+b ; pair(mu,nu)),   ldx >= n
-// One thread per two adjacent nu (16-byte stores).  grid = (ceil(n*ldx/2 / 256), B)
+// Slab expansion (the unpack of E.f90:1047-1063 / :1623-1630), block form:
+//   X[b][row][col] = AO(slab0+b ; pair(r0+row, c0+col) - colbase),  row < nrows, col < ncols, ldx >= ncols (even)
+// The full slab is (r0,c0,nrows,ncols) = (0,0,n,n); the chunked second half expands only the rows/columns a
+// chunk of AO-pair rows touches.  One CTA per 32x32 tile per slab: tiles of the upper triangle are read along
+// the column index (contiguous in the packed row), tiles of the lower triangle along the ROW index (the
+// transposed element (col,row) is contiguous in row) and turned in shared memory, so both triangles are read
+// with full 32-byte sectors; the tile is written back with 16-byte stores.
+// grid = (ceil(ldx/32), ceil(nrows/32), B), block = 256.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expand_slabs_kernel(AoSource src, int64_t slab0, int n, int ldx, double *__restrict__ X) {
-  const int64_t b = blockIdx.y;
+__global__ void __launch_bounds__(256) expand_block_kernel(AoSource src, int64_t slab0, int n, int r0, int nrows, int c0, int ncols,
+                                                          int64_t colbase, int ldx, double *__restrict__ X) {
+  __shared__ double tile[32][33];
+  const int64_t b = blockIdx.z;
   const int64_t slab = slab0 + b;
-  const int half = ldx >> 1;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (int64_t)n * half) return;
-  const int mu = (int)(e / half);
-  const int nu = (int)(e % half) * 2;
-  double2 v;
-  v.x = (nu < n) ? ao_value(src, slab, pair0(mu, nu, n)) : 0.0;
-  v.y = (nu + 1 < n) ? ao_value(src, slab, pair0(mu, nu + 1, n)) : 0.0;
-  *reinterpret_cast<double2 *>(X + ((b * n + mu) * (int64_t)ldx + nu)) = v;
+  const int tr0 = blockIdx.y * 32, tc0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grow0 = r0 + tr0, gcol0 = c0 + tc0;
+  if (grow0 >= gcol0 + 31) {
+    // strictly-lower tile: element (row,col) lives at pair(col,row) = base(col) + row - col  -> lanes along rows
+    const int row = grow0 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = warp + 8 * k, col = gcol0 + c;
+      double v = 0.0;
+      if (tr0 + lane < nrows && tc0 + c < ncols) v = ao_value(src, slab, pair0(col, row, n) - colbase);
+      tile[lane][c] = v;
+    }
+  } else {
+    const int col = gcol0 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = warp + 8 * k, row = grow0 + r;
+      double v = 0.0;
+      if (tr0 + r < nrows && tc0 + lane < ncols) v = ao_value(src, slab, pair0(row, col, n) - colbase);
+      tile[r][lane] = v;
+    }
+  }
+  __syncthreads();
+  const int cp = (threadIdx.x & 15) * 2, rr = threadIdx.x >> 4;  // 16 column pairs x 16 rows per sweep
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = rr + 16 * k;
+    if (tr0 + r < nrows && tc0 + cp < ldx) {
+      double2 v = make_double2(tile[r][cp], tile[r][cp + 1]);
+      *reinterpret_cast<double2 *>(X + ((b * nrows + tr0 + r) * (int64_t)ldx + tc0 + cp)) = v;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,27 +180,39 @@ struct EpiPlain {  // C[z][m][n]
   double *C; int64_t ldc, strideC;
   __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { C[z * strideC + (int64_t)m * ldc + n] = v; }
 };
-// First quarter: m = (z, mu) over the stacked slabs of a batch, n = if (first-contracted window)
-//   T1t[z][if][mu]  (mu contiguous so the second quarter reads K-contiguous rows)
+// First quarter: m = (z, mu) over the bc stacked slabs of a batch, n = f (first-contracted window)
+//   T1t[f][z][mu]  (mu contiguous: the second quarter reads K-contiguous rows; z inside f so that the
+//   second quarter's output columns for one window pair are consecutive AO-pair slabs)
 struct EpiQ1 {
-  double *T1t; int nc; int nf; int64_t ldt;
+  double *T1t; int nc; int bc; int64_t ldt;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int zz = m / nc, mu = m - zz * nc;
-    T1t[((int64_t)zz * nf + n) * ldt + mu] = v;
+    T1t[((int64_t)n * bc + zz) * ldt + mu] = v;
   }
 };
-// Second quarter of a first half: m = is (second-contracted window), n = (z, if).
-// T2 -> H[slot(is,if)][s0+z], keeping only window pairs (slot >= 0) and, for transformer E
-// semantics, zeroing |t| <= tol (E.f90:1113).  tol < 0 keeps everything.
+// Second quarter of a first half: m = is (second-contracted window), n = (f, z).
+// T2 -> H[slot(is,f)][col0+z], keeping only window pairs (slot >= 0) and, for transformer E
+// semantics, zeroing |t| <= tol (E.f90:1113).  tol < 0 keeps everything.  Consecutive n are consecutive
+// columns of one H row: 64-byte runs per 8x8 accumulator tile.
 struct EpiScatterH {
-  double *H; int64_t ldh; int64_t col0; const int32_t *slot; int nf; double tol;
+  double *H; int64_t ldh; int64_t col0; const int32_t *slot; int nf; int bc; double tol;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
-    int zz = n / nf, jf = n - zz * nf;
-    int sl = __ldg(slot + (int64_t)m * nf + jf);
+    int f = n / bc, zz = n - f * bc;
+    int sl = __ldg(slot + (int64_t)m * nf + f);
     if (sl >= 0) H[(int64_t)sl * ldh + col0 + zz] = (fabs(v) > tol) ? v : 0.0;
   }
 };
-// Fourth quarter: m = ks, n = (z, kf)  ->  OUT[slot0+z][ks][kf]
+// Third quarter, chunked: m = (z, row) over `nrows` rows of each slot's expanded block, n = kf.
+//   T3[slot0+z][kf][roff+row] += v   (accumulated over the AO-pair chunks; mu contiguous for the fourth quarter)
+struct EpiAccT {
+  double *T3; int nrows; int roff; int nf2; int64_t ldt;
+  __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
+    int zz = m / nrows, r = m - zz * nrows;
+    double *p = T3 + (((int64_t)zz * nf2 + n) * ldt + roff + r);
+    *p += v;
+  }
+};
+// Fourth quarter: m = ks, n = (z, kf)  ->  OUT[z][ks][kf]
 struct EpiOut {
   double *OUT; int ns2, nf2;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
@@ -261,12 +312,129 @@ __global__ void __launch_bounds__(WM *WN * 32) dgemm_tn_kernel(GemmArgs g, Epi e
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused slab generation + first quarter for GENERATED AO sources (SRC_HASH_*):
+//   T1t[f][z][mu] = sum_nu AO(slab0+z ; pair(mu,nu)) * C(nu, f)          (E.f90:1047-1090 in one kernel)
+// The dense N x N slab never exists: every lane produces its own DMMA A-fragment element
+// (row = mu, k = nu) straight into a register from the counter hash, so neither HBM nor shared memory
+// carries the expanded slab.  Only the coefficient window (the B operand, L2 resident) is staged through a
+// cp.async shared-memory ring.  CTA = 8 warps x 16 rows = 128 rows of one slab, all BN = 8*TN window columns.
+// grid = (ceil(nc/128), bc)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gen_value(const AoSource &src, uint32_t slab, uint32_t mu, uint32_t nu, uint32_t n) {
+  const uint32_t lo = min(mu, nu), hi = max(mu, nu);
+  const uint32_t pair = lo * n - ((lo * (lo - 1u)) >> 1) + (hi - lo);  // (lo*(lo-1)) is even; lo=0 wraps to 0*... = 0
+  uint64_t key;
+  if (src.kind == SRC_HASH_SYM) {
+    const uint32_t a = min(slab, pair), b = max(slab, pair);
+    key = (uint64_t)b * (uint64_t)src.M + a;
+  } else {
+    key = (uint64_t)pair * (uint64_t)src.aux + slab;
+  }
+  return hash_value(src.seed, key);
+}
+
+template <int TN, int STAGES>
+__global__ void __launch_bounds__(256) q1_gen_kernel(AoSource src, int64_t slab0, int bc, int nc, const double *__restrict__ Cf,
+                                                     int64_t ldc, int nfb, double *__restrict__ T1t, int64_t ldt) {
+  constexpr int BN = TN * 8, BK = 16, LDS = BK + 4, NT = 256, TM = 2;
+  extern __shared__ __align__(16) double smem[];  // [STAGES][BN][LDS]
+  const int z = blockIdx.y;
+  const uint32_t slab = (uint32_t)(slab0 + z);
+  const int m0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int KT = (nc + BK - 1) / BK;
+  const uint32_t n = (uint32_t)nc;
+
+  auto load_b = [&](int stage, int kt) {
+    const int k0 = kt * BK;
+    double *bs = smem + stage * BN * LDS;
+    for (int c = tid; c < BN * (BK / 2); c += NT) {
+      int row = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+      int gk = k0 + kc;
+      int valid = (row < nfb) ? min(max(nc - gk, 0), 2) : 0;
+      const double *g = Cf + (int64_t)(row < nfb ? row : 0) * ldc + (valid ? gk : 0);
+      cp_async16(bs + row * LDS + kc, g, valid * 8);
+    }
+  };
+
+  uint32_t mu[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) mu[i] = (uint32_t)(m0 + warp * 16 + i * 8 + grp);
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_b(s, s);
+    cp_async_commit();
+  }
+  // A fragments of k-tile 0
+  double a_nxt[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) a_nxt[i][kk] = gen_value(src, slab, min(mu[i], n - 1u), min((uint32_t)(kk * 4 + tig), n - 1u), n);
+
+  for (int kt = 0; kt < KT; ++kt) {
+    double a_cur[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) a_cur[i][kk] = a_nxt[i][kk];
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + STAGES - 1;
+      if (nk < KT) load_b(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    // generate the next k-tile's fragments while this tile's DMMAs are in flight (k beyond nc multiplies zero-filled B)
+    if (kt + 1 < KT) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          a_nxt[i][kk] = gen_value(src, slab, min(mu[i], n - 1u), min((uint32_t)((kt + 1) * BK + kk * 4 + tig), n - 1u), n);
+    }
+    const double *bs = smem + (kt % STAGES) * BN * LDS + grp * LDS + tig;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      double b[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = bs[j * 8 * LDS + kk * 4];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a_cur[i][kk], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + warp * 16 + i * 8 + grp;
+    if (m >= nc) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int f = j * 8 + tig * 2;
+      if (f < nfb) T1t[((int64_t)f * bc + z) * ldt + m] = acc[i][j][0];
+      if (f + 1 < nfb) T1t[((int64_t)(f + 1) * bc + z) * ldt + m] = acc[i][j][1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Result selection / compaction.  Candidates are enumerated in the reference's loop order:
 // slot (the (i,j) or (p,q) pair, ijmap order), then the outer index of the second pair, then the inner.
 // ---------------------------------------------------------------------------------------------
 struct SelectArgs {
-  const double *OUT;    // [nslots_batch][ns2][nf2]
-  int64_t slot0;        // first slot of this batch
+  const double *OUT;    // [nslots][ns2][nf2], indexed by slot
+  const int32_t *order; // slots in the reference's loop order (convention order -> slot)
   int nslots_batch;
   int ns2, nf2;         // extents of OUT's two trailing dims (second-contracted, first-contracted window)
   int swap2;            // 0: outer loop index of the convention == OUT's ns2 dim; 1: == nf2 dim
@@ -281,11 +449,12 @@ struct SelectArgs {
 
 __device__ __forceinline__ bool select_candidate(const SelectArgs &a, int64_t c, double &v, int &slot, int &o, int &in) {
   const int64_t per = (int64_t)a.n_outer * a.n_inner;
-  slot = (int)(c / per);
-  const int rem = (int)(c % per);
+  const int kk = (int)(c / per);
+  const int rem = (int)(c - (int64_t)kk * per);
+  slot = __ldg(a.order + kk);
   o = rem / a.n_inner + a.lo_outer;
   in = rem % a.n_inner + a.lo_inner;
-  const int64_t gs = a.slot0 + slot;
+  const int64_t gs = slot;
   bool keep;
   if (a.conv == 1) keep = (in <= o);  // klmap: l <= k   (E.f90:901-907)
   else {
@@ -376,7 +545,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(SelectArgs a, 
     if (keep) {
       const int64_t pos = blockoff[blockIdx.x] + rb + pre + __popc(bal & ((1u << lane) - 1u));
       if (pos < e.capacity) {
-        const int64_t gs = a.slot0 + s;
+        const int64_t gs = s;
         e.o_v[pos] = v;
         if (a.conv == 1) {
           e.o_ij[pos] = pair0(a.slot_a[gs] - 1, a.slot_b[gs] - 1, a.nA) + 1;
@@ -400,8 +569,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_emit_kernel(SelectArgs a, 
 // sums: [0]=count, [1]=sum, [2]=sum sq, [3]=energy   (double atomics, order non-deterministic)
 // ---------------------------------------------------------------------------------------------
 struct ReduceArgs {
-  const double *OUT;                // [nslots][ns2][nf2], all slots of the pass
-  int nslots, ns2, nf2;
+  const double *OUT;                // [nslots][ns2][nf2]: the slots [slot_base, slot_base+nslots) of the pass (whole f-blocks)
+  int nslots, ns2, nf2, slot_base;
   const int32_t *slot_s, *slot_f;   // per pass-local slot: index in the second / first window of the first pair
   const int32_t *slot_table;        // [ns1][nfb] -> pass-local slot or -1
   int nfb;
@@ -426,8 +595,8 @@ __global__ void __launch_bounds__(256) reduce_block_kernel(ReduceArgs a, double 
       const int o1s = a.orb_s1 + i2, o1f = a.orb_f1 + i1, o2s = a.orb_s2 + k2, o2f = a.orb_f2 + k1;
       const double den = a.epsA[min(o1s, o1f) - 1] + a.epsB[min(o2s, o2f) - 1] - a.epsA[max(o1s, o1f) - 1] - a.epsB[max(o2s, o2f) - 1];
       if (a.exchange) {
-        const int xs = a.slot_table[(int64_t)k2 * a.nfb + i1];   // slot of (second=k2, first=i1)
-        const double xe = (xs >= 0) ? a.OUT[(int64_t)xs * per + (int64_t)i2 * a.nf2 + k1] : 0.0;
+        const int xs = a.slot_table[(int64_t)k2 * a.nfb + i1] - a.slot_base;   // slot of (second=k2, first=i1): same f-block
+        const double xe = (xs >= 0 && xs < a.nslots) ? a.OUT[(int64_t)xs * per + (int64_t)i2 * a.nf2 + k1] : 0.0;
         en += x * (a.lambda * x - xe) / den;
       } else {
         en += x * x / den;

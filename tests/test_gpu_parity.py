@@ -214,3 +214,103 @@ def test_empty_ao_list_gives_no_integrals(O, T):
     T.upload_ao(0, 0, e, e, e, e, np.zeros(0))
     ij, kl, v = T.transform(0, 0, [1, n, 1, n, 1, n, 1, n], ol.CONV_E)
     assert len(v) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# chunked second half (third-quarter accumulation over chunks of AO-pair rows) and the fused
+# generation + first-quarter kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture
+def chunked(T):
+    """Force many small chunks (the large-N code path) for the duration of one test."""
+    def _set(cols):
+        T.set_option(T.OPT_CHUNK_COLS, cols)
+    yield _set
+    T.set_option(T.OPT_CHUNK_COLS, 0)
+
+
+@pytest.mark.parametrize("cols", [1, 40, 100])
+@pytest.mark.parametrize("n,occ,mode", [(19, 5, "MP2"), (19, 5, "MP2-PT2"), (13, 4, "ALLACTIVE")])
+def test_chunked_second_half_e_intra(O, T, chunked, n, occ, mode, cols):
+    packed, Cm = _intra_setup(O, T, n, 900 + n)
+    win = O.windows_e_intra(mode, n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    chunked(cols)
+    ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+    M = O.npairs(n)
+    assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
+    assert_lists_match((ij, kl), v, (rij, rkl), rv)
+    if len(v) == len(rv):
+        assert np.array_equal(ij, rij) and np.array_equal(kl, rkl)
+
+
+@pytest.mark.parametrize("cols", [1, 30])
+def test_chunked_second_half_c_and_inter(O, T, chunked, cols):
+    n, occ = 14, 4
+    packed, Cm = _intra_setup(O, T, n, 77)
+    win, sym = O.windows_c_intra("MP2", n, occ)
+    ref = O.transform_c_intra(Cm, packed, win, sym)
+    chunked(cols)
+    got = T.transform(0, 0, win, ol.CONV_C, symmetric=sym)
+    assert np.abs(dense_quads(*got, n, n) - dense_quads(*ref, n, n)).max() <= TOL
+    assert_lists_match(got[:4], got[4], ref[:4], ref[4])
+    na, nb = 11, 9
+    rect, Ca, Cb = _inter_setup(O, T, na, nb, 31)
+    win = O.windows_e_inter("MP2", na, nb, 3, 2)
+    rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, win)
+    ij, kl, v = T.transform(0, 1, win, ol.CONV_E)
+    Ma, Mb = O.npairs(na), O.npairs(nb)
+    assert np.abs(dense_pairs(ij, kl, v, Ma, Mb) - dense_pairs(rij, rkl, rv, Ma, Mb)).max() <= TOL
+
+
+@pytest.mark.parametrize("n,win", [(19, [6, 19, 1, 5, 6, 19, 1, 5]), (23, [1, 23, 1, 23, 1, 23, 1, 23]), (37, [12, 37, 1, 11, 12, 37, 1, 11]),
+                                   (70, [1, 70, 1, 1, 1, 70, 1, 70]), (70, [66, 70, 1, 65, 1, 3, 1, 2])])
+def test_generated_source_fused_first_quarter(O, T, n, win):
+    """Slabs generated inside the first-quarter kernel (no dense slab in memory) == uploaded list + expansion."""
+    seed = 4242 + n
+    packed = O.hash_packed_intra(seed, n)
+    Cm = O.random_orthonormal(n, n)
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, seed)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+    M = O.npairs(n)
+    assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
+    assert_lists_match((ij, kl), v, (rij, rkl), rv)
+
+
+def test_generated_source_inter_and_chunked_stream(O, T, chunked):
+    na, nb, oa, ob = 21, 16, 5, 2
+    seed = 99
+    rect = O.hash_rect_inter(seed, na, nb)
+    Ca, Cb = O.random_orthonormal(na, 3), O.random_orthonormal(nb, 4)
+    T.set_species(0, Ca); T.set_species(1, Cb)
+    T.set_generator(0, 1, seed)
+    ea, eb = O.synthetic_eps(oa, na), O.synthetic_eps(ob, nb)
+    win = O.windows_e_inter("MP2", na, nb, oa, ob)
+    rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, win)
+    e_orc = O.mp2_inter_from_pairs(rij, rkl, rv, na, nb, oa, ob, ea, eb, charge_a=1.0, charge_b=1.0, lam_a=1.0, lam_b=1.0)
+    for cols, qb in ((0, 0), (25, 2), (1, 3)):
+        chunked(cols)
+        sums = T.transform_stream(0, 1, win, ol.CONV_E, occ_batch=qb, epsA=ea, epsB=eb)
+        assert sums[0] == len(rv)
+        assert abs(sums[3] - e_orc) <= 1e-9
+
+
+def test_chunked_stream_mp2_energy_intra(O, T, chunked):
+    n, occ = 24, 6
+    seed = 31337
+    packed = O.hash_packed_intra(seed, n)
+    Cm = O.random_orthonormal(n, n)
+    eps = O.synthetic_eps(occ, n)
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, seed)
+    win = O.windows_e_intra("MP2", n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    e_orc = O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)
+    for cols, qb in ((0, 0), (60, 4), (1, 1), (200, 6)):
+        chunked(cols)
+        sums = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, epsA=eps, lam=2.0)
+        assert sums[0] == len(rv)
+        assert abs(sums[2] - (rv * rv).sum()) <= 1e-9
+        assert abs(sums[3] - e_orc) <= 1e-9
