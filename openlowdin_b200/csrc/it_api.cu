@@ -500,8 +500,8 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
                    out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
     const double per_col = (double)pt.nslots * 8.0 + (G > 1 ? 2.0 * (double)nmine * 8.0 : 0.0);
     int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
-    if (h->chunk_cols_limit > 0) max_cols = std::min<int64_t>(max_cols, h->chunk_cols_limit);
     if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
+    if (h->chunk_cols_limit > 0) max_cols = std::min<int64_t>(max_cols, h->chunk_cols_limit);
     // chunks: rows [p0,p1) of the pair triangle, even boundaries, as many rows as fit
     std::vector<Chunk> chunks;
     for (int p0 = 0; p0 < n2;) {
