@@ -1,0 +1,71 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): first half sharded over AO-pair slabs,
+NCCL all-to-all per chunk, second half on the slot owners; the summed results must equal the CPU oracle's.
+Used by tests/test_multi_gpu.py and by hand:  torchrun --nproc-per-node 2 scripts/mgpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import openlowdin_b200 as ol  # noqa: E402
+from openlowdin_b200 import capi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    T = ol.Transformer(local)
+    uid = [capi.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    T.comm_init(rank, world, uid[0])
+    ok = True
+    # intra, MP2 window with exchange energy; inter MP2
+    cases = [("intra", 24, 6, 31337), ("intra", 19, 5, 7), ("inter", (21, 16), (5, 2), 99)]
+    for kind, n, occ, seed in cases:
+        if kind == "intra":
+            packed = O.hash_packed_intra(seed, n)
+            Cm = O.random_orthonormal(n, n)
+            eps = O.synthetic_eps(occ, n)
+            T.set_species(0, Cm)
+            T.set_generator(0, 0, seed)
+            win = O.windows_e_intra("MP2", n, occ)
+            rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+            want = np.array([len(rv), rv.sum(), (rv * rv).sum(), O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)])
+            run = lambda qb: T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, epsA=eps, lam=2.0)  # noqa: E731
+        else:
+            (na, nb), (oa, ob) = n, occ
+            rect = O.hash_rect_inter(seed, na, nb)
+            Ca, Cb = O.random_orthonormal(na, 3), O.random_orthonormal(nb, 4)
+            ea, eb = O.synthetic_eps(oa, na), O.synthetic_eps(ob, nb)
+            T.set_species(0, Ca); T.set_species(1, Cb)
+            T.set_generator(0, 1, seed)
+            win = O.windows_e_inter("MP2", na, nb, oa, ob)
+            rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, win)
+            want = np.array([len(rv), rv.sum(), (rv * rv).sum(),
+                             O.mp2_inter_from_pairs(rij, rkl, rv, na, nb, oa, ob, ea, eb, charge_a=1.0, charge_b=1.0, lam_a=1.0, lam_b=1.0)])
+            run = lambda qb: T.transform_stream(0, 1, win, ol.CONV_E, occ_batch=qb, epsA=ea, epsB=eb)  # noqa: E731
+        for cols, qb in ((0, 0), (60, 4), (1, 2), (200, 3)):
+            T.set_option(T.OPT_CHUNK_COLS, cols)
+            s = torch.tensor(run(qb), dtype=torch.float64, device=dev)
+            dist.all_reduce(s)
+            got = s.cpu().numpy()
+            good = got[0] == want[0] and np.all(np.abs(got[1:] - want[1:]) <= 1e-9)
+            ok = ok and bool(good)
+            if rank == 0:
+                print(f"{kind} n={n} chunk_cols={cols} occ_batch={qb}: got {got} want {want} -> {'ok' if good else 'MISMATCH'}", flush=True)
+    T.set_option(T.OPT_CHUNK_COLS, 0)
+    T.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_CHECK_OK" if ok else "MGPU_CHECK_FAILED", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
