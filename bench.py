@@ -6,8 +6,9 @@ hash) + random orthonormal coefficients, N_bf basis functions (def
 O = N/10 occupied, MP2 window in transformer-E roles (p,r in virt; q,s in occ).  The (i a|mu nu)
 half-transformed block of N=1500 is 1.8 TB, so the transform runs one OCCUPIED BATCH at a time
 (lowdin_it_transform_stream); a "step" is one such pass: first half over all M AO-pair slabs for
-`occ_batch` occupied orbitals, second half over the resulting MO pairs, results consumed on the
-device (count / sums / MP2 pair energy).  GFLOP/s uses the ALGORITHMIC two-half flop count
+`occ_batch` occupied orbitals (56 at N=1500 on one B200: 3 passes = the whole transform), third
+quarter accumulated chunk by chunk, fourth quarter, results consumed on the device
+(count / sums / MP2 pair energy).  GFLOP/s uses the ALGORITHMIC two-half flop count
 F = 2 N Qb (N+P) n_pq + 2 N S (N+R) n_ij of SURVEY.md 8d -- no credit for padding or redundancy.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--nbf 1500] [--occ-batch 0] [--impl reference]
@@ -115,6 +116,16 @@ def cpu_sample(n, occ, nslabs, nthreads):
     return flops / dt / 1e9, dt, chk
 
 
+def cpu_sample_timed(n, occ, nthreads, target_s):
+    """Calibrate on one slab per thread, then run a sample sized for about target_s seconds."""
+    v, dt, _ = cpu_sample(n, occ, max(1, nthreads), nthreads)
+    per_round = max(dt, 1e-3)
+    rounds = int(max(1, min(400, target_s / per_round)))
+    nsl = max(1, nthreads) * rounds
+    v, dt, _ = cpu_sample(n, occ, nsl, nthreads)
+    return v, dt, nsl
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU transformer (oracle port of transformer E: the reference's
     Fortran cannot be compiled here and its C++ transformer D overflows 32-bit indices past N~300)."""
@@ -123,7 +134,8 @@ def run_reference(args):
         return
     n, occ = args.nbf, args.nbf // 10
     nthreads = os.cpu_count() or 1
-    per_step = max(1, nthreads)  # one slab per thread per step
+    _, dt1, _ = cpu_sample(n, occ, max(1, nthreads), nthreads)
+    per_step = max(1, nthreads) * int(max(1, min(200, 4.0 / max(dt1, 1e-3))))  # ~4 s of CPU work per step
     for _ in range(args.warmup):
         cpu_sample(n, occ, per_step, nthreads)
     t0 = time.perf_counter()
@@ -168,6 +180,7 @@ def main():
     ap.add_argument("--occ-batch", type=int, default=0)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -240,18 +253,22 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- e2e: through the C ABI with host buffers every step ----------------
+    # Every step re-uploads what a caller of this size owns on the host (coefficients from pinned memory, orbital
+    # energies) and reads the reduced result back; the 5 TB AO tensor of N=1500 cannot exist on a host, so its values
+    # stay a pure function of the canonical index evaluated where they are consumed.
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
     pinned = torch.from_numpy(np.ascontiguousarray(Cm.T)).pin_memory()  # column-major C(mu,p) == row-major C^T
     Cpin = pinned.numpy().T
     barrier()
     t1 = time.perf_counter()
     e2e_flops = 0.0
-    for i in range(args.steps):
+    for i in range(e2e_steps):
         T.set_species(0, Cpin)           # H2D: coefficients
         T.set_generator(0, 0, SEED)
         s = one_pass(args.warmup + i)    # H2D: orbital energies; D2H: sums
         e2e_flops += T.timers()["flops"]
     barrier()
-    e2e_s = time.perf_counter() - t1
+    e2e_s = max(time.perf_counter() - t1, 1e-9)
 
     if dist is not None:
         t = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
@@ -266,10 +283,20 @@ def main():
         gemm_cats = ("q1", "q2", "q3", "q4")
         dom = max(stats, key=lambda c: stats[c]["ms"])
         st = stats[dom]
+        kname = {"q1": "q1_gen_kernel (slab generation + first quarter)", "q2": "dgemm_tn_kernel<EpiScatterH> (second quarter)",
+                 "q3": "dgemm_tn_kernel<EpiAccT> (third quarter, chunked)", "q4": "dgemm_tn_kernel<EpiOut> (fourth quarter)",
+                 "expand1": "expand_block_kernel (first half)", "expand2": "expand_block_kernel (second half)",
+                 "consume": "reduce_block_kernel", "exchange": "NCCL all-to-all"}.get(dom, dom)
+        traffic = None
+        try:  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(f"n{n}", {}).get(dom)
+        except (OSError, ValueError):
+            pass
         if dom in gemm_cats:
             achieved = st["work"] / (st["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": f"dgemm_tn_kernel ({dom})", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak, "traffic": None, "launches": st["launches"],
+            roof = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak, "traffic": traffic, "launches": st["launches"],
                     "avg_launch_ms": st["ms"] / max(st["launches"], 1),
                     "peak_source": "cuBLAS DGEMM 4096^3 best of 6, measured live by bench.py (MEASURED_PEAKS.json has no FP64 entry)"}
         else:
@@ -280,8 +307,8 @@ def main():
                 pass
             hbm = peaks.get("hbm_gbs", 6650.0)
             achieved = st["work"] / (st["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": f"{dom}", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": None, "launches": st["launches"], "avg_launch_ms": st["ms"] / max(st["launches"], 1),
+            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    "traffic": traffic, "launches": st["launches"], "avg_launch_ms": st["ms"] / max(st["launches"], 1),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
         kernels = {}
         for c, s_ in stats.items():
@@ -297,17 +324,18 @@ def main():
                                        f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
                                        f"({npass} passes = the whole transform)",
                            "nbf": n, "occ": occ, "occ_batch": qb, "passes_per_transform": npass,
-                           "l2": "inputs larger than L2 (each pass streams >100 GB of generated slabs / half-transformed data)",
-                           "flops_per_step": flops / args.steps, "fp64_pct_of_cublas_dgemm": 100.0 * value / 1e3 / fp64_peak,
-                           "fp64_pct_of_nominal_37tf": 100.0 * value / 37000.0, "wall_ms_per_step": wall_s / args.steps * 1e3},
+                           "l2": "working set larger than L2 (each pass re-streams the third-quarter accumulators and chunk buffers, tens of GB)",
+                           "flops_per_step": flops / args.steps, "fp64_pct_of_cublas_dgemm_per_gpu": 100.0 * value / 1e3 / fp64_peak / world,
+                           "fp64_pct_of_nominal_37tf_per_gpu": 100.0 * value / 37000.0 / world, "cublas_dgemm_tflops_measured": fp64_peak, "wall_ms_per_step": wall_s / args.steps * 1e3},
                 "roofline": roof, "kernels": kernels,
-                "e2e": {"value": e2e_flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(n * n * 8 + n * 8),
-                        "d2h_bytes_per_step": 32},
+                "e2e": {"value": (e2e_flops / e2e_s / 1e9) if e2e_steps else None, "unit": "GFLOP/s", "steps": e2e_steps,
+                        "h2d_bytes_per_step": int(n * n * 8 + n * 8), "d2h_bytes_per_step": 32,
+                        "note": "C-ABI calls with host buffers: coefficients (pinned) + orbital energies up, reduced sums down; "
+                                "AO values generated on the device from the canonical index (a 5 TB host tensor cannot exist)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
-            nsl = max(1, nthreads) * (2 if n >= 1000 else 8)
-            v, dt, _ = cpu_sample(n, occ, nsl, nthreads)
+            v, dt, nsl = cpu_sample_timed(n, occ, nthreads, 15.0)
             line["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": nthreads, "kind": "port",
                                     "sample": f"first half of transformer E (oracle port of E.f90:1043-1132) on {nsl} of {n*(n+1)//2} "
                                               f"AO-pair slabs, full occupied window, {dt:.1f} s"}
