@@ -226,3 +226,136 @@ def transform_inter_all(coeff, ocoeff, ints):
     if L.lowdin_it_transform_inter_all(coeff, ocoeff, ints, coeff.shape[0], ocoeff.shape[0]):
         raise LowdinITError("lowdin_it_transform_inter_all failed: " + L.lowdin_it_last_error(None).decode())
     return ints
+
+
+# ---------------------------------------------------------------------------------------------
+# include/lowdin_it_host.h -- host-side mirror of the reference's transformer interface (C and E)
+# ---------------------------------------------------------------------------------------------
+HOST_SYMBOLS = [
+    "lowdin_host_last_error", "lowdin_host_partial_transform", "lowdin_host_windows", "lowdin_host_ints_filename",
+    "lowdin_host_write_ints_file", "lowdin_host_read_ints_file", "lowdin_host_write_moint_quads",
+    "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
+    "lowdin_host_atomic_to_molecular_two_species",
+]
+
+
+class HostControl(C.Structure):
+    _fields_ = [("method", C.c_char), ("partial_transform", C.c_char * 16), ("integral_stack_size", C.c_int),
+                ("nfiles", C.c_int), ("ionize_mo", C.c_int), ("pt_transition_operator", C.c_int),
+                ("n_ionize_species", C.c_int), ("ionize_species", (C.c_char * 32) * 4), ("scratch_dir", C.c_char * 512),
+                ("verbose", C.c_int)]
+
+
+class HostSpecies(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("id", C.c_int), ("nao", C.c_int), ("occupation", C.c_int),
+                ("core_orbitals", C.c_int), ("active_orbitals", C.c_int), ("coeff", C.c_void_p), ("ldc", C.c_int),
+                ("ncols", C.c_int)]
+
+
+def host_control(method="C", partial="MP2", stack=30000, nfiles=1, ionize_mo=0, pt_transition_operator=False,
+                 ionize_species=(), scratch_dir="", verbose=False):
+    c = HostControl()
+    c.method = method.encode()
+    c.partial_transform = partial.encode()
+    c.integral_stack_size, c.nfiles, c.ionize_mo = stack, nfiles, ionize_mo
+    c.pt_transition_operator = int(pt_transition_operator)
+    sp = [s for s in ionize_species if s and s != "NONE"]
+    c.n_ionize_species = len(sp)
+    for i, s in enumerate(sp[:4]):
+        c.ionize_species[i].value = s.encode()
+    c.scratch_dir = scratch_dir.encode()
+    c.verbose = int(verbose)
+    return c
+
+
+def host_species(name, sid, nao, occ, core=0, active=0, coeff=None):
+    s = HostSpecies()
+    s.name = name.encode()
+    s.id, s.nao, s.occupation, s.core_orbitals, s.active_orbitals = sid, nao, occ, core, active
+    if coeff is not None:
+        coeff = np.asfortranarray(coeff, dtype=np.float64)
+        s._keep = coeff  # keep the buffer alive
+        s.coeff = coeff.ctypes.data
+        s.ldc, s.ncols = coeff.shape[0], coeff.shape[1]
+    return s
+
+
+def _host():
+    L = load()
+    if getattr(L, "_host_ready", False):
+        return L
+    PC, PS = C.POINTER(HostControl), C.POINTER(HostSpecies)
+    L.lowdin_host_last_error.restype = C.c_char_p
+    L.lowdin_host_partial_transform.argtypes = [C.c_int] * 4 + [C.c_char_p]
+    L.lowdin_host_windows.argtypes = [PC, PS, PS, _i32p, C.POINTER(C.c_int)]
+    L.lowdin_host_ints_filename.argtypes = [C.c_int, PS, PS, C.c_char_p, C.POINTER(C.c_int)]
+    L.lowdin_host_write_ints_file.argtypes = [C.c_char_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int64]
+    L.lowdin_host_read_ints_file.argtypes = [C.c_char_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int64,
+                                             C.POINTER(C.c_int64)]
+    L.lowdin_host_write_moint_quads.argtypes = [C.c_char_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int64]
+    L.lowdin_host_write_moint_pairs.argtypes = [C.c_char_p, C.c_int, _i64p, _i64p, _f64p, C.c_int64]
+    L.lowdin_host_atomic_to_molecular_one_species.argtypes = [C.c_void_p, PC, PS, C.POINTER(C.c_int64)]
+    L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
+    L._host_ready = True
+    return L
+
+
+def _hck(rc):
+    if rc:
+        raise LowdinITError(_host().lowdin_host_last_error().decode())
+
+
+def host_partial_transform(mp=0, pt=0, en=0, ci_level="NONE"):
+    out = C.create_string_buffer(16)
+    _hck(_host().lowdin_host_partial_transform(mp, pt, en, int(ci_level == "NONE"), out))
+    return out.value.decode()
+
+
+def host_windows(ctl, a, b=None):
+    win = np.zeros(8, np.int32)
+    sym = C.c_int()
+    _hck(_host().lowdin_host_windows(C.byref(ctl), C.byref(a), C.byref(b) if b is not None else None, win, C.byref(sym)))
+    return [int(x) for x in win], bool(sym.value)
+
+
+def host_ints_filename(tid, a, b=None):
+    out = C.create_string_buffer(256)
+    sw = C.c_int()
+    _hck(_host().lowdin_host_ints_filename(tid, C.byref(a), C.byref(b) if b is not None else None, out, C.byref(sw)))
+    return out.value.decode(), bool(sw.value)
+
+
+def host_write_ints_file(path, stack, p, q, r, s, v):
+    a = [np.ascontiguousarray(x, np.int32) for x in (p, q, r, s)]
+    _hck(_host().lowdin_host_write_ints_file(path.encode(), stack, *a, np.ascontiguousarray(v, np.float64), len(v)))
+
+
+def host_read_ints_file(path, stack, cap):
+    a = [np.zeros(max(cap, 1), np.int32) for _ in range(4)]
+    v = np.zeros(max(cap, 1))
+    n = C.c_int64()
+    _hck(_host().lowdin_host_read_ints_file(path.encode(), stack, *a, v, cap, C.byref(n)))
+    m = min(n.value, cap)
+    return tuple(x[:m] for x in a) + (v[:m],), n.value
+
+
+def host_write_moint_quads(path, stack, p, q, r, s, v):
+    a = [np.ascontiguousarray(x, np.int32) for x in (p, q, r, s)]
+    _hck(_host().lowdin_host_write_moint_quads(path.encode(), stack, *a, np.ascontiguousarray(v, np.float64), len(v)))
+
+
+def host_write_moint_pairs(path, stack, ij, kl, v):
+    _hck(_host().lowdin_host_write_moint_pairs(path.encode(), stack, np.ascontiguousarray(ij, np.int64),
+                                               np.ascontiguousarray(kl, np.int64), np.ascontiguousarray(v, np.float64), len(v)))
+
+
+def host_transform_one_species(T, ctl, a):
+    n = C.c_int64()
+    _hck(_host().lowdin_host_atomic_to_molecular_one_species(T.h, C.byref(ctl), C.byref(a), C.byref(n)))
+    return n.value
+
+
+def host_transform_two_species(T, ctl, a, b):
+    n = C.c_int64()
+    _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
+    return n.value

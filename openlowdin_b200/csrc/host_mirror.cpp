@@ -1,0 +1,404 @@
+// host_mirror.cpp -- C++ mirror of the reference's Fortran host side for transformers C and E
+// (include/lowdin_it_host.h): window tables, partialTransform choice, .ints stream readers, moint.dat record
+// writers and the per-species / per-pair transformer calls on top of the C ABI of lowdin_it.h.
+// No arithmetic of the transformation lives here (that is csrc/it_kernels.cuh); this file is integer / file logic.
+#include "../../include/lowdin_it_host.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int hfail(const std::string &m) { g_err = m; return 1; }
+
+struct Win { int pl, pu, ql, qu, rl, ru, sl, su; };
+void put(const Win &w, int out[8]) {
+  const int v[8] = {w.pl, w.pu, w.ql, w.qu, w.rl, w.ru, w.sl, w.su};
+  memcpy(out, v, sizeof v);
+}
+bool is(const lowdin_host_control *c, const char *s) { return strncmp(c->partial_transform, s, sizeof c->partial_transform) == 0; }
+
+std::string trimmed(const char *s, size_t cap) {
+  std::string t(s, strnlen(s, cap));
+  while (!t.empty() && t.back() == ' ') t.pop_back();
+  return t;
+}
+
+void ionize_flags(const lowdin_host_control *c, const lowdin_host_species *a, const lowdin_host_species *b, bool &ia, bool &ib) {
+  ia = ib = false;  // C.f90:1703-1716 / E.f90:2156-2168: species names compared with every IONIZE_SPECIES entry
+  const std::string na = trimmed(a->name, sizeof a->name), nb = trimmed(b->name, sizeof b->name);
+  for (int s = 0; s < c->n_ionize_species && s < 4; ++s) {
+    const std::string t = trimmed(c->ionize_species[s], 32);
+    if (na == t) ia = true;
+    if (nb == t) ib = true;
+  }
+}
+
+// ---- transformer C, intra: TransformIntegralsC.f90:1436-1622 ------------------------------------
+Win win_c_intra(const lowdin_host_control *c, const lowdin_host_species *a, int *symmetric) {
+  const int occ = a->occupation, core = a->core_orbitals, act = a->active_orbitals ? a->active_orbitals : a->nao, mo = c->ionize_mo;
+  *symmetric = 1;
+  Win w{core + 1, act, core + 1, act, core + 1, act, core + 1, act};
+  if (is(c, "ALL")) w = Win{1, a->nao, 1, a->nao, 1, a->nao, 1, a->nao};
+  if (is(c, "ALLACTIVE")) w = Win{1, act, 1, act, 1, act, 1, act};
+  if (is(c, "MP2")) w = Win{core + 1, occ, occ + 1, act, core + 1, occ, occ + 1, act};
+  if (is(c, "PT2") || is(c, "MP2-PT2")) {
+    *symmetric = 0;
+    const bool both = is(c, "MP2-PT2");
+    int pl, pu;
+    if (mo == 0) { pl = both ? core + 1 : occ; pu = occ + 1; }          // HOMO..LUMO (PT2) / core+1..LUMO (MP2-PT2)
+    else if (both) { pl = core + 1; pu = std::max(mo, occ); }
+    else { pl = mo; pu = mo; }
+    const int sl = (mo != 0 && c->pt_transition_operator) ? core + 1 : occ + 1;
+    w = Win{pl, pu, core + 1, act, core + 1, occ, sl, act};
+  }
+  return w;
+}
+
+// ---- transformer E, intra: TransformIntegralsE.f90:1899-2073 (roles of the pair members swapped; no ALL case) ----
+Win win_e_intra(const lowdin_host_control *c, const lowdin_host_species *a) {
+  const int occ = a->occupation, core = a->core_orbitals, act = a->active_orbitals ? a->active_orbitals : a->nao, mo = c->ionize_mo;
+  Win w{core + 1, act, core + 1, act, core + 1, act, core + 1, act};
+  if (is(c, "ALLACTIVE")) w = Win{1, act, 1, act, 1, act, 1, act};
+  if (is(c, "MP2")) w = Win{occ + 1, act, core + 1, occ, occ + 1, act, core + 1, occ};
+  if (is(c, "PT2") || is(c, "MP2-PT2")) {
+    int ql, qu;
+    if (mo == 0) { ql = core + 1; qu = occ + 1; }
+    else if (is(c, "MP2-PT2")) { ql = core + 1; qu = std::max(mo, occ); }
+    else { ql = mo; qu = mo; }
+    const int rl = (mo != 0 && c->pt_transition_operator) ? core + 1 : occ + 1;
+    w = Win{core + 1, act, ql, qu, rl, act, core + 1, occ};
+  }
+  return w;
+}
+
+// ---- transformer C, inter: TransformIntegralsC.f90:1625-1963 ------------------------------------
+Win win_c_inter(const lowdin_host_control *c, const lowdin_host_species *a, const lowdin_host_species *b, int *symmetric) {
+  const int oa = a->occupation, ob = b->occupation, ca = a->core_orbitals, cb = b->core_orbitals;
+  const int aa = a->active_orbitals ? a->active_orbitals : a->nao, ab = b->active_orbitals ? b->active_orbitals : b->nao;
+  const int mo = c->ionize_mo;
+  *symmetric = 1;
+  Win w{ca + 1, aa, ca + 1, aa, cb + 1, ab, cb + 1, ab};
+  if (is(c, "ALL")) w = Win{1, a->nao, 1, a->nao, 1, b->nao, 1, b->nao};
+  if (is(c, "ALLACTIVE")) w = Win{1, aa, 1, aa, 1, ab, 1, ab};
+  if (is(c, "MP2")) w = Win{ca + 1, oa, oa + 1, aa, cb + 1, ob, ob + 1, ab};
+  if (is(c, "PT2") || is(c, "MP2-PT2")) {
+    const bool both = is(c, "MP2-PT2");
+    w = Win{ca + 1, oa + 1, ca + 1, aa, cb + 1, ob + 1, cb + 1, ab};
+    if (c->n_ionize_species > 0) {
+      *symmetric = 0;
+      bool ia, ib;
+      ionize_flags(c, a, b, ia, ib);
+      if (mo == 0) {
+        if (ia && ib) w = Win{ca + 1, oa + 1, ca + 1, aa, cb + 1, ob + 1, cb + 1, ab};
+        else if (ia) w = Win{ca + 1, oa + 1, ca + 1, aa, cb + 1, ob, ob + 1, ab};
+        else if (ib) w = Win{ca + 1, oa, oa + 1, aa, cb + 1, ob + 1, cb + 1, ab};
+      } else {
+        if (ia && ib) {
+          if (mo <= oa && mo <= ob) w = Win{ca + 1, oa, ca + 1, aa, cb + 1, ob, cb + 1, ab};
+          else if (mo > oa && mo > ob) w = Win{ca + 1, mo, ca + 1, aa, cb + 1, mo, cb + 1, ab};
+        } else if (ia) {
+          w = both ? Win{ca + 1, std::max(mo, oa), ca + 1, aa, cb + 1, ob, ob + 1, ab} : Win{mo, mo, ca + 1, aa, cb + 1, ob, ob + 1, ab};
+        } else if (ib) {
+          w = both ? Win{ca + 1, oa, oa + 1, aa, cb + 1, std::max(mo, ob), cb + 1, ab} : Win{ca + 1, oa, oa + 1, aa, mo, mo, cb + 1, ab};
+        }
+      }
+    }
+  }
+  return w;
+}
+
+// ---- transformer E, inter: TransformIntegralsE.f90:2076-2418 ------------------------------------
+// Quirks kept as they are in the reference: the PT2 default takes s_l and r_l from the FIRST species' core
+// orbitals (E.f90:2142-2145) and the MP2-PT2 default sets r_u to the first species' active count (E.f90:2283).
+Win win_e_inter(const lowdin_host_control *c, const lowdin_host_species *a, const lowdin_host_species *b) {
+  const int oa = a->occupation, ob = b->occupation, ca = a->core_orbitals, cb = b->core_orbitals;
+  const int aa = a->active_orbitals ? a->active_orbitals : a->nao, ab = b->active_orbitals ? b->active_orbitals : b->nao;
+  const int mo = c->ionize_mo;
+  Win w{ca + 1, aa, ca + 1, aa, cb + 1, ab, cb + 1, ab};
+  if (is(c, "ALLACTIVE")) w = Win{1, aa, 1, aa, 1, ab, 1, ab};
+  if (is(c, "MP2")) w = Win{oa + 1, aa, ca + 1, oa, ob + 1, ab, cb + 1, ob};
+  if (is(c, "PT2") || is(c, "MP2-PT2")) {
+    const bool both = is(c, "MP2-PT2");
+    w = both ? Win{ca + 1, aa, ca + 1, oa + 1, cb + 1, aa, cb + 1, ob + 1} : Win{ca + 1, aa, ca + 1, oa + 1, ca + 1, ab, ca + 1, ob + 1};
+    if (c->n_ionize_species > 0) {
+      bool ia, ib;
+      ionize_flags(c, a, b, ia, ib);
+      if (mo == 0) {
+        if (ia && ib) w = Win{ca + 1, aa, ca + 1, oa + 1, cb + 1, ab, cb + 1, ob + 1};
+        else if (ia) w = Win{ca + 1, aa, ca + 1, oa + 1, ob + 1, ab, cb + 1, ob};
+        else if (ib) w = Win{oa + 1, aa, ca + 1, oa, cb + 1, ab, cb + 1, ob + 1};
+      } else {
+        if (ia && ib) {
+          if (mo <= oa && mo <= ob) w = Win{ca + 1, aa, ca + 1, oa, cb + 1, ab, cb + 1, ob};
+          else if (mo > oa && mo > ob) w = Win{ca + 1, aa, ca + 1, aa, cb + 1, ab, cb + 1, ab};
+        } else if (ia) {
+          int ql = both ? ca + 1 : mo, qu = both ? std::max(mo, oa) : mo;
+          if (c->pt_transition_operator) { ql = ca + 1; qu = aa; }
+          w = Win{ca + 1, aa, ql, qu, ob + 1, ab, cb + 1, ob};
+        } else if (ib) {
+          w = Win{oa + 1, aa, ca + 1, oa, cb + 1, ab, cb + 1, ab};
+        }
+      }
+    }
+  }
+  return w;
+}
+
+std::string join(const char *dir, const std::string &file) {
+  std::string d = trimmed(dir, 512);
+  if (d.empty()) return file;
+  if (d.back() != '/') d += '/';
+  return d + file;
+}
+
+int check_ctl(const lowdin_host_control *c) {
+  if (!c) return hfail("null control block");
+  if (c->method != 'C' && c->method != 'E') return hfail("method must be 'C' or 'E'");
+  if (c->integral_stack_size < 1) return hfail("integral_stack_size < 1");
+  if (c->nfiles < 1) return hfail("nfiles < 1");
+  return 0;
+}
+
+// Reads every stack of one stream file and hands it to `sink` (the reader loops of C.f90:251-295).
+template <class Sink>
+int for_each_stack(const std::string &path, int S, Sink sink) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return hfail("cannot open " + path);
+  std::vector<int32_t> p(S), q(S), r(S), s(S);
+  std::vector<double> v(S);
+  int rc = 0;
+  for (;;) {
+    size_t a = fread(p.data(), 4, S, f);
+    if (a == 0) break;  // the reference trusts filesize/24/S; a file without terminator simply ends
+    if (a != (size_t)S || fread(q.data(), 4, S, f) != (size_t)S || fread(r.data(), 4, S, f) != (size_t)S ||
+        fread(s.data(), 4, S, f) != (size_t)S || fread(v.data(), 8, S, f) != (size_t)S) { rc = hfail("truncated stack in " + path); break; }
+    bool last = false;
+    for (int i = 0; i < S; ++i) if (p[i] == -1) { last = true; break; }
+    if ((rc = sink(p.data(), q.data(), r.data(), s.data(), v.data(), S)) != 0) break;
+    if (last) break;
+  }
+  fclose(f);
+  return rc;
+}
+
+int write_record(FILE *f, const void *a, size_t na, const void *b, size_t nb, const void *c, size_t nc, const void *d, size_t nd,
+                 const void *e, size_t ne) {
+  const uint32_t len = (uint32_t)(na + nb + nc + nd + ne);  // gfortran sequential unformatted: 4-byte length before and after
+  if (fwrite(&len, 4, 1, f) != 1) return 1;
+  if (na && fwrite(a, 1, na, f) != na) return 1;
+  if (nb && fwrite(b, 1, nb, f) != nb) return 1;
+  if (nc && fwrite(c, 1, nc, f) != nc) return 1;
+  if (nd && fwrite(d, 1, nd, f) != nd) return 1;
+  if (ne && fwrite(e, 1, ne, f) != ne) return 1;
+  return fwrite(&len, 4, 1, f) != 1;
+}
+
+int load_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b) {
+  const int slot_b = b ? 1 : 0;
+  int swapped = 0;
+  char name[256];
+  if (lowdin_host_ints_filename(0, a, b, name, &swapped)) return 1;
+  if (lowdin_it_ao_begin(h, 0, slot_b, swapped)) return hfail(lowdin_it_last_error(h));
+  for (int tid = 0; tid < ctl->nfiles; ++tid) {
+    if (lowdin_host_ints_filename(tid, a, b, name, &swapped)) return 1;
+    int rc = for_each_stack(join(ctl->scratch_dir, name), ctl->integral_stack_size,
+                            [&](const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s, const double *v, int n) {
+                              return lowdin_it_ao_push_stacks(h, p, q, r, s, v, n) ? hfail(lowdin_it_last_error(h)) : 0;
+                            });
+    if (rc) return rc;
+  }
+  if (lowdin_it_ao_end(h)) return hfail(lowdin_it_last_error(h));
+  return 0;
+}
+
+int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b,
+                  int64_t *nonzero) {
+  if (check_ctl(ctl)) return 1;
+  if (!h || !a || !a->coeff) return hfail("null handle / species");
+  int win[8], symmetric = 0;
+  if (lowdin_host_windows(ctl, a, b, win, &symmetric)) return 1;
+  if (ctl->verbose) {  // the "Transformation boundaries" table of C.f90:1614-1620
+    printf("              Transformation boundaries \n              orbital   lower upper\n");
+    const char *nm = "pqrs";
+    for (int w = 0; w < 4; ++w) printf("                   %c%6d%6d\n", nm[w], win[2 * w], win[2 * w + 1]);
+  }
+  if (lowdin_it_set_species(h, 0, a->nao, a->coeff, a->ldc, a->ncols)) return hfail(lowdin_it_last_error(h));
+  if (b && lowdin_it_set_species(h, 1, b->nao, b->coeff, b->ldc, b->ncols)) return hfail(lowdin_it_last_error(h));
+  if (load_ints(h, ctl, a, b)) return 1;
+  const int conv = (ctl->method == 'E') ? LOWDIN_IT_CONV_E : LOWDIN_IT_CONV_C;
+  if (lowdin_it_transform(h, 0, b ? 1 : 0, win, conv, symmetric, 1e-10)) return hfail(lowdin_it_last_error(h));
+  int64_t n = 0;
+  if (lowdin_it_result_count(h, &n)) return hfail(lowdin_it_last_error(h));
+  const std::string prefix = b ? trimmed(a->name, 32) + "." + trimmed(b->name, 32) : trimmed(a->name, 32);  // C.f90:192, :788
+  const std::string path = join(ctl->scratch_dir, prefix + "moint.dat");
+  const size_t m = (size_t)std::max<int64_t>(n, 1);
+  std::vector<double> v(m);
+  int rc;
+  if (conv == LOWDIN_IT_CONV_E) {
+    std::vector<int64_t> ij(m), kl(m);
+    if (lowdin_it_download_pairs(h, ij.data(), kl.data(), v.data())) return hfail(lowdin_it_last_error(h));
+    rc = lowdin_host_write_moint_pairs(path.c_str(), ctl->integral_stack_size, ij.data(), kl.data(), v.data(), n);
+  } else {
+    std::vector<int32_t> p(m), q(m), r(m), s(m);
+    if (lowdin_it_download_quads(h, p.data(), q.data(), r.data(), s.data(), v.data())) return hfail(lowdin_it_last_error(h));
+    rc = lowdin_host_write_moint_quads(path.c_str(), ctl->integral_stack_size, p.data(), q.data(), r.data(), s.data(), v.data(), n);
+  }
+  if (rc) return rc;
+  if (ctl->verbose) printf("   %36s%12lld\n", "Non-zero transformed integrals: ", (long long)n);  // C.f90:469
+  if (nonzero) *nonzero = n;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lowdin_host_last_error(void) { return g_err.c_str(); }
+
+int lowdin_host_partial_transform(int mp, int pt, int en, int ci_none, char out[16]) {
+  const char *r = "BOUNDS";  // IntegralTransformation.f90:106-126
+  if (mp == 2 && pt == 0 && en == 0 && ci_none) r = "MP2";
+  else if (pt == 2 && mp == 0 && en == 0 && ci_none) r = "PT2";
+  else if (pt == 2 && mp == 2 && en == 0 && ci_none) r = "MP2-PT2";
+  else if (!ci_none) r = "ALL";
+  memset(out, 0, 16);
+  strncpy(out, r, 15);
+  return 0;
+}
+
+int lowdin_host_windows(const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b, int win[8],
+                        int *symmetric) {
+  if (check_ctl(ctl)) return 1;
+  if (!a || !win) return hfail("null species / window output");
+  int sym = 1;
+  Win w;
+  if (ctl->method == 'C') w = b ? win_c_inter(ctl, a, b, &sym) : win_c_intra(ctl, a, &sym);
+  else { w = b ? win_e_inter(ctl, a, b) : win_e_intra(ctl, a); sym = 0; }
+  put(w, win);
+  if (symmetric) *symmetric = sym;
+  return 0;
+}
+
+int lowdin_host_ints_filename(int tid, const lowdin_host_species *a, const lowdin_host_species *b, char out[256], int *swapped) {
+  if (!a || !out) return hfail("null argument");
+  const std::string na = trimmed(a->name, 32);
+  std::string file;
+  int sw = 0;
+  if (!b) {
+    file = (na == "E-BETA") ? "E-ALPHA" : na;  // C.f90:241-245
+  } else {
+    const std::string nb = trimmed(b->name, 32);
+    // the stream on disk was written for the pair in molecular-system order (lower id first); E-BETA reads E-ALPHA's
+    const bool forward = a->id < b->id;  // C.f90:838 / :906
+    const std::string &first = forward ? na : nb, &second = forward ? nb : na;
+    sw = forward ? 0 : 1;
+    if (first == "E-ALPHA" && second == "E-BETA") file = "E-ALPHA.E-BETA";
+    else if (second == "E-BETA") file = first + ".E-ALPHA";
+    else if (first == "E-BETA") file = "E-ALPHA." + second;
+    else file = first + "." + second;
+  }
+  snprintf(out, 256, "%d%s.ints", tid, file.c_str());
+  if (swapped) *swapped = sw;
+  return 0;
+}
+
+int lowdin_host_write_ints_file(const char *path, int S, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s,
+                                const double *v, int64_t n) {
+  if (S < 1) return hfail("stack size < 1");
+  FILE *f = fopen(path, "wb");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  std::vector<int32_t> bp(S), bq(S), br(S), bs(S);
+  std::vector<double> bv(S);
+  int64_t done = 0;
+  bool terminated = false;
+  while (!terminated) {  // Libint2Iface.cpp:3414-3426: full blocks, the last one carrying p = -1 after its last entry
+    const int64_t m = std::min<int64_t>(S, n - done);
+    std::fill(bp.begin(), bp.end(), 0); std::fill(bq.begin(), bq.end(), 0); std::fill(br.begin(), br.end(), 0);
+    std::fill(bs.begin(), bs.end(), 0); std::fill(bv.begin(), bv.end(), 0.0);
+    for (int64_t i = 0; i < m; ++i) { bp[i] = p[done + i]; bq[i] = q[done + i]; br[i] = r[done + i]; bs[i] = s[done + i]; bv[i] = v[done + i]; }
+    if (m < S) { bp[m] = -1; terminated = true; }
+    done += m;
+    if (fwrite(bp.data(), 4, S, f) != (size_t)S || fwrite(bq.data(), 4, S, f) != (size_t)S || fwrite(br.data(), 4, S, f) != (size_t)S ||
+        fwrite(bs.data(), 4, S, f) != (size_t)S || fwrite(bv.data(), 8, S, f) != (size_t)S) { fclose(f); return hfail("short write"); }
+  }
+  fclose(f);
+  return 0;
+}
+
+int lowdin_host_read_ints_file(const char *path, int S, int32_t *p, int32_t *q, int32_t *r, int32_t *s, double *v, int64_t cap,
+                               int64_t *n) {
+  if (S < 1) return hfail("stack size < 1");
+  int64_t cnt = 0;
+  int rc = for_each_stack(path, S, [&](const int32_t *bp, const int32_t *bq, const int32_t *br, const int32_t *bs, const double *bv, int m) {
+    for (int i = 0; i < m; ++i) {
+      if (bp[i] == -1) break;
+      if (cnt < cap) { p[cnt] = bp[i]; q[cnt] = bq[i]; r[cnt] = br[i]; s[cnt] = bs[i]; v[cnt] = bv[i]; }
+      ++cnt;
+    }
+    return 0;
+  });
+  if (n) *n = cnt;
+  return rc;
+}
+
+int lowdin_host_write_moint_quads(const char *path, int S, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s,
+                                  const double *v, int64_t n) {
+  if (S < 1) return hfail("stack size < 1");
+  FILE *f = fopen(path, "wb");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  std::vector<int32_t> bp(S, 0), bq(S, 0), br(S, 0), bs(S, 0);
+  std::vector<double> bv(S, 0.0);
+  int m = 0, rc = 0;
+  for (int64_t k = 0; k < n && !rc; ++k) {  // C.f90:419-440
+    bp[m] = p[k]; bq[m] = q[k]; br[m] = r[k]; bs[m] = s[k]; bv[m] = v[k];
+    if (++m == S) {
+      rc = write_record(f, bp.data(), 4 * (size_t)S, bq.data(), 4 * (size_t)S, br.data(), 4 * (size_t)S, bs.data(), 4 * (size_t)S, bv.data(), 8 * (size_t)S);
+      m = 0;
+      std::fill(bp.begin(), bp.end(), 0); std::fill(bq.begin(), bq.end(), 0); std::fill(br.begin(), br.end(), 0);
+      std::fill(bs.begin(), bs.end(), 0); std::fill(bv.begin(), bv.end(), 0.0);
+    }
+  }
+  bp[m] = -1;  // C.f90:450-456: the terminator record is always written
+  if (!rc) rc = write_record(f, bp.data(), 4 * (size_t)S, bq.data(), 4 * (size_t)S, br.data(), 4 * (size_t)S, bs.data(), 4 * (size_t)S, bv.data(), 8 * (size_t)S);
+  fclose(f);
+  return rc ? hfail("short write") : 0;
+}
+
+int lowdin_host_write_moint_pairs(const char *path, int S, const int64_t *ij, const int64_t *kl, const double *v, int64_t n) {
+  if (S < 1) return hfail("stack size < 1");
+  FILE *f = fopen(path, "wb");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  std::vector<int64_t> bi(S, 0), bk(S, 0);
+  std::vector<double> bv(S, 0.0);
+  int m = 0, rc = 0;
+  for (int64_t k = 0; k < n && !rc; ++k) {  // E.f90:1244-1257
+    bi[m] = ij[k]; bk[m] = kl[k]; bv[m] = v[k];
+    if (++m == S) {
+      rc = write_record(f, bi.data(), 8 * (size_t)S, bk.data(), 8 * (size_t)S, bv.data(), 8 * (size_t)S, nullptr, 0, nullptr, 0);
+      m = 0;
+      std::fill(bi.begin(), bi.end(), 0); std::fill(bk.begin(), bk.end(), 0); std::fill(bv.begin(), bv.end(), 0.0);
+    }
+  }
+  bi[m] = -1;  // E.f90:1263-1268
+  if (!rc) rc = write_record(f, bi.data(), 8 * (size_t)S, bk.data(), 8 * (size_t)S, bv.data(), 8 * (size_t)S, nullptr, 0, nullptr, 0);
+  fclose(f);
+  return rc ? hfail("short write") : 0;
+}
+
+int lowdin_host_atomic_to_molecular_one_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
+                                                int64_t *nonzero) {
+  return run_and_write(h, ctl, a, nullptr, nonzero);
+}
+
+int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
+                                                const lowdin_host_species *b, int64_t *nonzero) {
+  if (!b) return hfail("second species missing");
+  return run_and_write(h, ctl, a, b, nonzero);
+}
+
+}  // extern "C"

@@ -15,7 +15,7 @@ def declared_symbols():
     names = []
     for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
         src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
-        names += re.findall(r"\b(lowdin_it_[a-z0-9_]+)\s*\(", src)
+        names += re.findall(r"\b(lowdin_(?:it|host)_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     L = capi.load()
     for s in declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/ but not exported by liblowdin_itgpu.so"
-    assert sorted(capi.ABI_SYMBOLS) == declared_symbols()
+    assert sorted(capi.ABI_SYMBOLS + capi.HOST_SYMBOLS) == declared_symbols()
 
 
 def test_library_is_sm100a_cuda_code():

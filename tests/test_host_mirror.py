@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's transformer interface (include/lowdin_it_host.h): window tables against the
+oracle's restatement and literal expectations, file names, .ints stream files, moint.dat record layouts (CPU), and the
+file-to-file transformer calls on the GPU against the oracle."""
+import itertools
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from openlowdin_b200 import capi
+from helpers import assert_lists_match, dense_pairs, dense_quads
+
+MODES = ["MP2", "PT2", "MP2-PT2", "ALL", "ALLACTIVE", "BOUNDS"]
+
+
+# ---------------------------------------------------------------------------------------------
+# integer host logic (CPU)
+# ---------------------------------------------------------------------------------------------
+def test_partial_transform_choice(O):
+    for mp, pt, en, ci in itertools.product((0, 2), (0, 2, 3), (0, 2), ("NONE", "CISD")):
+        assert capi.host_partial_transform(mp, pt, en, ci) == O.partial_transform(mp, pt, en, ci)
+    assert capi.host_partial_transform(mp=2) == "MP2"
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_intra_windows_match_restated_tables(O, mode):
+    for n, occ, core, active, mo, pto in itertools.product((19,), (1, 5), (0, 1), (0, 15), (0, 3, 7), (False, True)):
+        a = capi.host_species("E-", 1, n, occ, core, active)
+        wc, sym = capi.host_windows(capi.host_control("C", mode, ionize_mo=mo, pt_transition_operator=pto), a)
+        assert (wc, sym) == O.windows_c_intra(mode, n, occ, core, active, mo, pto)
+        we, _ = capi.host_windows(capi.host_control("E", mode, ionize_mo=mo, pt_transition_operator=pto), a)
+        assert we == O.windows_e_intra(mode, n, occ, core, active, mo, pto)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_inter_windows_match_restated_tables(O, mode):
+    for (oa, ob), (ca, cb), (aa, ab), mo, ion, pto in itertools.product(
+            ((5, 1), (1, 5)), ((0, 0), (1, 0)), ((0, 0), (15, 40)), (0, 1, 3, 9),
+            ((), ("E-",), ("H_1",), ("E-", "H_1")), (False, True)):
+        a = capi.host_species("E-", 1, 19, oa, ca, aa)
+        b = capi.host_species("H_1", 2, 50, ob, cb, ab)
+        kw = dict(core_a=ca, core_b=cb, active_a=aa, active_b=ab, ionize_mo=mo, ionize_species=ion or ("NONE",),
+                  name_a="E-", name_b="H_1")
+        wc, sym = capi.host_windows(capi.host_control("C", mode, ionize_mo=mo, ionize_species=ion, pt_transition_operator=pto), a, b)
+        assert (wc, sym) == O.windows_c_inter(mode, 19, 50, oa, ob, **kw)
+        we, _ = capi.host_windows(capi.host_control("E", mode, ionize_mo=mo, ionize_species=ion, pt_transition_operator=pto), a, b)
+        assert we == O.windows_e_inter(mode, 19, 50, oa, ob, pt_transition_operator=pto, **kw)
+
+
+def test_window_literals_from_the_reference():
+    e = capi.host_species("E-", 1, 19, 5)
+    h = capi.host_species("H_1", 2, 50, 1)
+    assert capi.host_windows(capi.host_control("C", "MP2"), e) == ([1, 5, 6, 19, 1, 5, 6, 19], True)      # C.f90:1489-1501
+    assert capi.host_windows(capi.host_control("C", "PT2"), e) == ([5, 6, 1, 19, 1, 5, 6, 19], False)     # C.f90:1509-1520
+    assert capi.host_windows(capi.host_control("E", "MP2"), e)[0] == [6, 19, 1, 5, 6, 19, 1, 5]           # E.f90:1938-1949
+    assert capi.host_windows(capi.host_control("C", "MP2"), e, h) == ([1, 5, 6, 19, 1, 1, 2, 50], True)  # C.f90:1672-1684
+    assert capi.host_windows(capi.host_control("E", "PT2"), e, h)[0] == [1, 19, 1, 6, 1, 50, 1, 2]        # E.f90:2135-2145 (first species' core)
+    assert capi.host_windows(capi.host_control("E", "MP2-PT2"), e, h)[0] == [1, 19, 1, 6, 1, 19, 1, 2]    # E.f90:2283 quirk: r_u = active of A
+
+
+def test_ints_file_names():
+    ea, eb = capi.host_species("E-ALPHA", 1, 7, 3), capi.host_species("E-BETA", 2, 7, 2)
+    hh = capi.host_species("H_1", 3, 5, 1)
+    assert capi.host_ints_filename(0, ea) == ("0E-ALPHA.ints", False)
+    assert capi.host_ints_filename(3, eb) == ("3E-ALPHA.ints", False)                 # C.f90:241-245
+    assert capi.host_ints_filename(1, ea, eb) == ("1E-ALPHA.E-BETA.ints", False)      # C.f90:838-848
+    assert capi.host_ints_filename(0, eb, hh) == ("0E-ALPHA.H_1.ints", False)
+    assert capi.host_ints_filename(0, hh, eb) == ("0E-ALPHA.H_1.ints", True)          # C.f90:906-915 (reversed call order)
+    assert capi.host_ints_filename(2, hh, ea) == ("2E-ALPHA.H_1.ints", True)
+    assert capi.host_ints_filename(0, ea, hh) == ("0E-ALPHA.H_1.ints", False)
+
+
+def test_ints_stream_roundtrip_and_layout(tmp_path):
+    rng = np.random.default_rng(1)
+    for n, S in ((0, 4), (3, 4), (4, 4), (9, 4), (30, 7)):
+        p, q, r, s = (rng.integers(1, 9, n).astype(np.int32) for _ in range(4))
+        v = rng.uniform(-1, 1, n)
+        path = str(tmp_path / f"0X{n}.ints")
+        capi.host_write_ints_file(path, S, p, q, r, s, v)
+        nblocks = n // S + 1                                        # a terminator always follows the last entry
+        assert os.path.getsize(path) == nblocks * 24 * S             # C.f90:251-253: nblocks = filesize/24/S
+        raw = open(path, "rb").read()
+        blk = raw[(nblocks - 1) * 24 * S:]
+        assert struct.unpack_from("<i", blk, 4 * (n % S))[0] == -1  # p(counter) = -1, Libint2Iface.cpp:395-396
+        (gp, gq, gr, gs, gv), cnt = capi.host_read_ints_file(path, S, n + 5)
+        assert cnt == n and np.array_equal(gp, p) and np.array_equal(gq, q) and np.array_equal(gr, r) and np.array_equal(gs, s)
+        assert np.array_equal(gv, v)
+
+
+def _records(raw):
+    out, o = [], 0
+    while o < len(raw):
+        (ln,) = struct.unpack_from("<I", raw, o)
+        body = raw[o + 4:o + 4 + ln]
+        assert struct.unpack_from("<I", raw, o + 4 + ln)[0] == ln   # trailing gfortran marker
+        out.append(body)
+        o += 8 + ln
+    return out
+
+
+def read_moint_quads(path, S):
+    """ReadTransformedIntegrals.f90:225-236 (method C layout)."""
+    P, Q, R, Sx, V = [], [], [], [], []
+    for body in _records(open(path, "rb").read()):
+        assert len(body) == 24 * S
+        a = np.frombuffer(body, np.int32, 4 * S).reshape(4, S)
+        v = np.frombuffer(body, np.float64, S, 16 * S)
+        for i in range(S):
+            if a[0, i] == -1:
+                return tuple(np.array(x) for x in (P, Q, R, Sx, V))
+            P.append(a[0, i]); Q.append(a[1, i]); R.append(a[2, i]); Sx.append(a[3, i]); V.append(v[i])
+    raise AssertionError("no terminator record")
+
+
+def read_moint_pairs(path, S):
+    """ReadTransformedIntegrals.f90:302-311 (method E layout)."""
+    IJ, KL, V = [], [], []
+    for body in _records(open(path, "rb").read()):
+        assert len(body) == 24 * S
+        a = np.frombuffer(body, np.int64, 2 * S).reshape(2, S)
+        v = np.frombuffer(body, np.float64, S, 16 * S)
+        for i in range(S):
+            if a[0, i] == -1:
+                return np.array(IJ, np.int64), np.array(KL, np.int64), np.array(V)
+            IJ.append(a[0, i]); KL.append(a[1, i]); V.append(v[i])
+    raise AssertionError("no terminator record")
+
+
+def test_moint_record_layouts(tmp_path):
+    rng = np.random.default_rng(2)
+    for n, S in ((0, 5), (4, 5), (5, 5), (12, 5)):
+        p, q, r, s = (rng.integers(1, 9, n).astype(np.int32) for _ in range(4))
+        v = rng.uniform(-1, 1, n)
+        path = str(tmp_path / "Xmoint.dat")
+        capi.host_write_moint_quads(path, S, p, q, r, s, v)
+        assert os.path.getsize(path) == (n // S + 1) * (24 * S + 8)   # one sequential record per stack + terminator stack
+        g = read_moint_quads(path, S)
+        assert all(np.array_equal(a, b) for a, b in zip(g, (p, q, r, s, v)))
+        ij, kl = rng.integers(1, 99, n), rng.integers(1, 99, n)
+        capi.host_write_moint_pairs(path, S, ij, kl, v)
+        assert os.path.getsize(path) == (n // S + 1) * (24 * S + 8)
+        g = read_moint_pairs(path, S)
+        assert np.array_equal(g[0], ij) and np.array_equal(g[1], kl) and np.array_equal(g[2], v)
+
+
+def test_errors_are_reported():
+    with pytest.raises(capi.LowdinITError):
+        capi.host_windows(capi.host_control("Q", "MP2"), capi.host_species("E-", 1, 5, 2))
+    with pytest.raises(capi.LowdinITError):
+        capi.host_read_ints_file("/nonexistent/0E-.ints", 4, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# file -> GPU -> file, against the oracle
+# ---------------------------------------------------------------------------------------------
+def _split_to_files(tmp_path, name, lst, nfiles, S):
+    """lowdin-ints.x writes quartet k to file k % nthreads (Libint2Iface.cpp:282-286, :332)."""
+    for t in range(nfiles):
+        part = [x[t::nfiles] for x in lst]
+        capi.host_write_ints_file(str(tmp_path / f"{t}{name}.ints"), S, *part)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,mode", [("C", "MP2"), ("C", "ALL"), ("C", "PT2"), ("E", "MP2"), ("E", "MP2-PT2")])
+def test_one_species_file_to_file(O, T, tmp_path, method, mode):
+    n, occ, S, nfiles = 13, 4, 64, 3
+    packed = O.hash_packed_intra(61, n)
+    Cm = O.random_orthonormal(n, n)
+    _split_to_files(tmp_path, "E-", O.canonical_list_intra(packed, n), nfiles, S)
+    ctl = capi.host_control(method, mode, stack=S, nfiles=nfiles, scratch_dir=str(tmp_path))
+    sp = capi.host_species("E-", 1, n, occ, coeff=Cm)
+    cnt = capi.host_transform_one_species(T, ctl, sp)
+    path = str(tmp_path / "E-moint.dat")
+    if method == "C":
+        win, sym = O.windows_c_intra(mode, n, occ)
+        ref = O.transform_c_intra(Cm, packed, win, sym)
+        got = read_moint_quads(path, S)
+        assert len(got[4]) == cnt
+        assert np.abs(dense_quads(*got, n, n) - dense_quads(*ref, n, n)).max() <= 1e-10
+        assert_lists_match(got[:4], got[4], ref[:4], ref[4])
+        e_got = O.mp2_intra_from_quads(*[np.ascontiguousarray(x) for x in got], n, occ, O.synthetic_eps(occ, n))
+        e_ref = O.mp2_intra_from_quads(*ref, n, occ, O.synthetic_eps(occ, n))
+    else:
+        win = O.windows_e_intra(mode, n, occ)
+        ref = O.transform_e_intra(Cm, packed, win)
+        got = read_moint_pairs(path, S)
+        assert len(got[2]) == cnt
+        M = O.npairs(n)
+        assert np.abs(dense_pairs(*got, M, M) - dense_pairs(*ref, M, M)).max() <= 1e-10
+        assert_lists_match(got[:2], got[2], ref[:2], ref[2])
+        e_got = O.mp2_intra_from_pairs(*got, n, occ, O.synthetic_eps(occ, n))
+        e_ref = O.mp2_intra_from_pairs(*ref, n, occ, O.synthetic_eps(occ, n))
+    if mode == "MP2":
+        assert abs(e_got - e_ref) <= 1e-9          # downstream energy read back from the file
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["C", "E"])
+def test_two_species_file_to_file_both_call_orders(O, T, tmp_path, method):
+    na, nb, oa, ob, S = 9, 7, 3, 1, 50
+    rect = O.hash_rect_inter(17, na, nb)                       # stored (rs_B, pq_A)
+    Ca, Cb = O.random_orthonormal(na, 5), O.random_orthonormal(nb, 6)
+    lst = O.canonical_list_inter(rect, na, nb)                 # file order (A A|B B), A = lower species id
+    _split_to_files(tmp_path, "E-.H_1", lst, 2, S)
+    A = capi.host_species("E-", 1, na, oa, coeff=Ca)
+    B = capi.host_species("H_1", 2, nb, ob, coeff=Cb)
+    ctl = capi.host_control(method, "MP2", stack=S, nfiles=2, scratch_dir=str(tmp_path))
+    # forward order
+    cnt = capi.host_transform_two_species(T, ctl, A, B)
+    if method == "C":
+        win, sym = O.windows_c_inter("MP2", na, nb, oa, ob)
+        ref = O.transform_c_inter(Ca, Cb, rect, win, sym)
+        got = read_moint_quads(str(tmp_path / "E-.H_1moint.dat"), S)
+        assert len(got[4]) == cnt
+        assert np.abs(dense_quads(*got, na, nb) - dense_quads(*ref, na, nb)).max() <= 1e-10
+        # reversed call order (the species with fewer occupied orbitals first, IntegralTransformation.f90:322-334)
+        cnt2 = capi.host_transform_two_species(T, ctl, B, A)
+        rect_sw = O.scatter_inter(*lst, nb, na, swapped=True)
+        win2, sym2 = O.windows_c_inter("MP2", nb, na, ob, oa)
+        ref2 = O.transform_c_inter(Cb, Ca, rect_sw, win2, sym2)
+        got2 = read_moint_quads(str(tmp_path / "H_1.E-moint.dat"), S)
+        assert len(got2[4]) == cnt2
+        assert np.abs(dense_quads(*got2, nb, na) - dense_quads(*ref2, nb, na)).max() <= 1e-10
+        # same physical integrals, transposed roles
+        assert np.abs(dense_quads(*got2, nb, na).transpose(2, 3, 0, 1) - dense_quads(*got, na, nb)).max() <= 1e-10
+    else:
+        win = O.windows_e_inter("MP2", na, nb, oa, ob)
+        ref = O.transform_e_inter(Ca, Cb, rect, win)
+        got = read_moint_pairs(str(tmp_path / "E-.H_1moint.dat"), S)
+        assert len(got[2]) == cnt
+        Ma, Mb = O.npairs(na), O.npairs(nb)
+        assert np.abs(dense_pairs(*got, Ma, Mb) - dense_pairs(*ref, Ma, Mb)).max() <= 1e-10
+        assert_lists_match(got[:2], got[2], ref[:2], ref[2])
