@@ -99,6 +99,13 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
 
 /* ---- multi-GPU (one process per GPU; first half sharded over AO pair slabs,
  *      NCCL all-to-all, second half sharded over MO pairs) ----------------------------- */
+/* The division of work the library uses (no device needed; the CPU multi-rank test drives it):
+ * own[r]..own[r+1] = slots of rank r (fbeg[f] = first slot of first-contracted index f, nfb+1 entries);
+ * columns [col_lo,col_hi) of a chunk of chunk_width AO-pair slabs belong to `rank`, wblk = columns per rank.
+ * After the all-to-all rank r holds element (its local slot `row`, chunk column `col`) at lowdin_it_blocked_offset(). */
+int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_width, int nranks, int rank, int *own, int64_t *wblk,
+                         int64_t *col_lo, int64_t *col_hi);
+int64_t lowdin_it_blocked_offset(int64_t row, int64_t col, int64_t wblk, int64_t rows);
 int lowdin_it_comm_unique_id(char id[128]);
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]);
 

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "lowdin_it_ao_push_stacks", "lowdin_it_ao_end", "lowdin_it_ao_set_generator", "lowdin_it_transform",
     "lowdin_it_result_count", "lowdin_it_download_pairs", "lowdin_it_download_quads", "lowdin_it_transform_stream",
     "lowdin_it_stream_num_passes", "lowdin_it_transform_all", "lowdin_it_transform_inter_all",
-    "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_timers", "lowdin_it_kernel_bench",
+    "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_shard_plan", "lowdin_it_blocked_offset", "lowdin_it_timers", "lowdin_it_kernel_bench",
     "lowdin_it_set_profiling", "lowdin_it_set_option", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
 ]
 
@@ -69,6 +69,10 @@ def load():
     L.lowdin_it_transform_inter_all.argtypes = [_f64pf, _f64pf, _f64p, C.c_int, C.c_int]
     L.lowdin_it_comm_unique_id.argtypes = [C.c_char_p]
     L.lowdin_it_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
+    L.lowdin_it_shard_plan.argtypes = [C.c_int, _i32p, C.c_int64, C.c_int, C.c_int, _i32p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lowdin_it_blocked_offset.argtypes = [C.c_int64] * 4
+    L.lowdin_it_blocked_offset.restype = C.c_int64
     L.lowdin_it_timers.argtypes = [H, _f64p]
     L.lowdin_it_kernel_bench.argtypes = [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
@@ -200,6 +204,20 @@ class Transformer:
         X = np.zeros((nb, n, n))
         self._ck(self.L.lowdin_it_debug_expand(self.h, a, b, slab0, nb, X))
         return X
+
+
+def shard_plan(fbeg, chunk_width, nranks, rank):
+    """(own[nranks+1], wblk, col_lo, col_hi): the library's division of slots and chunk columns among ranks."""
+    fbeg = np.ascontiguousarray(fbeg, np.int32)
+    own = np.zeros(nranks + 1, np.int32)
+    w, lo, hi = C.c_int64(), C.c_int64(), C.c_int64()
+    if load().lowdin_it_shard_plan(len(fbeg) - 1, fbeg, chunk_width, nranks, rank, own, C.byref(w), C.byref(lo), C.byref(hi)):
+        raise LowdinITError("bad shard_plan arguments")
+    return own, w.value, lo.value, hi.value
+
+
+def blocked_offset(row, col, wblk, rows):
+    return load().lowdin_it_blocked_offset(row, col, wblk, rows)
 
 
 def unique_id() -> bytes:

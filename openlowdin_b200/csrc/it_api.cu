@@ -442,6 +442,15 @@ int second_half_partial(lowdin_it_handle h, const Plan &pl, const AoSource &hsrc
   return 0;
 }
 
+// How one chunk of `width` AO-pair slabs and the pass's slots are divided among G ranks:
+// slabs in G contiguous blocks of wblk columns; slots by contiguous blocks of first-contracted indices.
+void shard_plan(int nfb, const int *fbeg, int64_t width, int G, int rank, int *own, int64_t *wblk, int64_t *c_lo, int64_t *c_hi) {
+  for (int r = 0; r <= G; ++r) own[r] = fbeg[(int)((int64_t)nfb * r / G)];
+  *wblk = ceil_div(width, G);
+  *c_lo = std::min<int64_t>(width, *wblk * rank);
+  *c_hi = std::min<int64_t>(width, *c_lo + *wblk);
+}
+
 struct Consumer {
   int mode = 0;  // 0: compaction (download), 1: streaming reduce
   double tol = 1e-10;
@@ -484,7 +493,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       return 1;
     // slot ownership: rank r owns the slots of a contiguous block of first-contracted indices
     std::vector<int> own(G + 1, 0);
-    for (int r = 0; r <= G; ++r) own[r] = pt.fbeg[(int)((int64_t)nfb * r / G)];
+    { int64_t w_, a_, b_; shard_plan(nfb, pt.fbeg.data(), 0, G, h->rank, own.data(), &w_, &a_, &b_); }
     const int s_lo = own[h->rank], s_hi = own[h->rank + 1], nmine = s_hi - s_lo;
     // ---- device memory of the pass: T3 accumulators (own slots) + one chunk of half-transformed rows ----
     const size_t t3_bytes = std::max<size_t>((size_t)std::max(nmine, 1) * nf2 * ldt2, 1) * sizeof(double);
@@ -521,8 +530,8 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     float ms_first = 0, ms_exch = 0, ms_second = 0;
     for (const Chunk &ck : chunks) {
       // ---------------- first half (E.f90:1043-1132) over this rank's share of the chunk's slabs ----------------
-      const int64_t wblk = ceil_div(ck.width, G);
-      const int64_t c_lo = std::min<int64_t>(ck.width, wblk * h->rank), c_hi = std::min<int64_t>(ck.width, c_lo + wblk);
+      int64_t wblk, c_lo, c_hi;
+      shard_plan(nfb, pt.fbeg.data(), ck.width, G, h->rank, own.data(), &wblk, &c_lo, &c_hi);
       const int64_t ldh = (G > 1) ? wblk : ck.width;
       CK(h->H.ensure(std::max<size_t>((size_t)pt.nslots * ldh, 1) * sizeof(double)));
       CK(cudaEventRecord(h->ev[1], h->stream));
@@ -1030,6 +1039,15 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------
+int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_width, int nranks, int rank, int *own, int64_t *wblk,
+                         int64_t *col_lo, int64_t *col_hi) {
+  if (nfb < 1 || !fbeg || nranks < 1 || rank < 0 || rank >= nranks || !own || !wblk || !col_lo || !col_hi) return 1;
+  shard_plan(nfb, fbeg, chunk_width, nranks, rank, own, wblk, col_lo, col_hi);
+  return 0;
+}
+
+int64_t lowdin_it_blocked_offset(int64_t row, int64_t col, int64_t wblk, int64_t rows) { return blocked_offset(row, col, wblk, rows); }
+
 int lowdin_it_comm_unique_id(char id[128]) {
   std::string err;
   if (!load_nccl(err)) return fail(nullptr, err);

@@ -51,6 +51,13 @@ __host__ __device__ __forceinline__ double hash_value(uint64_t seed, uint64_t ke
   return 2.0 * ((double)(splitmix64(seed ^ key) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
 }
 
+// Offset of (row `slab`, column `pair`) in the chunk as it arrives from the all-to-all: one [rows][ld] block per
+// sending rank, ld = columns per rank.  Host-callable so that the CPU multi-rank test checks the same function.
+__host__ __device__ __forceinline__ int64_t blocked_offset(int64_t slab, int64_t pair, int64_t ld, int64_t rows) {
+  const int64_t blk = pair / ld;
+  return (blk * rows + slab) * ld + (pair - blk * ld);
+}
+
 __device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, int64_t pair) {
   switch (src.kind) {
     case SRC_SYM_PACKED: {
@@ -59,10 +66,8 @@ __device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, in
     }
     case SRC_RECT:
       return __ldg(src.data + (slab * src.ld + pair));
-    case SRC_RECT_BLOCKED: {
-      int64_t blk = pair / src.ld;
-      return __ldg(src.data + ((blk * src.aux + slab) * src.ld + (pair - blk * src.ld)));
-    }
+    case SRC_RECT_BLOCKED:
+      return __ldg(src.data + blocked_offset(slab, pair, src.ld, src.aux));
     case SRC_HASH_SYM: {
       int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
       return hash_value(src.seed, (uint64_t)(hi * src.M + lo));

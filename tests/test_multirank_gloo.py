@@ -1,0 +1,118 @@
+"""N>1 path on CPU (gloo, world_size 2): the library's division of work (lowdin_it_shard_plan) and the layout the
+all-to-all leaves behind (lowdin_it_blocked_offset) drive a numpy emulation of the two-half transform; the ranks'
+combined result must equal the oracle's.  The arithmetic here is numpy (test scaffolding); what is under test is the
+host-side sharding logic that the CUDA path uses unchanged."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, occ, rows_per_chunk, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openlowdin_b200 import capi
+        from oracle import oracle as O
+        M = O.npairs(n)
+        packed = O.hash_packed_intra(5, n)
+        Cm = np.asarray(O.random_orthonormal(n, n))
+        sq = O.packed_to_square(packed, M)
+        xy = O.pair_table(n)
+        V = n - occ
+        # MP2 window, transformer-E roles: slots (a virt, i occ), numbered f-major (f = i)
+        fbeg = np.arange(occ + 1, dtype=np.int32) * V
+        own, _, _, _ = capi.shard_plan(fbeg, 0, world, rank)
+        mine = own[rank + 1] - own[rank]
+        Hmine = np.zeros((mine, M))
+        Cv, Co = Cm[:, occ:], Cm[:, :occ]
+        for p0 in range(0, n, rows_per_chunk):
+            p1 = min(n, p0 + rows_per_chunk)
+            base, width = xy[p0, p0], sum(n - p for p in range(p0, p1))
+            own, wblk, lo, hi = capi.shard_plan(fbeg, width, world, rank)
+            # first half of my columns of the chunk, for ALL slots
+            Hc = np.zeros((occ * V, wblk))
+            for c in range(lo, hi):
+                X = sq[base + c][xy]                             # dense slab (mu,nu)
+                T2 = Cv.T @ X @ Co                               # [a][i]
+                Hc[:, c - lo] = T2.T.reshape(-1)                 # slot = i*V + a
+            # exchange: rows own[g]:own[g+1] go to rank g (grouped send/recv like ncclSend/ncclRecv)
+            recv = [torch.zeros(mine * wblk, dtype=torch.float64) for _ in range(world)]
+            reqs = []
+            for g in range(world):
+                blk = torch.from_numpy(np.ascontiguousarray(Hc[own[g]:own[g + 1]]).reshape(-1))
+                if g == rank:
+                    recv[g].copy_(blk)
+                else:
+                    reqs.append(dist.isend(blk, g))
+                    reqs.append(dist.irecv(recv[g], g))
+            for r in reqs:
+                r.wait()
+            flat = torch.cat(recv).numpy()                       # [g][slot_local][wblk]
+            for s in range(mine):
+                for c in range(width):
+                    Hmine[s, base + c] = flat[capi.blocked_offset(s, c, wblk, mine)]
+        # second half on my slots
+        out = {}
+        for s in range(mine):
+            Y = Hmine[s][xy]
+            out[own[rank] + s] = Cv.T @ Y @ Co                   # [b][j]
+        q.put((rank, int(own[rank]), int(own[rank + 1]), {k: v.copy() for k, v in out.items()}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,occ,rows", [(8, 3, 2), (7, 2, 4), (6, 4, 6)])
+def test_two_rank_sharding_reproduces_the_oracle(O, n, occ, rows):
+    world, port = 2, 29611 + n
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, occ, rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # slot ranges tile [0, occ*V) without overlap
+    res.sort()
+    V = n - occ
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == occ * V
+    packed = O.hash_packed_intra(5, n)
+    Cm = O.random_orthonormal(n, n)
+    ij, kl, v = O.transform_e_intra(Cm, packed, O.windows_e_intra("MP2", n, occ))
+    M = O.npairs(n)
+    ref = np.zeros((M, M))
+    ref[ij - 1, kl - 1] = v
+    xy = O.pair_table(n)
+    for _, _, _, out in res:
+        for slot, blk in out.items():
+            i, a = slot // V, occ + slot % V
+            for b in range(V):
+                for j in range(occ):
+                    want = ref[xy[i, a], xy[j, occ + b]]
+                    got = blk[b, j]
+                    assert abs(got - want) <= 1e-10 or abs(want) == 0.0 and abs(got) <= 1.1e-10
+
+
+def test_shard_plan_properties():
+    from openlowdin_b200 import capi
+    fbeg = np.array([0, 3, 7, 7, 12, 20], np.int32)
+    for G in (1, 2, 3, 5, 8):
+        cover = []
+        for r in range(G):
+            own, wblk, lo, hi = capi.shard_plan(fbeg, 101, G, r)
+            assert own[0] == 0 and own[G] == 20 and all(own[k] <= own[k + 1] for k in range(G))
+            assert all(o in fbeg for o in own)               # whole f-blocks only: exchange partners stay together
+            assert wblk * G >= 101 and 0 <= lo <= hi <= 101 and hi - lo <= wblk
+            cover += list(range(lo, hi))
+        assert cover == list(range(101))
+    assert capi.blocked_offset(2, 7, 5, 4) == (1 * 4 + 2) * 5 + 2
