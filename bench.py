@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 20261017
+GEN_KIND = 1
 
 
 def mp2_window_e(n, occ):
@@ -181,6 +182,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
+    ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -216,7 +219,9 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         T.comm_init(rank, world, uid[0])
     T.set_species(0, Cm)
-    T.set_generator(0, 0, SEED)
+    if args.q1_variant:
+        T.set_option(T.OPT_Q1_VARIANT, args.q1_variant)
+    T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 
     def barrier():
@@ -264,7 +269,7 @@ def main():
     e2e_flops = 0.0
     for i in range(e2e_steps):
         T.set_species(0, Cpin)           # H2D: coefficients
-        T.set_generator(0, 0, SEED)
+        T.set_generator(0, 0, SEED, args.gen)
         s = one_pass(args.warmup + i)    # H2D: orbital energies; D2H: sums
         e2e_flops += T.timers()["flops"]
     barrier()

@@ -39,7 +39,8 @@ typedef struct lowdin_it_ctx *lowdin_it_handle;
 #define LOWDIN_IT_CONV_E 1 /* transformer E: pair ids (ij,kl), j<=i, l<=k, half-drop (TransformIntegralsE.f90:1043-1260) */
 
 /* Synthetic AO generators (benchmark inputs). */
-#define LOWDIN_IT_GEN_HASH 1 /* value = 2u-1, u = (splitmix64(seed ^ key) >> 11) * 2^-53 */
+#define LOWDIN_IT_GEN_HASH 1 /* kind H: value = 2u-1, u = (splitmix64(seed ^ key) >> 11) * 2^-53 */
+#define LOWDIN_IT_GEN_FOLD 2 /* kind F: same, with mulfold64(x) = ((x*K1) ^ ((x*K1)>>32)) * K2 instead of splitmix64 */
 
 /* ---- lifetime --------------------------------------------------------------------- */
 /* Replaces the per-call malloc/free of IntTransfD.cpp:131-143: device buffers live in the handle. */
@@ -112,6 +113,8 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
 /* ---- tuning ----------------------------------------------------------------------- */
 #define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
 #define LOWDIN_IT_OPT_CHUNK_COLS 2      /* cap on AO-pair columns per chunk of the half-transformed block (0 = from free HBM) */
+#define LOWDIN_IT_OPT_Q1_VARIANT 3      /* fused generation + first quarter: 1 = shared-memory ring, 2 = L1 path without barriers */
+#define LOWDIN_IT_OPT_BENCH_GEN 4       /* generator kind used by lowdin_it_kernel_bench kind 2 */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 
 /* ---- instrumentation -------------------------------------------------------------- */

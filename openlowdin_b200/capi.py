@@ -8,7 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CONV_C, CONV_E = 0, 1
-GEN_HASH = 1
+GEN_HASH, GEN_FOLD = 1, 2
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
@@ -175,7 +175,7 @@ class Transformer:
 
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
-    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS = 1, 2
+    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN = 1, 2, 3, 4
 
     def set_option(self, option, value):
         self._ck(self.L.lowdin_it_set_option(self.h, option, int(value)))

@@ -102,6 +102,8 @@ struct lowdin_it_ctx {
   int rank = 0, nranks = 1;
   void *comm = nullptr;
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
+  int q1_variant = 1;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier
+  int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
   bool prof_on = false;
@@ -318,17 +320,21 @@ int launch_expand(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_
 template <int TN>
 cudaError_t launch_q1_gen_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
                               int nfb, double *T1t, int64_t ldt) {
-  constexpr int ST = 4;
-  constexpr size_t smem = (size_t)ST * (TN * 8) * 20 * sizeof(double);
-  auto kern = q1_gen_kernel<TN, ST>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   dim3 grid((unsigned)ceil_div(nc, 128), (unsigned)bc);
-  kern<<<grid, 256, smem, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  if (h->q1_variant == 1) {  // coefficient window through a shared-memory ring
+    constexpr int ST = 4;
+    constexpr size_t smem = (size_t)ST * (TN * 8) * 20 * sizeof(double);
+    auto kern = q1_gen_smem_kernel<TN, ST>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<grid, 256, smem, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  } else {
+    q1_gen_kernel<TN><<<grid, 256, 0, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  }
   h->launches += 1;
   return cudaGetLastError();
 }
@@ -822,10 +828,10 @@ int lowdin_it_ao_end(lowdin_it_handle h) {
 int lowdin_it_ao_set_generator(lowdin_it_handle h, int a, int b, int kind, uint64_t seed) {
   if (!h) return 1;
   if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].n || !h->sp[b].n) return fail(h, "ao_set_generator: species not set");
-  if (kind != LOWDIN_IT_GEN_HASH) return fail(h, "unknown generator kind");
+  if (kind != LOWDIN_IT_GEN_HASH && kind != LOWDIN_IT_GEN_FOLD) return fail(h, "unknown generator kind");
   AoSet &S = h->ao[a][b];
   S.data.release();
-  S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed};
+  S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed, kind} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed, kind};
   S.valid = true;
   return 0;
 }
@@ -957,6 +963,12 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
     case LOWDIN_IT_OPT_CHUNK_COLS:
       if (value < 0) return fail(h, "negative chunk column limit");
       h->chunk_cols_limit = value; return 0;
+    case LOWDIN_IT_OPT_Q1_VARIANT:
+      if (value != 1 && value != 2) return fail(h, "q1 variant must be 1 or 2");
+      h->q1_variant = (int)value; return 0;
+    case LOWDIN_IT_OPT_BENCH_GEN:
+      if (value != 1 && value != 2) return fail(h, "generator kind must be 1 or 2");
+      h->bench_gen = (int)value; return 0;
     default: return fail(h, "unknown option");
   }
 }
@@ -1080,7 +1092,7 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
   if (kind == 0) {  // slab expansion of n slabs of an m-function hash tensor
     const int nc = (int)m; const int64_t ldx = roundup2(nc);
     CK(h->X.ensure((size_t)n * nc * ldx * sizeof(double)));
-    AoSource src{(int)k /* source kind */, nullptr, npairs(nc), npairs(nc), npairs(nc), 12345};
+    AoSource src{(int)k /* source kind */, nullptr, npairs(nc), npairs(nc), npairs(nc), 12345, 1};
     if (src.kind == SRC_SYM_PACKED || src.kind == SRC_RECT) {
       const int64_t M = npairs(nc);
       const size_t cnt = (src.kind == SRC_SYM_PACKED) ? (size_t)(M * (M + 1) / 2) : (size_t)(n * M);
@@ -1096,6 +1108,21 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (check) CK(cudaMemcpy(check, h->X.p, sizeof(double), cudaMemcpyDeviceToHost));
+  } else if (kind == 2) {  // fused slab generation + first quarter: m = basis size, n = window columns, k = slabs per launch
+    const int nc = (int)m, nfb = (int)n, bc = (int)k;
+    const int64_t ldc = roundup2(nc), ldt = roundup2(nc);
+    CK(h->X.ensure((size_t)nfb * ldc * sizeof(double)));
+    CK(h->T1t.ensure((size_t)bc * nfb * ldt * sizeof(double)));
+    CK(cudaMemsetAsync(h->X.p, 0x3f, (size_t)nfb * ldc * sizeof(double), h->stream));
+    AoSource src{SRC_HASH_SYM, nullptr, npairs(nc), 0, 0, 12345, h->bench_gen};
+    if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < iters; ++i)
+      if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (check) CK(cudaMemcpy(check, h->T1t.p, sizeof(double), cudaMemcpyDeviceToHost));
   } else {  // DGEMM m x n x k on generated operands
     const int64_t lda = roundup2(k);
     CK(h->X.ensure((size_t)m * lda * sizeof(double)));

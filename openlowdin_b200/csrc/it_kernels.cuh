@@ -39,6 +39,7 @@ struct AoSource {
   int64_t ld;   // SRC_RECT row stride
   int64_t aux;  // SRC_HASH_RECT: number of slabs (M_b)
   uint64_t seed;
+  int gen;      // generated sources: 1 = splitmix64 (kind H), 2 = mul-fold-mul (kind F)
 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -47,8 +48,29 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__host__ __device__ __forceinline__ double hash_value(uint64_t seed, uint64_t key) {
-  return 2.0 * ((double)(splitmix64(seed ^ key) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+// kind F ("mul-fold-mul"): two odd 64-bit multiplies around a 32-bit fold -- a bijection of the 64-bit key like
+// splitmix64, at a third of the integer instructions (the slab generator is a stand-in for AO production; it must be a
+// pure function of the canonical index, not a strong hash).
+__host__ __device__ __forceinline__ uint64_t mulfold64(uint64_t x) {
+  x *= 0x9E3779B97F4A7C15ull;
+  x ^= x >> 32;
+  return x * 0xD6E8FEB86659FD93ull;
+}
+// bits -> value in [-1,1): 2u-1 with u = (bits >> 11) * 2^-53, i.e. (2(bits>>11) - 2^53) * 2^-53, exact in FP64.
+// The device form converts the signed integer (XU pipe) and rescales by an exponent subtraction, so that no FP64-pipe
+// instruction (the pipe the DMMAs run on) is spent on generation; the value is identical to the host expression.
+__host__ __device__ __forceinline__ double bits_to_value(uint64_t bits) {
+#ifdef __CUDA_ARCH__
+  const long long t = (long long)((bits >> 11) << 1) - (1ll << 53);
+  const double d = __ll2double_rn(t);
+  const int hi = __double2hiint(d), lo = __double2loint(d);
+  return __hiloint2double(t ? hi - (53 << 20) : hi, lo);
+#else
+  return 2.0 * ((double)(bits >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+#endif
+}
+__host__ __device__ __forceinline__ double hash_value(int gen, uint64_t seed, uint64_t key) {
+  return bits_to_value(gen == 2 ? mulfold64(seed ^ key) : splitmix64(seed ^ key));
 }
 
 // Offset of (row `slab`, column `pair`) in the chunk as it arrives from the all-to-all: one [rows][ld] block per
@@ -70,10 +92,10 @@ __device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, in
       return __ldg(src.data + blocked_offset(slab, pair, src.ld, src.aux));
     case SRC_HASH_SYM: {
       int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
-      return hash_value(src.seed, (uint64_t)(hi * src.M + lo));
+      return hash_value(src.gen, src.seed, (uint64_t)(hi * src.M + lo));
     }
     default:
-      return hash_value(src.seed, (uint64_t)(pair * src.aux + slab));
+      return hash_value(src.gen, src.seed, (uint64_t)(pair * src.aux + slab));
   }
 }
 
@@ -335,11 +357,12 @@ __device__ __forceinline__ double gen_value(const AoSource &src, uint32_t slab, 
   } else {
     key = (uint64_t)pair * (uint64_t)src.aux + slab;
   }
-  return hash_value(src.seed, key);
+  return hash_value(src.gen, src.seed, key);
 }
 
+// Variant with the coefficient window staged through a cp.async shared-memory ring (block-wide barrier per k-tile).
 template <int TN, int STAGES>
-__global__ void __launch_bounds__(256) q1_gen_kernel(AoSource src, int64_t slab0, int bc, int nc, const double *__restrict__ Cf,
+__global__ void __launch_bounds__(256) q1_gen_smem_kernel(AoSource src, int64_t slab0, int bc, int nc, const double *__restrict__ Cf,
                                                      int64_t ldc, int nfb, double *__restrict__ T1t, int64_t ldt) {
   constexpr int BN = TN * 8, BK = 16, LDS = BK + 4, NT = 256, TM = 2;
   extern __shared__ __align__(16) double smem[];  // [STAGES][BN][LDS]
@@ -398,17 +421,14 @@ __global__ void __launch_bounds__(256) q1_gen_kernel(AoSource src, int64_t slab0
       if (nk < KT) load_b(nk % STAGES, nk);
       cp_async_commit();
     }
-    // generate the next k-tile's fragments while this tile's DMMAs are in flight (k beyond nc multiplies zero-filled B)
-    if (kt + 1 < KT) {
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          a_nxt[i][kk] = gen_value(src, slab, min(mu[i], n - 1u), min((uint32_t)((kt + 1) * BK + kk * 4 + tig), n - 1u), n);
-    }
     const double *bs = smem + (kt % STAGES) * BN * LDS + grp * LDS + tig;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      // the next k-tile's fragment for this kk is hashed between the DMMA groups, so that every warp always has
+      // tensor work queued behind its integer work (k beyond nc multiplies zero-filled B)
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+        a_nxt[i][kk] = gen_value(src, slab, min(mu[i], n - 1u), min((uint32_t)((kt + 1) * BK + kk * 4 + tig), n - 1u), n);
       double b[TN];
 #pragma unroll
       for (int j = 0; j < TN; ++j) b[j] = bs[j * 8 * LDS + kk * 4];
@@ -419,6 +439,80 @@ __global__ void __launch_bounds__(256) q1_gen_kernel(AoSource src, int64_t slab0
     }
   }
   cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + warp * 16 + i * 8 + grp;
+    if (m >= nc) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int f = j * 8 + tig * 2;
+      if (f < nfb) T1t[((int64_t)f * bc + z) * ldt + m] = acc[i][j][0];
+      if (f + 1 < nfb) T1t[((int64_t)(f + 1) * bc + z) * ldt + m] = acc[i][j][1];
+    }
+  }
+}
+
+// No shared memory and no block-wide barrier: the A fragments come from the hash, the B fragments (coefficient window,
+// 8 columns x 32 bytes per load, identical for all warps of all CTAs on the SM) from L1 through the read-only path.
+// Each warp therefore runs its own software pipeline (next k-step's hash + loads issued before this k-step's DMMAs)
+// and the warps of an SM drift apart, which keeps the FP64 tensor pipe fed while other warps are hashing.
+template <int TN>
+__global__ void __launch_bounds__(256, 2) q1_gen_kernel(AoSource src, int64_t slab0, int bc, int nc, const double *__restrict__ Cf,
+                                                        int64_t ldc, int nfb, double *__restrict__ T1t, int64_t ldt) {
+  constexpr int TM = 2;
+  const int z = blockIdx.y;
+  const uint32_t slab = (uint32_t)(slab0 + z);
+  const int m0 = blockIdx.x * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 2, tig = lane & 3;
+  const uint32_t n = (uint32_t)nc;
+  const int KS = (nc + 3) >> 2;
+
+  uint32_t mu[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) mu[i] = min((uint32_t)(m0 + warp * 16 + i * 8 + grp), n - 1u);
+  const double *bp[TN];
+  bool bok[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int f = j * 8 + grp;
+    bok[j] = f < nfb;
+    bp[j] = Cf + (int64_t)(bok[j] ? f : 0) * ldc + tig;
+  }
+
+  double acc[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double a_cur[TM], b_cur[TN];
+  {
+    const bool kok = tig < nc;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a_cur[i] = gen_value(src, slab, mu[i], min((uint32_t)tig, n - 1u), n);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b_cur[j] = (bok[j] && kok) ? __ldg(bp[j]) : 0.0;
+  }
+#pragma unroll 2
+  for (int ks = 0; ks < KS; ++ks) {
+    double a_nxt[TM], b_nxt[TN];
+    const int kn = (ks + 1) * 4 + tig;
+    const bool kok = kn < nc;  // also false past the last k-step
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b_nxt[j] = (bok[j] && kok) ? __ldg(bp[j] + (ks + 1) * 4) : 0.0;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a_nxt[i] = gen_value(src, slab, mu[i], min((uint32_t)kn, n - 1u), n);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a_cur[i], b_cur[j]);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a_cur[i] = a_nxt[i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b_cur[j] = b_nxt[j];
+  }
 
 #pragma unroll
   for (int i = 0; i < TM; ++i) {

@@ -489,6 +489,18 @@ double orc_hash_value(uint64_t seed, uint64_t key) {
   return 2.0 * ((double)(splitmix64(seed ^ key) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
 }
 
+/* kind F: the same value map over mulfold64(x) = ((x*K1) ^ ((x*K1) >> 32)) * K2 (two odd multiplies around a
+ * 32-bit fold: a bijection of the key, a third of splitmix64's integer work on the GPU). */
+static inline uint64_t mulfold64(uint64_t x) {
+  x *= 0x9E3779B97F4A7C15ull;
+  x ^= x >> 32;
+  return x * 0xD6E8FEB86659FD93ull;
+}
+double orc_gen_value(int kind, uint64_t seed, uint64_t key) {
+  if (kind == 2) return 2.0 * ((double)(mulfold64(seed ^ key) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+  return orc_hash_value(seed, key);
+}
+
 /* Fill the packed intra array (C/E layout, 1-based pair ids pq<=rs stored at
  * ioff(pq)+rs) with kind-H values.  Canonical key uses 0-based ids, PQ>=RS. */
 void orc_fill_hash_intra(uint64_t seed, int nbf, double *packed) {
@@ -499,6 +511,17 @@ void orc_fill_hash_intra(uint64_t seed, int nbf, double *packed) {
 }
 
 /* rect[(rs-1)*Ma + pq] = hash(seed, PQ*Mb + RS), PQ of species A, RS of species B (0-based). */
+void orc_fill_gen_intra(int kind, uint64_t seed, int nbf, double *packed) {
+  int64_t M = (int64_t)nbf * (nbf + 1) / 2;
+  for (int64_t lo = 1; lo <= M; ++lo)
+    for (int64_t hi = lo; hi <= M; ++hi)
+      packed[orc_ioff(lo, M) + hi - 1] = orc_gen_value(kind, seed, (uint64_t)((hi - 1) * M + (lo - 1)));
+}
+void orc_fill_gen_inter(int kind, uint64_t seed, int na, int nb, double *rect) {
+  int64_t Ma = (int64_t)na * (na + 1) / 2, Mb = (int64_t)nb * (nb + 1) / 2;
+  for (int64_t rs = 0; rs < Mb; ++rs)
+    for (int64_t pq = 0; pq < Ma; ++pq) rect[rs * Ma + pq] = orc_gen_value(kind, seed, (uint64_t)(pq * Mb + rs));
+}
 void orc_fill_hash_inter(uint64_t seed, int na, int nb, double *rect) {
   int64_t Ma = (int64_t)na * (na + 1) / 2, Mb = (int64_t)nb * (nb + 1) / 2;
   for (int64_t rs = 0; rs < Mb; ++rs)

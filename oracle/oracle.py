@@ -86,6 +86,12 @@ def lib():
         L.orc_fill_hash_intra.argtypes = [C.c_uint64, C.c_int, _f64p]
         L.orc_fill_hash_inter.restype = None
         L.orc_fill_hash_inter.argtypes = [C.c_uint64, C.c_int, C.c_int, _f64p]
+        L.orc_fill_gen_intra.restype = None
+        L.orc_fill_gen_intra.argtypes = [C.c_int, C.c_uint64, C.c_int, _f64p]
+        L.orc_fill_gen_inter.restype = None
+        L.orc_fill_gen_inter.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, _f64p]
+        L.orc_gen_value.restype = C.c_double
+        L.orc_gen_value.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
         L.orc_e_first_half_sample.restype = C.c_double
         L.orc_e_first_half_sample.argtypes = [C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int]
         L.orc_reader_pairs_intra.restype = None
@@ -204,16 +210,17 @@ def synthetic_eps(occ, n):
     return np.concatenate([np.linspace(-2.0, -0.5, occ), np.linspace(0.2, 3.0, n - occ)])
 
 
-def hash_packed_intra(seed, n):
+def hash_packed_intra(seed, n, kind=1):
+    """Synthetic AO tensor, packed C/E layout.  kind 1 = H (splitmix64), 2 = F (mul-fold-mul)."""
     M = npairs(n)
     out = np.empty(M * (M + 1) // 2)
-    lib().orc_fill_hash_intra(seed, n, out)
+    lib().orc_fill_gen_intra(kind, seed, n, out)
     return out
 
 
-def hash_rect_inter(seed, na, nb):
+def hash_rect_inter(seed, na, nb, kind=1):
     out = np.empty(npairs(na) * npairs(nb))
-    lib().orc_fill_hash_inter(seed, na, nb, out)
+    lib().orc_fill_gen_inter(kind, seed, na, nb, out)
     return out
 
 

@@ -314,3 +314,32 @@ def test_chunked_stream_mp2_energy_intra(O, T, chunked):
         assert sums[0] == len(rv)
         assert abs(sums[2] - (rv * rv).sum()) <= 1e-9
         assert abs(sums[3] - e_orc) <= 1e-9
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("kind", [1, 2])
+def test_generator_kinds_and_fused_kernel_variants(O, T, kind, variant):
+    """Both synthetic generators (H: splitmix64, F: mul-fold-mul) are bit-identical on host and device, through the
+    expansion kernel and through both variants of the fused generation + first-quarter kernel."""
+    n = 21
+    seed = 1000 + kind
+    packed = O.hash_packed_intra(seed, n, kind)
+    Cm = O.random_orthonormal(n, n)
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, seed, kind)
+    M = O.npairs(n)
+    assert np.array_equal(T.debug_expand(0, 0, 0, M), O.packed_to_square(packed, M)[:, O.pair_table(n)])
+    win = O.windows_e_intra("MP2", n, 6)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    T.set_option(T.OPT_Q1_VARIANT, variant)
+    try:
+        ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+    finally:
+        T.set_option(T.OPT_Q1_VARIANT, 1)
+    assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
+    assert_lists_match((ij, kl), v, (rij, rkl), rv)
+    na, nb = 8, 6
+    rect = O.hash_rect_inter(seed, na, nb, kind)
+    T.set_species(1, O.random_orthonormal(na, 1)); T.set_species(2, O.random_orthonormal(nb, 2))
+    T.set_generator(1, 2, seed, kind)
+    assert np.array_equal(T.debug_expand(1, 2, 0, O.npairs(nb)), rect.reshape(O.npairs(nb), O.npairs(na))[:, O.pair_table(na)])
