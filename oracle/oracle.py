@@ -607,3 +607,34 @@ def e_first_half_sample(seed, Cm, win, pq0, npq, nthreads=1):
     """CPU baseline sample: first half of transformer E on npq slabs of the kind-H tensor."""
     n = Cm.shape[0]
     return lib().orc_e_first_half_sample(seed, n, np.asfortranarray(Cm), n, _win(win), pq0, npq, nthreads)
+
+
+# ----------------------------------------------------------------------------------------
+# large-N checks: vectorised AO list of a dense pair matrix, closed-form MO integrals of a rank-K tensor
+# ----------------------------------------------------------------------------------------
+def list_from_pair_matrix_intra(sq, n, rows_per_block=256):
+    """Every unique (pq|rs), pq<=rs in xy numbering, of a symmetric [M,M] pair matrix as 1-based AO quartets
+    (the loader is order independent, C.f90:262-273).  Yields blocks (p,q,r,s,v) to bound memory."""
+    M = npairs(n)
+    i1, i2 = np.triu_indices(n)
+    for a0 in range(0, M, rows_per_block):
+        a1 = min(M, a0 + rows_per_block)
+        a = np.repeat(np.arange(a0, a1), M)
+        b = np.tile(np.arange(M), a1 - a0)
+        keep = b >= a
+        a, b = a[keep], b[keep]
+        yield ((i2[a] + 1).astype(np.int32), (i1[a] + 1).astype(np.int32), (i2[b] + 1).astype(np.int32),
+               (i1[b] + 1).astype(np.int32), np.ascontiguousarray(sq[a, b]))
+
+
+def rankk_mo_block(La, Ca, rows_a, cols_a, Lb=None, Cb=None, rows_b=None, cols_b=None):
+    """Closed form of the MO integrals of (mu nu|lam sig) = sum_k La^k[mu,nu] Lb^k[lam,sig]:
+    (p q|r s) = sum_k (Ca^T La^k Ca)[p,q] (Cb^T Lb^k Cb)[r,s] for p in rows_a, q in cols_a, r in rows_b, s in cols_b
+    (0-based orbital index arrays) -> array [len(rows_a), len(cols_a), len(rows_b), len(cols_b)].  O(K N^3)."""
+    Lb = La if Lb is None else Lb
+    Cb = Ca if Cb is None else Cb
+    rows_b = rows_a if rows_b is None else rows_b
+    cols_b = cols_a if cols_b is None else cols_b
+    Ta = np.einsum("mp,kmn,nq->kpq", np.asarray(Ca)[:, rows_a], La, np.asarray(Ca)[:, cols_a], optimize=True)
+    Tb = np.einsum("mp,kmn,nq->kpq", np.asarray(Cb)[:, rows_b], Lb, np.asarray(Cb)[:, cols_b], optimize=True)
+    return np.einsum("kpq,krs->pqrs", Ta, Tb, optimize=True)
