@@ -175,7 +175,7 @@ class Transformer:
 
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
-    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN = 1, 2, 3, 4
+    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT = 1, 2, 3, 4, 5
 
     def set_option(self, option, value):
         self._ck(self.L.lowdin_it_set_option(self.h, option, int(value)))

@@ -6,6 +6,7 @@
 // :1285-1837 (two-half), TransformIntegralsC.f90:141-471, :728-1168 (window/skip semantics),
 // IntTransfD.cpp:125-181, :245-323 (full in-place transform behind the same style of C ABI).
 #include "it_kernels.cuh"
+#include "it_gemm_tma.cuh"
 #include "../../include/lowdin_it.h"
 
 #include <dlfcn.h>
@@ -103,6 +104,8 @@ struct lowdin_it_ctx {
   void *comm = nullptr;
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
   int q1_variant = 1;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier
+  int gemm_variant = 1;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
+  int num_sms = 148;
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
@@ -175,19 +178,72 @@ cudaError_t launch_gemm_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &ep
   return cudaGetLastError();
 }
 
+// ---- TMA + mbarrier persistent GEMM (it_gemm_tma.cuh) -----------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (TensorMapEncodeFn)p;
+  }();
+  return fn;
+}
+// [rows][K] FP64 operand, K contiguous, row stride ld doubles; box = 16 doubles x box_rows rows, 128-byte swizzle, zero fill
+bool make_operand_map(CUtensorMap *m, const double *base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  TensorMapEncodeFn fn = tensor_map_encoder();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool tma_eligible(const GemmArgs &g) {
+  return ((uintptr_t)g.A % 16 == 0) && ((uintptr_t)g.B % 16 == 0) && (g.lda % 2 == 0) && (g.ldb % 2 == 0) && g.K >= 1 &&
+         g.strideA == 0 && g.strideB == 0 && tensor_map_encoder() != nullptr;
+}
+
+template <int BM, int BN, int WM, int WN, class Epi>
+cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
+  constexpr int ST_RAW = (int)(200704 / ((BM + BN) * 128));
+  constexpr int ST = ST_RAW > 8 ? 8 : ST_RAW;
+  constexpr size_t smem = tma_gemm_smem_bytes<BM, BN, ST>();
+  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap mapA, mapB;
+  if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda, BM) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, BN)) return cudaErrorInvalidValue;
+  const int64_t ntiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
+  kern<<<grid, WM * WN * 32, smem, h->stream>>>(mapA, mapB, TmaGemmShape{g.M, g.N, g.K}, epi);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+
 template <class Epi>
 cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   const int n = g.N;
-  if (n <= 8) return launch_gemm_cfg<256, 8, 8, 1>(h, g, epi);
-  if (n <= 16) return launch_gemm_cfg<256, 16, 8, 1>(h, g, epi);
-  if (n <= 32) return launch_gemm_cfg<256, 32, 8, 1>(h, g, epi);
-  if (n <= 64) return launch_gemm_cfg<128, 64, 4, 2>(h, g, epi);
+  const bool tma = (h->gemm_variant == 2) && tma_eligible(g);
+#define LOWDIN_GEMM_CFG(BM, BN, WM, WN) (tma ? launch_gemm_tma_cfg<BM, BN, WM, WN>(h, g, epi) : launch_gemm_cfg<BM, BN, WM, WN>(h, g, epi))
+  if (n <= 8) return LOWDIN_GEMM_CFG(256, 8, 8, 1);
+  if (n <= 16) return LOWDIN_GEMM_CFG(256, 16, 8, 1);
+  if (n <= 32) return LOWDIN_GEMM_CFG(256, 32, 8, 1);
+  if (n <= 64) return LOWDIN_GEMM_CFG(128, 64, 4, 2);
   // pick the N tile with the least padding (ties -> the larger tile)
   const int64_t p128 = ceil_div(n, 128) * 128, p80 = ceil_div(n, 80) * 80, p64 = ceil_div(n, 64) * 64;
-  if (p128 <= p80 && p128 <= p64) return launch_gemm_cfg<128, 128, 2, 4>(h, g, epi);
-  if (p80 <= p64) return launch_gemm_cfg<128, 80, 4, 2>(h, g, epi);
-  return launch_gemm_cfg<128, 64, 4, 2>(h, g, epi);
+  if (p128 <= p80 && p128 <= p64) return LOWDIN_GEMM_CFG(128, 128, 2, 4);
+  if (p80 <= p64) return LOWDIN_GEMM_CFG(128, 80, 4, 2);
+  return LOWDIN_GEMM_CFG(128, 64, 4, 2);
+#undef LOWDIN_GEMM_CFG
 }
 
 // ---- plan -------------------------------------------------------------------------------------
@@ -722,6 +778,7 @@ int lowdin_it_create(int device, lowdin_it_handle *out) {
   if (prop.major != 10) return fail(nullptr, "this build targets sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
   h = new lowdin_it_ctx();
   h->device = device;
+  h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, "cudaStreamCreate failed"); }
   for (auto &ev : h->ev) cudaEventCreate(&ev);
   *out = h;
@@ -966,6 +1023,10 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
     case LOWDIN_IT_OPT_Q1_VARIANT:
       if (value != 1 && value != 2) return fail(h, "q1 variant must be 1 or 2");
       h->q1_variant = (int)value; return 0;
+    case LOWDIN_IT_OPT_GEMM_VARIANT:
+      if (value != 1 && value != 2) return fail(h, "gemm variant must be 1 or 2");
+      if (value == 2 && !tensor_map_encoder()) return fail(h, "cuTensorMapEncodeTiled is not available from this driver");
+      h->gemm_variant = (int)value; return 0;
     case LOWDIN_IT_OPT_BENCH_GEN:
       if (value != 1 && value != 2) return fail(h, "generator kind must be 1 or 2");
       h->bench_gen = (int)value; return 0;

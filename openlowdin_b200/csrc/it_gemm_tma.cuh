@@ -1,0 +1,195 @@
+// it_gemm_tma.cuh -- FP64 tensor-core GEMM with a TMA + mbarrier producer/consumer pipeline (sm_100a).
+//
+//   C[m][n] = sum_k A[m][k] B[n][k]        A: [M][K], B: [N][K], both K-contiguous (the quarter transforms of
+//                                          TransformIntegralsE.f90:1081-1110, :1213-1239 in this layout)
+//
+// Differences from dgemm_tn_kernel (it_kernels.cuh):
+//   * ONE lane (lane 0 of warp 0) issues cp.async.bulk.tensor (TMA) loads of 128-byte-swizzled [rows][16 doubles]
+//     boxes into a STAGES-deep shared-memory ring, each load signalling the stage's "full" mbarrier; no thread computes
+//     a per-element global address and the warps never meet at a block-wide barrier: each warp waits on the stage's
+//     mbarrier, runs its DMMAs and arrives on the stage's "empty" mbarrier, which the producing lane polls without
+//     blocking.  (A dedicated producer warp would make the CTA 288 threads, which the register file allocates as 384
+//     and caps at 168 registers per thread -- the 128x128 tile needs more -- so the producer rides on a consumer warp.)
+//   * the kernel is persistent (one CTA per SM, tiles walked m-fastest so that concurrently processed tiles share the
+//     streamed operand in L2) and the ring keeps filling with the next tile's k-tiles while the warps are in the epilogue;
+//   * fragments are read with 128-bit shared loads: lane (grp,tig) reads the 16-byte chunk (4h+tig) of row grp, i.e.
+//     k = 8h+2tig and 8h+2tig+1, and feeds the two values to two DMMAs.  Both operands use the same k permutation,
+//     so the sum over k is unchanged.  With the 128B swizzle (chunk ^= row & 7) a warp's 512 bytes hit every bank
+//     group exactly four times: the 4-wavefront minimum, no padding.
+// K tails and row tails are zero-filled by TMA (out-of-bounds box elements), so there is no predication in the loop.
+#pragma once
+#include <cuda.h>
+#include "it_kernels.cuh"
+
+namespace lowdin {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol error becomes a kernel fault (reported through the C ABI) instead of a hung device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+struct TmaGemmShape {
+  int M, N, K;
+};
+
+template <int BM, int BN, int STAGES>
+constexpr size_t tma_gemm_smem_bytes() {
+  return (size_t)STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024;  // ring + barriers + alignment slack
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES, class Epi>
+__global__ void __launch_bounds__(WM *WN * 32, 1)
+    dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaGemmShape g, Epi epi) {
+  constexpr int BK = 16;
+  constexpr int NCW = WM * WN;  // warps; all of them consume, lane 0 of warp 0 also produces
+  constexpr int TM = BM / WM / 8, TN = BN / WN / 8;
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(BM % (WM * 8) == 0 && BN % (WN * 8) == 0, "tile/warp mismatch");
+  static_assert(BM <= 256 && BN <= 256, "TMA box rows");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle atom alignment");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KT = (g.K + BK - 1) / BK;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
+  // k-tiles this CTA goes through, over all of its output tiles (blockIdx.x, +gridDim.x, ...)
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)KT;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);               // the producer's arrive.expect_tx
+      mbar_init(bars + 8 * (STAGES + s), NCW);  // one arrive per warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  __syncthreads();
+
+  // ---- producer side (lane 0 of warp 0): load number p of this CTA's k-tile sequence -> ring slot p % STAGES ----
+  const bool producer = (tid == 0);
+  uint32_t prod_it = 0;
+  auto issue = [&](uint32_t p) {
+    const int tile = (int)blockIdx.x + (int)(p / (uint32_t)KT) * (int)gridDim.x;
+    const int kt = (int)(p % (uint32_t)KT);
+    const int tm = tile % tiles_m, tn = tile / tiles_m;
+    const uint32_t s = p % STAGES, full = bars + 8 * s;
+    mbar_expect_tx(full, STAGE_BYTES);
+    tma_load_2d(ring_u + s * STAGE_BYTES, &mapA, full, kt * BK, tm * BM);
+    tma_load_2d(ring_u + s * STAGE_BYTES + A_BYTES, &mapB, full, kt * BK, tn * BN);
+  };
+  // the slot of load p was last used by load p - STAGES: it is free once every warp has arrived for that one
+  auto slot_free_parity = [&](uint32_t p) { return ((p / STAGES) & 1u) ^ 1u; };
+  if (producer)
+    for (; prod_it < total_it && prod_it < (uint32_t)STAGES; ++prod_it) issue(prod_it);  // fresh slots
+
+  const int wm = warp / WN, wn = warp % WN;
+  const int grp = lane >> 2, tig = lane & 3;
+  const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk of k-half 0; half 1 is off0 ^ 64
+  const uint8_t *a_base = ring + (wm * TM * 8 + grp) * 128;
+  const uint8_t *b_base = ring + A_BYTES + (wn * TN * 8 + grp) * 128;
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tm = tile % tiles_m, tn = tile / tiles_m;
+    const int m0 = tm * BM, n0 = tn * BN;
+    double acc[TM][TN][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+      if (producer) {
+        // the load this iteration needs must be in flight before waiting for it (blocks only if a warp lags a whole ring)
+        while (prod_it <= it) {
+          mbar_wait(bars + 8 * (STAGES + prod_it % STAGES), slot_free_parity(prod_it));
+          issue(prod_it);
+          ++prod_it;
+        }
+      }
+      mbar_wait(bars + 8 * s, ph);
+      const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = h ? (off0 ^ 64u) : off0;
+        double2 a[TM], b[TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const double2 *>(as + i * 8 * 128 + off);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const double2 *>(bs + j * 8 * 128 + off);
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+      if (producer) {
+        // refill, without blocking, every slot that all warps have released (runs ahead into the next tile)
+        while (prod_it < total_it && prod_it < it + 1u + (uint32_t)STAGES) {
+          if (!mbar_try_wait(bars + 8 * (STAGES + prod_it % STAGES), slot_free_parity(prod_it))) break;
+          issue(prod_it);
+          ++prod_it;
+        }
+      }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + wm * TM * 8 + i * 8 + grp;
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
+        if (n < g.N) epi(0, m, n, acc[i][j][0]);
+        if (n + 1 < g.N) epi(0, m, n + 1, acc[i][j][1]);
+      }
+    }
+  }
+}
+
+}  // namespace lowdin

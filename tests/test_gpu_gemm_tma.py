@@ -1,0 +1,103 @@
+"""GPU parity tests of the TMA + mbarrier persistent DMMA GEMM (csrc/it_gemm_tma.cuh, LOWDIN_IT_OPT_GEMM_VARIANT=2):
+the kernel alone against numpy, then whole transforms (transformers E and C, intra and inter, stored and generated
+AO sources, chunked second half) against the CPU oracle, exactly as tests/test_gpu_parity.py does for the cp.async
+variant.  Tolerance 1e-10 on MO integrals (BASELINE.json north_star), 1e-9 on the MP2 energy."""
+import numpy as np
+import pytest
+
+import openlowdin_b200 as ol
+from helpers import dense_pairs, dense_quads
+
+TOL = 1e-10
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tma(T):
+    T.set_option(T.OPT_GEMM_VARIANT, 2)
+    yield T
+    T.set_option(T.OPT_GEMM_VARIANT, 1)
+
+
+# every tile configuration (n <= 8, 16, 32, 64, 80-, 128-wide), K tails, row tails, several tiles per CTA, K < 16
+@pytest.mark.parametrize("m,n,k", [(19, 5, 19), (300, 150, 120), (1000, 8, 333), (257, 129, 65), (128, 128, 16), (7, 3, 2),
+                                    (513, 81, 1501), (64, 24, 50), (2000, 16, 100), (700, 33, 18), (5000, 56, 130),
+                                    (1350, 700, 96), (40000, 150, 34), (130, 1000, 1), (256, 256, 1600)])
+def test_tma_gemm_vs_numpy(tma, m, n, k):
+    rng = np.random.default_rng(m * 1000 + n)
+    A, B = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (n, k))
+    got = tma.debug_gemm(A, B)
+    ref = A @ B.T
+    assert np.abs(got - ref).max() <= 4e-16 * k + 1e-14
+
+
+def test_tma_gemm_matches_cp_async_variant(T):
+    rng = np.random.default_rng(5)
+    A, B = rng.uniform(-1, 1, (3000, 777)), rng.uniform(-1, 1, (290, 777))
+    T.set_option(T.OPT_GEMM_VARIANT, 1)
+    c1 = T.debug_gemm(A, B)
+    T.set_option(T.OPT_GEMM_VARIANT, 2)
+    try:
+        c2 = T.debug_gemm(A, B)
+    finally:
+        T.set_option(T.OPT_GEMM_VARIANT, 1)
+    assert np.abs(c1 - c2).max() <= 1e-12
+
+
+@pytest.mark.parametrize("n,occ,mode", [(7, 3, "MP2"), (19, 5, "MP2"), (19, 5, "PT2"), (19, 5, "BOUNDS"), (12, 11, "MP2")])
+def test_tma_transform_e_intra(O, tma, n, occ, mode):
+    packed = O.hash_packed_intra(100 + n, n)
+    Cm = O.random_orthonormal(n, n)
+    tma.set_species(0, Cm)
+    tma.upload_ao(0, 0, *O.canonical_list_intra(packed, n), stack=1024)
+    win = O.windows_e_intra(mode, n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    ij, kl, v = tma.transform(0, 0, win, ol.CONV_E)
+    M = O.npairs(n)
+    assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
+
+
+def test_tma_transform_c_intra_and_inter(O, tma):
+    n, occ = 19, 5
+    packed = O.hash_packed_intra(3, n)
+    Cm = O.random_orthonormal(n, n)
+    tma.set_species(0, Cm)
+    tma.upload_ao(0, 0, *O.canonical_list_intra(packed, n), stack=1024)
+    win, sym = O.windows_c_intra("MP2", n, occ)
+    ref = O.transform_c_intra(Cm, packed, win, sym)
+    got = tma.transform(0, 0, win, ol.CONV_C, symmetric=sym)
+    assert np.abs(dense_quads(*got, n, n) - dense_quads(*ref, n, n)).max() <= TOL
+    na, nb = 19, 12
+    rect = O.hash_rect_inter(9, na, nb)
+    Ca, Cb = O.random_orthonormal(na, na), O.random_orthonormal(nb, nb + 1)
+    tma.set_species(0, Ca)
+    tma.set_species(1, Cb)
+    tma.upload_ao(0, 1, *O.canonical_list_inter(rect, na, nb), stack=1024)
+    wine = O.windows_e_inter("MP2", na, nb, 5, 1)
+    rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, wine)
+    ij, kl, v = tma.transform(0, 1, wine, ol.CONV_E)
+    Ma, Mb = O.npairs(na), O.npairs(nb)
+    assert np.abs(dense_pairs(ij, kl, v, Ma, Mb) - dense_pairs(rij, rkl, rv, Ma, Mb)).max() <= TOL
+
+
+@pytest.mark.parametrize("cols", [0, 1, 40])
+def test_tma_generated_chunked_stream_energy(O, tma, cols):
+    n, occ, seed = 37, 11, 4242
+    packed = O.hash_packed_intra(seed, n)
+    Cm = O.random_orthonormal(n, n)
+    eps = O.synthetic_eps(occ, n)
+    win = O.windows_e_intra("MP2", n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    e = O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)
+    tma.set_species(0, Cm)
+    tma.set_generator(0, 0, seed)
+    tma.set_option(tma.OPT_CHUNK_COLS, cols)
+    try:
+        for qb in (0, 4):
+            sums = tma.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, epsA=eps, lam=2.0)
+            assert sums[0] == len(rv)
+            assert abs(sums[1] - rv.sum()) <= 1e-9 and abs(sums[2] - (rv * rv).sum()) <= 1e-9
+            assert abs(sums[3] - e) <= 1e-9
+    finally:
+        tma.set_option(tma.OPT_CHUNK_COLS, 0)
