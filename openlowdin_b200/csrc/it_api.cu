@@ -209,9 +209,13 @@ inline bool tma_eligible(const GemmArgs &g) {
 
 template <int BM, int BN, int WM, int WN, class Epi>
 cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
-  constexpr int ST_RAW = (int)(200704 / ((BM + BN) * 128));
+  constexpr int TNW = BN / WN / 8;
+  constexpr bool staged = Epi::kRowCoalesced && (BM / WM / 8 == 4);  // row-coalescing epilogue: 32-row warp tiles only
+  constexpr size_t staging = staged ? (size_t)WM * WN * TNW * 8 * TMA_STAGE_LDM * 8 : 0;
+  constexpr int ST_RAW = (int)((200704 + (staged ? 26624 : 0) - staging) / ((BM + BN) * 128));
   constexpr int ST = ST_RAW > 8 ? 8 : ST_RAW;
-  constexpr size_t smem = tma_gemm_smem_bytes<BM, BN, ST>();
+  constexpr size_t smem = tma_gemm_smem_bytes<BM, BN, ST>(staged ? WM * WN : 0, TNW);
+  static_assert(smem <= 232448, "shared memory per CTA");
   auto kern = dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi>;
   static bool configured = false;
   if (!configured) {
@@ -240,7 +244,10 @@ cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
   if (n <= 64) return LOWDIN_GEMM_CFG(128, 64, 4, 2);
   // pick the N tile with the least padding (ties -> the larger tile)
   const int64_t p128 = ceil_div(n, 128) * 128, p80 = ceil_div(n, 80) * 80, p64 = ceil_div(n, 64) * 64;
-  if (p128 <= p80 && p128 <= p64) return LOWDIN_GEMM_CFG(128, 128, 2, 4);
+  // very wide outputs: padding is negligible, take the tile with the best DMMA : shared-load ratio.
+  // (The row-coalescing epilogue works on 32-row warp tiles, which the 128x128 configuration does not have.)
+  const bool allow128 = !(tma && Epi::kRowCoalesced);
+  if (allow128 && (n >= 2048 || (p128 <= p80 && p128 <= p64))) return LOWDIN_GEMM_CFG(128, 128, 2, 4);
   if (p80 <= p64) return LOWDIN_GEMM_CFG(128, 80, 4, 2);
   return LOWDIN_GEMM_CFG(128, 64, 4, 2);
 #undef LOWDIN_GEMM_CFG
@@ -395,25 +402,60 @@ cudaError_t launch_q1_gen_cfg(lowdin_it_handle h, const AoSource &src, int64_t s
   return cudaGetLastError();
 }
 
+// warp-specialised variant (q1_gen_ws_kernel): generator warps + DMMA warps, coefficient window through TMA
+template <int TN, int KIND, int GEN>
+cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
+                             int nfb, double *T1t, int64_t ldt) {
+  constexpr int ST = 6;
+  constexpr size_t smem = q1_ws_smem_bytes<TN, ST>();
+  auto kern = q1_gen_ws_kernel<TN, ST, KIND, GEN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap mapB;
+  if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
+  const int64_t ntiles = ceil_div(nc, 128) * (int64_t)bc;
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
+  Q1WsArgs q{slab0, bc, nc, nfb, (uint64_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
+  kern<<<grid, 512, smem, h->stream>>>(mapB, q);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+template <int TN>
+cudaError_t launch_q1_ws(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb,
+                         double *T1t, int64_t ldt) {
+  if (src.kind == SRC_HASH_SYM)
+    return src.gen == 2 ? launch_q1_ws_cfg<TN, SRC_HASH_SYM, 2>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt)
+                        : launch_q1_ws_cfg<TN, SRC_HASH_SYM, 1>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  return src.gen == 2 ? launch_q1_ws_cfg<TN, SRC_HASH_RECT, 2>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt)
+                      : launch_q1_ws_cfg<TN, SRC_HASH_RECT, 1>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+}
+
 // fused generation + first quarter; window columns in groups of at most 64
 int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb,
                   double *T1t, int64_t ldt) {
+  const bool ws = (h->q1_variant == 3) && tensor_map_encoder() != nullptr && ((uintptr_t)Cf % 16 == 0) && (ldc % 2 == 0);
   for (int f = 0; f < nfb; f += 64) {
     const int w = std::min(64, nfb - f);
     const int tn = (int)ceil_div(w, 8);
     const double *cf = Cf + (int64_t)f * ldc;
     double *out = T1t + (int64_t)f * bc * ldt;
     cudaError_t e = cudaSuccess;
+#define LOWDIN_Q1_CFG(TN) (ws ? launch_q1_ws<TN>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt) : launch_q1_gen_cfg<TN>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt))
     switch (tn) {
-      case 1: e = launch_q1_gen_cfg<1>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 2: e = launch_q1_gen_cfg<2>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 3: e = launch_q1_gen_cfg<3>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 4: e = launch_q1_gen_cfg<4>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 5: e = launch_q1_gen_cfg<5>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 6: e = launch_q1_gen_cfg<6>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      case 7: e = launch_q1_gen_cfg<7>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
-      default: e = launch_q1_gen_cfg<8>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt); break;
+      case 1: e = LOWDIN_Q1_CFG(1); break;
+      case 2: e = LOWDIN_Q1_CFG(2); break;
+      case 3: e = LOWDIN_Q1_CFG(3); break;
+      case 4: e = LOWDIN_Q1_CFG(4); break;
+      case 5: e = LOWDIN_Q1_CFG(5); break;
+      case 6: e = LOWDIN_Q1_CFG(6); break;
+      case 7: e = LOWDIN_Q1_CFG(7); break;
+      default: e = LOWDIN_Q1_CFG(8); break;
     }
+#undef LOWDIN_Q1_CFG
     CK(e);
   }
   return 0;
@@ -1021,7 +1063,7 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       if (value < 0) return fail(h, "negative chunk column limit");
       h->chunk_cols_limit = value; return 0;
     case LOWDIN_IT_OPT_Q1_VARIANT:
-      if (value != 1 && value != 2) return fail(h, "q1 variant must be 1 or 2");
+      if (value < 1 || value > 3) return fail(h, "q1 variant must be 1, 2 or 3");
       h->q1_variant = (int)value; return 0;
     case LOWDIN_IT_OPT_GEMM_VARIANT:
       if (value != 1 && value != 2) return fail(h, "gemm variant must be 1 or 2");

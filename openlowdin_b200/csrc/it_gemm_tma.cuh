@@ -63,9 +63,11 @@ struct TmaGemmShape {
   int M, N, K;
 };
 
+constexpr int TMA_STAGE_LDM = 34;  // staged epilogue: [n][34] doubles per warp (32 rows + padding)
 template <int BM, int BN, int STAGES>
-constexpr size_t tma_gemm_smem_bytes() {
-  return (size_t)STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024;  // ring + barriers + alignment slack
+constexpr size_t tma_gemm_smem_bytes(int warps = 0, int tn = 0) {
+  // ring + barriers + alignment slack (+ the per-warp staging tiles of a row-coalescing epilogue)
+  return (size_t)STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024 + (size_t)warps * tn * 8 * TMA_STAGE_LDM * 8;
 }
 
 template <int BM, int BN, int WM, int WN, int STAGES, class Epi>
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
   uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t ring_u = smem_u32(ring);
   const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+  double *staging = reinterpret_cast<double *>(ring + STAGES * STAGE_BYTES + 2 * STAGES * 8);  // Epi::kRowCoalesced only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KT = (g.K + BK - 1) / BK;
@@ -178,15 +181,203 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       }
     }
 
+    if constexpr (Epi::kRowCoalesced && TM == 4) {
+      // Output elements that are consecutive in m are consecutive in memory (third-quarter accumulators, mu contiguous):
+      // turn the warp's 32 x (8 TN) accumulator tile in shared memory so that lane l owns row l, then read-modify-write
+      // column by column with 256-byte coalesced accesses instead of 64-byte pieces per lane group.
+      double *st = staging + warp * (TN * 8 * TMA_STAGE_LDM);
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = m0 + wm * TM * 8 + i * 8 + grp;
-      if (m >= g.M) continue;
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          st[(j * 8 + tig * 2) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][0];
+          st[(j * 8 + tig * 2 + 1) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][1];
+        }
+      __syncwarp();
+      const int m = m0 + wm * 32 + lane;
+      const int nb = n0 + wn * TN * 8;
+      if (m < g.M) {
+        double *row = epi.row_ptr(m);
+        const int64_t cs = epi.col_stride();
+#pragma unroll
+        for (int u0 = 0; u0 < TN * 8; u0 += 8) {
+          double t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = (nb + u0 + u < g.N) ? row[(int64_t)(nb + u0 + u) * cs] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (nb + u0 + u < g.N) row[(int64_t)(nb + u0 + u) * cs] = t[u] + st[(u0 + u) * TMA_STAGE_LDM + lane];
+        }
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int m = m0 + wm * TM * 8 + i * 8 + grp;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
+          if (n < g.N) epi(0, m, n, acc[i][j][0]);
+          if (n + 1 < g.N) epi(0, m, n + 1, acc[i][j][1]);
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================================
+// Warp-specialised fused slab generation + first quarter for GENERATED AO sources (q1 variant 3):
+//   T1t[f][z][mu] = sum_nu AO(slab0+z ; pair(mu,nu)) * C(nu, f)                      (E.f90:1047-1090 in one kernel)
+// The ncu capture of the single-role kernel (profiles/r01b_ncu_summary.md) shows the FP64 tensor pipe at 67 %: every
+// warp alternates ~50 dependent integer instructions per generated value with its DMMAs, and since a warp issues in
+// order, a warp inside its hash chain has no DMMA to offer and a warp waiting for the tensor pipe cannot hash.  Here the
+// two jobs run in different warps of a 16-warp CTA (two of each kind per scheduler):
+//   generators (warps 8-15)  hash the A operand (the 128 x 16 slab tile of the k-tile) and store it into a STAGES-deep
+//                            shared-memory ring in the same 128-byte-swizzled layout TMA produces; one lane also issues
+//                            the TMA load of the coefficient-window tile (B operand) of the stage;
+//   consumers  (warps 0-7)   wait on the stage's "full" mbarrier, read fragments with 128-bit shared loads and do
+//                            nothing but DMMAs, then arrive on the stage's "empty" mbarrier.
+// Persistent: CTAs walk (slab, 128-row block) tiles; the generators run ahead into the next tile during the epilogue.
+// =================================================================================================================
+template <int KIND, int GEN>
+__device__ __forceinline__ double gen_value_t(uint32_t slab, uint32_t mu, uint32_t nu, uint32_t n, uint64_t M_or_aux, uint64_t seed) {
+  const uint32_t lo = min(mu, nu), hi = max(mu, nu);
+  const uint32_t pair = lo * n - ((lo * (lo - 1u)) >> 1) + (hi - lo);
+  uint64_t key;
+  if (KIND == SRC_HASH_SYM) {
+    const uint32_t a = min(slab, pair), b = max(slab, pair);
+    key = (uint64_t)b * M_or_aux + a;
+  } else {
+    key = (uint64_t)pair * M_or_aux + slab;
+  }
+  return bits_to_value(GEN == 2 ? mulfold64(seed ^ key) : splitmix64(seed ^ key));
+}
+
+struct Q1WsArgs {
+  int64_t slab0;
+  int bc, nc, nfb;
+  uint64_t M_or_aux, seed;
+  double *T1t;
+  int64_t ldt;
+};
+
+template <int TN, int STAGES>
+constexpr size_t q1_ws_smem_bytes() {
+  return (size_t)STAGES * (128 + TN * 8) * 128 + 2 * STAGES * 8 + 1024;
+}
+
+template <int TN, int STAGES, int KIND, int GEN>
+__global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant__ CUtensorMap mapB, Q1WsArgs q) {
+  constexpr int BK = 16, BM = 128, BN = TN * 8;
+  constexpr int NCW = 8, NGW = 8;  // consumer / generator warps
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int KT = (q.nc + BK - 1) / BK;
+  const int row_blocks = (q.nc + BM - 1) / BM;
+  const int ntiles = row_blocks * q.bc;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, NGW + 1);         // one arrive per generator warp + the arrive.expect_tx of the TMA issuer
+      mbar_init(bars + 8 * (STAGES + s), NCW);  // one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&mapB);
+  }
+  __syncthreads();
+
+  const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk tig of a row with (row & 7) == grp; chunk 4+tig is off0 ^ 64
+
+  if (warp >= NCW) {
+    // ============================== generators ==============================
+    const int gw = warp - NCW;
+    const uint32_t n = (uint32_t)q.nc;
+    uint8_t *a_rows = ring + (gw * 16 + grp) * 128;  // rows 16 gw + grp and + 8
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / row_blocks, rb = tile - z * row_blocks;
+      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t mu0 = (uint32_t)(rb * BM + gw * 16 + grp);
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const uint32_t s = it % STAGES;
+        if (it >= (uint32_t)STAGES) mbar_wait(bars + 8 * (STAGES + s), ((it / STAGES) & 1u) ^ 1u);
+        if (gw == 0 && lane == 0) {
+          mbar_expect_tx(bars + 8 * s, B_BYTES);
+          tma_load_2d(ring_u + s * STAGE_BYTES + A_BYTES, &mapB, bars + 8 * s, kt * BK, 0);
+        }
+        uint8_t *dst = a_rows + s * STAGE_BYTES;
+        const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
+#pragma unroll
+        for (int rg = 0; rg < 2; ++rg) {
+#pragma unroll
+          for (int cg = 0; cg < 2; ++cg) {
+            const uint32_t mu = mu0 + 8 * rg, nu = nu0 + 8 * cg;
+            double2 v;
+            v.x = gen_value_t<KIND, GEN>(slab, mu, nu, n, q.M_or_aux, q.seed);
+            v.y = gen_value_t<KIND, GEN>(slab, mu, nu + 1u, n, q.M_or_aux, q.seed);
+            *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (cg ? (off0 ^ 64u) : off0)) = v;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * s);
+      }
+    }
+    return;
+  }
+
+  // ============================== consumers ==============================
+  const uint8_t *a_base = ring + (warp * 16 + grp) * 128;
+  const uint8_t *b_base = ring + A_BYTES + grp * 128;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int z = tile / row_blocks, rb = tile - z * row_blocks;
+    double acc[2][TN][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const uint32_t s = it % STAGES;
+      mbar_wait(bars + 8 * s, (it / STAGES) & 1u);
+      const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = h ? (off0 ^ 64u) : off0;
+        double2 a[2], b[TN];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const double2 *>(as + i * 8 * 128 + off);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const double2 *>(bs + j * 8 * 128 + off);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = rb * BM + warp * 16 + i * 8 + grp;
+      if (m >= q.nc) continue;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
-        if (n < g.N) epi(0, m, n, acc[i][j][0]);
-        if (n + 1 < g.N) epi(0, m, n + 1, acc[i][j][1]);
+        const int f = j * 8 + tig * 2;
+        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+        if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
       }
     }
   }

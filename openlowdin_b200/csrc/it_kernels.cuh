@@ -204,6 +204,7 @@ struct GemmArgs {
 
 // Epilogues -----------------------------------------------------------------------------------
 struct EpiPlain {  // C[z][m][n]
+  static constexpr bool kRowCoalesced = false;
   double *C; int64_t ldc, strideC;
   __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { C[z * strideC + (int64_t)m * ldc + n] = v; }
 };
@@ -211,6 +212,7 @@ struct EpiPlain {  // C[z][m][n]
 //   T1t[f][z][mu]  (mu contiguous: the second quarter reads K-contiguous rows; z inside f so that the
 //   second quarter's output columns for one window pair are consecutive AO-pair slabs)
 struct EpiQ1 {
+  static constexpr bool kRowCoalesced = false;
   double *T1t; int nc; int bc; int64_t ldt;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int zz = m / nc, mu = m - zz * nc;
@@ -222,6 +224,7 @@ struct EpiQ1 {
 // semantics, zeroing |t| <= tol (E.f90:1113).  tol < 0 keeps everything.  Consecutive n are consecutive
 // columns of one H row: 64-byte runs per 8x8 accumulator tile.
 struct EpiScatterH {
+  static constexpr bool kRowCoalesced = false;
   double *H; int64_t ldh; int64_t col0; const int32_t *slot; int nf; int bc; double tol;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int f = n / bc, zz = n - f * bc;
@@ -232,15 +235,23 @@ struct EpiScatterH {
 // Third quarter, chunked: m = (z, row) over `nrows` rows of each slot's expanded block, n = kf.
 //   T3[slot0+z][kf][roff+row] += v   (accumulated over the AO-pair chunks; mu contiguous for the fourth quarter)
 struct EpiAccT {
+  static constexpr bool kRowCoalesced = true;  // consecutive m (mu within one slot) are consecutive in T3
   double *T3; int nrows; int roff; int nf2; int64_t ldt;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int zz = m / nrows, r = m - zz * nrows;
     double *p = T3 + (((int64_t)zz * nf2 + n) * ldt + roff + r);
     *p += v;
   }
+  // element (m, n) = row_ptr(m)[n * col_stride()]
+  __device__ __forceinline__ double *row_ptr(int m) const {
+    int zz = m / nrows, r = m - zz * nrows;
+    return T3 + ((int64_t)zz * nf2 * ldt + roff + r);
+  }
+  __device__ __forceinline__ int64_t col_stride() const { return ldt; }
 };
 // Fourth quarter: m = ks, n = (z, kf)  ->  OUT[z][ks][kf]
 struct EpiOut {
+  static constexpr bool kRowCoalesced = false;
   double *OUT; int ns2, nf2;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int zz = n / nf2, kf = n - zz * nf2;

@@ -101,3 +101,77 @@ def test_tma_generated_chunked_stream_energy(O, tma, cols):
             assert abs(sums[3] - e) <= 1e-9
     finally:
         tma.set_option(tma.OPT_CHUNK_COLS, 0)
+
+
+# ---- warp-specialised fused generation + first-quarter kernel (q1 variant 3, q1_gen_ws_kernel) --------------------------------
+@pytest.fixture()
+def ws(T):
+    T.set_option(T.OPT_Q1_VARIANT, 3)
+    yield T
+    T.set_option(T.OPT_Q1_VARIANT, 1)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("n,win", [(19, [6, 19, 1, 5, 6, 19, 1, 5]), (23, [1, 23, 1, 23, 1, 23, 1, 23]), (37, [12, 37, 1, 11, 12, 37, 1, 11]),
+                                   (70, [1, 70, 1, 1, 1, 70, 1, 70]), (70, [66, 70, 1, 65, 1, 3, 1, 2]), (133, [11, 133, 1, 10, 11, 133, 1, 10]),
+                                   (100, [1, 100, 1, 70, 1, 2, 1, 2])])
+def test_ws_generated_source_intra(O, ws, n, win, kind):
+    """several 128-row blocks, row and K tails, windows wider than 64 columns (two launches), both generators"""
+    seed = 4242 + n
+    packed = O.hash_packed_intra(seed, n, kind)
+    Cm = O.random_orthonormal(n, n)
+    ws.set_species(0, Cm)
+    ws.set_generator(0, 0, seed, kind)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    ij, kl, v = ws.transform(0, 0, win, ol.CONV_E)
+    M = O.npairs(n)
+    assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
+
+
+@pytest.mark.parametrize("gemm_variant", [1, 2])
+def test_ws_generated_source_inter_stream(O, ws, gemm_variant):
+    na, nb, oa, ob = 21, 16, 5, 2
+    seed = 99
+    rect = O.hash_rect_inter(seed, na, nb)
+    Ca, Cb = O.random_orthonormal(na, 3), O.random_orthonormal(nb, 4)
+    ws.set_species(0, Ca)
+    ws.set_species(1, Cb)
+    ws.set_generator(0, 1, seed)
+    ea, eb = O.synthetic_eps(oa, na), O.synthetic_eps(ob, nb)
+    win = O.windows_e_inter("MP2", na, nb, oa, ob)
+    rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, win)
+    e_orc = O.mp2_inter_from_pairs(rij, rkl, rv, na, nb, oa, ob, ea, eb, charge_a=1.0, charge_b=1.0, lam_a=1.0, lam_b=1.0)
+    ws.set_option(ws.OPT_GEMM_VARIANT, gemm_variant)
+    try:
+        for cols, qb in ((0, 0), (25, 2), (1, 3)):
+            ws.set_option(ws.OPT_CHUNK_COLS, cols)
+            sums = ws.transform_stream(0, 1, win, ol.CONV_E, occ_batch=qb, epsA=ea, epsB=eb)
+            assert sums[0] == len(rv)
+            assert abs(sums[3] - e_orc) <= 1e-9
+    finally:
+        ws.set_option(ws.OPT_CHUNK_COLS, 0)
+        ws.set_option(ws.OPT_GEMM_VARIANT, 1)
+
+
+def test_all_new_variants_n500_properties(T):
+    """BASELINE size N=500 (MP2 window, O=50) with the TMA GEMM + warp-specialised first quarter: the reduced sums must
+    agree with the default variants to 1e-9 relative (size-independent property: same transform, different kernels)."""
+    n, occ = 500, 50
+    q, _ = np.linalg.qr(np.random.default_rng(n).standard_normal((n, n)))
+    eps = np.concatenate([np.linspace(-2.0, -0.5, occ), np.linspace(0.2, 3.0, n - occ)])
+    win = [occ + 1, n, 1, occ, occ + 1, n, 1, occ]
+    T.set_species(0, np.asfortranarray(q))
+    T.set_generator(0, 0, 77)
+    T.set_option(T.OPT_CHUNK_COLS, 30000)
+    try:
+        ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
+        T.set_option(T.OPT_GEMM_VARIANT, 2)
+        T.set_option(T.OPT_Q1_VARIANT, 3)
+        got = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
+    finally:
+        T.set_option(T.OPT_GEMM_VARIANT, 1)
+        T.set_option(T.OPT_Q1_VARIANT, 1)
+        T.set_option(T.OPT_CHUNK_COLS, 0)
+    assert abs(got[0] - ref[0]) <= 2  # entries within rounding of the 1e-10 threshold may flip
+    for a, b in zip(got[1:], ref[1:]):
+        assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
