@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
     ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
+    ap.add_argument("--gemm-variant", type=int, default=0, help="quarter-transform GEMM variant (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -221,6 +222,8 @@ def main():
     T.set_species(0, Cm)
     if args.q1_variant:
         T.set_option(T.OPT_Q1_VARIANT, args.q1_variant)
+    if args.gemm_variant:
+        T.set_option(T.OPT_GEMM_VARIANT, args.gemm_variant)
     T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 

@@ -40,7 +40,7 @@ struct DevBuf {
 struct Species {
   int n = 0, ncols = 0;
   int64_t M = 0, ldc = 0;
-  DevBuf C, pi, pj;
+  DevBuf C, Cs, pi, pj;  // Cs = C * 2^-53 (exact): B operand of the warp-specialised fused first quarter (bits_to_unscaled)
 };
 
 struct AoSet {
@@ -103,8 +103,8 @@ struct lowdin_it_ctx {
   int rank = 0, nranks = 1;
   void *comm = nullptr;
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
-  int q1_variant = 1;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier
-  int gemm_variant = 1;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
+  int q1_variant = 3;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
+  int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
@@ -257,6 +257,7 @@ cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
 struct Half {
   int nc = 0;                 // basis size of the species contracted in this half
   const double *C = nullptr;  // device coefficients, column-major, ldc
+  const double *Cs = nullptr; // the same scaled by 2^-53 (generated-source first quarter)
   int64_t ldc = 0;
   int lf = 1, nf = 0;         // first-contracted window (1-based start, count)
   int ls = 1, ns = 0;         // second-contracted window
@@ -302,7 +303,7 @@ int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int
   // first pair (p|i , q|j) on species a; second pair (r|k , s|l) on species b.
   // The smaller window is contracted first (ties: the convention's second index, as in E.f90:1081).
   auto setup = [&](Half &hf, const Species &S, int w_first_listed, int w_second_listed) {
-    hf.nc = S.n; hf.C = S.C.as<double>(); hf.ldc = S.ldc;
+    hf.nc = S.n; hf.C = S.C.as<double>(); hf.Cs = S.Cs.as<double>(); hf.ldc = S.ldc;
     const int n1 = cnt(w_first_listed), n2 = cnt(w_second_listed);
     hf.first_is_conv_second = (n2 <= n1);
     const int wf = hf.first_is_conv_second ? w_second_listed : w_first_listed;
@@ -419,7 +420,7 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(nc, 128) * (int64_t)bc;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
-  Q1WsArgs q{slab0, bc, nc, nfb, (uint64_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
+  Q1WsArgs q{slab0, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
   kern<<<grid, 512, smem, h->stream>>>(mapB, q);
   h->launches += 1;
   return cudaGetLastError();
@@ -435,13 +436,14 @@ cudaError_t launch_q1_ws(lowdin_it_handle h, const AoSource &src, int64_t slab0,
 }
 
 // fused generation + first quarter; window columns in groups of at most 64
-int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb,
-                  double *T1t, int64_t ldt) {
-  const bool ws = (h->q1_variant == 3) && tensor_map_encoder() != nullptr && ((uintptr_t)Cf % 16 == 0) && (ldc % 2 == 0);
+// Cf: coefficient window [nfb][ldc]; Cfs: the same window of the 2^-53-scaled copy (needed by the warp-specialised variant)
+int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, const double *Cfs, int64_t ldc,
+                  int nfb, double *T1t, int64_t ldt) {
+  const bool ws = (h->q1_variant == 3) && Cfs && tensor_map_encoder() != nullptr && ((uintptr_t)Cfs % 16 == 0) && (ldc % 2 == 0);
   for (int f = 0; f < nfb; f += 64) {
     const int w = std::min(64, nfb - f);
     const int tn = (int)ceil_div(w, 8);
-    const double *cf = Cf + (int64_t)f * ldc;
+    const double *cf = (ws ? Cfs : Cf) + (int64_t)f * ldc;
     double *out = T1t + (int64_t)f * bc * ldt;
     cudaError_t e = cudaSuccess;
 #define LOWDIN_Q1_CFG(TN) (ws ? launch_q1_ws<TN>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt) : launch_q1_gen_cfg<TN>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt))
@@ -477,12 +479,13 @@ int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t
   if (!generated) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
   const double *Cf = hf.C + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc;
+  const double *Cfs = hf.Cs ? hf.Cs + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc : nullptr;
   for (int64_t s = 0; s < count; s += B) {
     const int64_t bc = std::min<int64_t>(B, count - s);
     if (generated) {
       // slab generation + first quarter in one kernel: the dense slab never exists
       ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
-      if (launch_q1_gen(h, pl.src, slab0 + s, (int)bc, nc, Cf, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+      if (launch_q1_gen(h, pl.src, slab0 + s, (int)bc, nc, Cf, Cfs, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
     } else {
       {  // unpack (E.f90:1047-1063)
         ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
@@ -832,7 +835,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  for (auto &s : h->sp) { s.C.release(); s.pi.release(); s.pj.release(); }
+  for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
   for (auto &row : h->ao) for (auto &a : row) a.data.release();
   DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp,
@@ -857,6 +860,12 @@ int lowdin_it_set_species(lowdin_it_handle h, int slot, int nao, const double *C
   CK(cudaMemsetAsync(S.C.p, 0, (size_t)S.ldc * ncols * sizeof(double), h->stream));
   CK(cudaMemcpy2DAsync(S.C.p, S.ldc * sizeof(double), C, (size_t)ldc * sizeof(double), (size_t)nao * sizeof(double), ncols,
                        cudaMemcpyHostToDevice, h->stream));
+  {
+    const int64_t cnt = S.ldc * (int64_t)ncols;
+    CK(S.Cs.ensure((size_t)cnt * sizeof(double)));
+    scale_copy_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, h->stream>>>(S.C.as<double>(), S.Cs.as<double>(), cnt, 0x1p-53);
+    CK(cudaGetLastError());
+  }
   std::vector<int32_t> pi(S.M), pj(S.M);
   int64_t m = 0;
   for (int i = 0; i < nao; ++i) for (int j = i; j < nao; ++j) { pi[m] = i; pj[m] = j; ++m; }
@@ -1218,10 +1227,10 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
     CK(h->T1t.ensure((size_t)bc * nfb * ldt * sizeof(double)));
     CK(cudaMemsetAsync(h->X.p, 0x3f, (size_t)nfb * ldc * sizeof(double), h->stream));
     AoSource src{SRC_HASH_SYM, nullptr, npairs(nc), 0, 0, 12345, h->bench_gen};
-    if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+    if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
     CK(cudaEventRecord(e0, h->stream));
     for (int i = 0; i < iters; ++i)
-      if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+      if (launch_q1_gen(h, src, 0, bc, nc, h->X.as<double>(), h->X.as<double>(), ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&ms, e0, e1));

@@ -44,6 +44,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait never does).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol error becomes a kernel fault (reported through the C ABI) instead of a hung device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       if (producer) {
         // refill, without blocking, every slot that all warps have released (runs ahead into the next tile)
         while (prod_it < total_it && prod_it < it + 1u + (uint32_t)STAGES) {
-          if (!mbar_try_wait(bars + 8 * (STAGES + prod_it % STAGES), slot_free_parity(prod_it))) break;
+          if (!mbar_test_wait(bars + 8 * (STAGES + prod_it % STAGES), slot_free_parity(prod_it))) break;
           issue(prod_it);
           ++prod_it;
         }
@@ -233,31 +245,46 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
 // warp alternates ~50 dependent integer instructions per generated value with its DMMAs, and since a warp issues in
 // order, a warp inside its hash chain has no DMMA to offer and a warp waiting for the tensor pipe cannot hash.  Here the
 // two jobs run in different warps of a 16-warp CTA (two of each kind per scheduler):
-//   generators (warps 8-15)  hash the A operand (the 128 x 16 slab tile of the k-tile) and store it into a STAGES-deep
-//                            shared-memory ring in the same 128-byte-swizzled layout TMA produces; one lane also issues
-//                            the TMA load of the coefficient-window tile (B operand) of the stage;
+//   generators (warps 8-15)  hash the A operand (the 128 x 16 slab tile of the k-tile, as unscaled integers-in-doubles,
+//                            see bits_to_unscaled) and store it into a STAGES-deep shared-memory ring in the same
+//                            128-byte-swizzled layout TMA produces; one lane also issues the TMA load of the stage's
+//                            tile of the coefficient window scaled by 2^-53 (B operand);
 //   consumers  (warps 0-7)   wait on the stage's "full" mbarrier, read fragments with 128-bit shared loads and do
 //                            nothing but DMMAs, then arrive on the stage's "empty" mbarrier.
 // Persistent: CTAs walk (slab, 128-row block) tiles; the generators run ahead into the next tile during the epilogue.
 // =================================================================================================================
+// Generated AO value WITHOUT its 2^-53 scale: the integer t = 2 (bits >> 11) - 2^53 as a double (exact, |t| <= 2^53).
+// value = t * 2^-53 (bits_to_value); the power of two is folded into the coefficient operand (Species::Cs = C * 2^-53,
+// exact), so the DMMA products t * (c 2^-53) round exactly like (t 2^-53) * c and T1t is bit-identical to the other
+// variants, while the exponent fix-up (two compares, an add and a select per value) disappears from the generator.
+//   t = ((int64)(bits ^ 2^63) >> 10) & ~1 :  bits ^ 2^63 is bits - 2^63 as a signed number, the arithmetic shift gives
+//   floor(bits / 2^10) - 2^53 = 2 (bits >> 11) + bit10 - 2^53, and clearing bit 0 removes bit10.
+__device__ __forceinline__ double bits_to_unscaled(uint64_t bits) {
+  const long long t = ((long long)(bits ^ 0x8000000000000000ull) >> 10) & ~1ll;
+  return __ll2double_rn(t);
+}
+// base(x) = x n - x (x - 1) / 2 - x, so that the 0-based pair id of (lo, hi >= lo) is base(lo) + hi   (C.f90:214-221)
+__device__ __forceinline__ uint32_t pair_base(uint32_t x, uint32_t n) { return x * n - ((x * (x - 1u)) >> 1) - x; }
+
 template <int KIND, int GEN>
-__device__ __forceinline__ double gen_value_t(uint32_t slab, uint32_t mu, uint32_t nu, uint32_t n, uint64_t M_or_aux, uint64_t seed) {
-  const uint32_t lo = min(mu, nu), hi = max(mu, nu);
-  const uint32_t pair = lo * n - ((lo * (lo - 1u)) >> 1) + (hi - lo);
+__device__ __forceinline__ double gen_unscaled(uint32_t slab, uint32_t mu, uint32_t nu, uint32_t base_mu, uint32_t base_nu, uint32_t m32,
+                                               uint64_t seed) {
+  const uint32_t pair = (nu >= mu) ? base_mu + nu : base_nu + mu;
   uint64_t key;
   if (KIND == SRC_HASH_SYM) {
     const uint32_t a = min(slab, pair), b = max(slab, pair);
-    key = (uint64_t)b * M_or_aux + a;
+    key = (uint64_t)b * (uint64_t)m32 + a;  // m32 = M (pairs per slab vector) < 2^32
   } else {
-    key = (uint64_t)pair * M_or_aux + slab;
+    key = (uint64_t)pair * (uint64_t)m32 + slab;  // m32 = number of slabs (M_b)
   }
-  return bits_to_value(GEN == 2 ? mulfold64(seed ^ key) : splitmix64(seed ^ key));
+  return bits_to_unscaled(GEN == 2 ? mulfold64(seed ^ key) : splitmix64(seed ^ key));
 }
 
 struct Q1WsArgs {
   int64_t slab0;
   int bc, nc, nfb;
-  uint64_t M_or_aux, seed;
+  uint32_t m32;   // SRC_HASH_SYM: pairs per slab vector (M); SRC_HASH_RECT: number of slabs (M_b)
+  uint64_t seed;
   double *T1t;
   int64_t ldt;
 };
@@ -307,6 +334,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
       const int z = tile / row_blocks, rb = tile - z * row_blocks;
       const uint32_t slab = (uint32_t)(q.slab0 + z);
       const uint32_t mu0 = (uint32_t)(rb * BM + gw * 16 + grp);
+      const uint32_t base_mu[2] = {pair_base(mu0, n), pair_base(mu0 + 8u, n)};
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const uint32_t s = it % STAGES;
         if (it >= (uint32_t)STAGES) mbar_wait(bars + 8 * (STAGES + s), ((it / STAGES) & 1u) ^ 1u);
@@ -316,14 +344,19 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
         }
         uint8_t *dst = a_rows + s * STAGE_BYTES;
         const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
+        // the lane's four k values of this k-tile (chunks tig and 4 + tig), shared by its two rows
+        const uint32_t nus[4] = {nu0, nu0 + 1u, nu0 + 8u, nu0 + 9u};
+        uint32_t base_nu[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base_nu[c] = pair_base(nus[c], n);
 #pragma unroll
         for (int rg = 0; rg < 2; ++rg) {
 #pragma unroll
           for (int cg = 0; cg < 2; ++cg) {
-            const uint32_t mu = mu0 + 8 * rg, nu = nu0 + 8 * cg;
+            const uint32_t mu = mu0 + 8 * rg;
             double2 v;
-            v.x = gen_value_t<KIND, GEN>(slab, mu, nu, n, q.M_or_aux, q.seed);
-            v.y = gen_value_t<KIND, GEN>(slab, mu, nu + 1u, n, q.M_or_aux, q.seed);
+            v.x = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg], base_mu[rg], base_nu[2 * cg], q.m32, q.seed);
+            v.y = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg + 1], base_mu[rg], base_nu[2 * cg + 1], q.m32, q.seed);
             *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (cg ? (off0 ^ 64u) : off0)) = v;
           }
         }

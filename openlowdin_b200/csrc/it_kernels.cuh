@@ -727,6 +727,12 @@ __global__ void __launch_bounds__(256) reduce_block_kernel(ReduceArgs a, double 
   }
 }
 
+// dst[i] = src[i] * factor (factor a power of two: exact).  Builds Species::Cs = C * 2^-53 for the warp-specialised first quarter.
+__global__ void scale_copy_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n, double factor) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * factor;
+}
+
 // D-layout -> internal layout (IntTransfD.cpp:25-65 Multi_Index / Multi_Index_Inter).
 // pairD(i,j) = i(i+1)/2 + j, i>=j (0-based).  pi/pj: (i,j) of each xy-numbered pair (i<=j).
 __device__ __forceinline__ int64_t pairD(int64_t i, int64_t j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }

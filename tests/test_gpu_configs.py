@@ -137,7 +137,7 @@ def test_full_size_properties_n500(T):
         b1 = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=4, first_pass=2, n_passes=2, epsA=eps)
     finally:
         T.set_option(T.OPT_CHUNK_COLS, 0)
-        T.set_option(T.OPT_Q1_VARIANT, 1)
+        T.set_option(T.OPT_Q1_VARIANT, T.DEFAULT_Q1_VARIANT)
     for other in (a, b1):
         assert other[0] == base[0]
         assert abs(other[1] - base[1]) <= 1e-9 * max(1.0, abs(base[1]))

@@ -316,7 +316,7 @@ def test_chunked_stream_mp2_energy_intra(O, T, chunked):
         assert abs(sums[3] - e_orc) <= 1e-9
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("kind", [1, 2])
 def test_generator_kinds_and_fused_kernel_variants(O, T, kind, variant):
     """Both synthetic generators (H: splitmix64, F: mul-fold-mul) are bit-identical on host and device, through the
@@ -335,7 +335,7 @@ def test_generator_kinds_and_fused_kernel_variants(O, T, kind, variant):
     try:
         ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
     finally:
-        T.set_option(T.OPT_Q1_VARIANT, 1)
+        T.set_option(T.OPT_Q1_VARIANT, T.DEFAULT_Q1_VARIANT)
     assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= TOL
     assert_lists_match((ij, kl), v, (rij, rkl), rv)
     na, nb = 8, 6

@@ -1,7 +1,9 @@
-"""GPU parity tests of the TMA + mbarrier persistent DMMA GEMM (csrc/it_gemm_tma.cuh, LOWDIN_IT_OPT_GEMM_VARIANT=2):
-the kernel alone against numpy, then whole transforms (transformers E and C, intra and inter, stored and generated
-AO sources, chunked second half) against the CPU oracle, exactly as tests/test_gpu_parity.py does for the cp.async
-variant.  Tolerance 1e-10 on MO integrals (BASELINE.json north_star), 1e-9 on the MP2 energy."""
+"""GPU parity tests of every kernel variant of the quarter transforms: the DMMA GEMM as a cp.async ring with a block barrier
+(LOWDIN_IT_OPT_GEMM_VARIANT=1) and as the TMA + mbarrier persistent kernel (=2, the default, csrc/it_gemm_tma.cuh), and the
+fused generation + first-quarter kernel single-role (LOWDIN_IT_OPT_Q1_VARIANT=1) and warp-specialised (=3, the default).
+Each kernel alone against numpy, then whole transforms (transformers E and C, intra and inter, stored and generated AO
+sources, chunked second half) against the CPU oracle.  tests/test_gpu_parity.py runs the same checks on the defaults.
+Tolerance 1e-10 on MO integrals (BASELINE.json north_star), 1e-9 on the MP2 energy."""
 import numpy as np
 import pytest
 
@@ -13,11 +15,11 @@ TOL = 1e-10
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def tma(T):
-    T.set_option(T.OPT_GEMM_VARIANT, 2)
+@pytest.fixture(params=[1, 2], ids=["cpasync", "tma"])
+def tma(T, request):
+    T.set_option(T.OPT_GEMM_VARIANT, request.param)
     yield T
-    T.set_option(T.OPT_GEMM_VARIANT, 1)
+    T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
 
 
 # every tile configuration (n <= 8, 16, 32, 64, 80-, 128-wide), K tails, row tails, several tiles per CTA, K < 16
@@ -41,7 +43,7 @@ def test_tma_gemm_matches_cp_async_variant(T):
     try:
         c2 = T.debug_gemm(A, B)
     finally:
-        T.set_option(T.OPT_GEMM_VARIANT, 1)
+        T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
     assert np.abs(c1 - c2).max() <= 1e-12
 
 
@@ -104,11 +106,11 @@ def test_tma_generated_chunked_stream_energy(O, tma, cols):
 
 
 # ---- warp-specialised fused generation + first-quarter kernel (q1 variant 3, q1_gen_ws_kernel) --------------------------------
-@pytest.fixture()
-def ws(T):
-    T.set_option(T.OPT_Q1_VARIANT, 3)
+@pytest.fixture(params=[1, 3], ids=["single_role", "warp_specialised"])
+def ws(T, request):
+    T.set_option(T.OPT_Q1_VARIANT, request.param)
     yield T
-    T.set_option(T.OPT_Q1_VARIANT, 1)
+    T.set_option(T.OPT_Q1_VARIANT, T.DEFAULT_Q1_VARIANT)
 
 
 @pytest.mark.parametrize("kind", [1, 2])
@@ -150,7 +152,7 @@ def test_ws_generated_source_inter_stream(O, ws, gemm_variant):
             assert abs(sums[3] - e_orc) <= 1e-9
     finally:
         ws.set_option(ws.OPT_CHUNK_COLS, 0)
-        ws.set_option(ws.OPT_GEMM_VARIANT, 1)
+        ws.set_option(ws.OPT_GEMM_VARIANT, ws.DEFAULT_GEMM_VARIANT)
 
 
 def test_all_new_variants_n500_properties(T):
@@ -164,13 +166,15 @@ def test_all_new_variants_n500_properties(T):
     T.set_generator(0, 0, 77)
     T.set_option(T.OPT_CHUNK_COLS, 30000)
     try:
+        T.set_option(T.OPT_GEMM_VARIANT, 1)
+        T.set_option(T.OPT_Q1_VARIANT, 1)
         ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
         T.set_option(T.OPT_GEMM_VARIANT, 2)
         T.set_option(T.OPT_Q1_VARIANT, 3)
         got = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
     finally:
-        T.set_option(T.OPT_GEMM_VARIANT, 1)
-        T.set_option(T.OPT_Q1_VARIANT, 1)
+        T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
+        T.set_option(T.OPT_Q1_VARIANT, T.DEFAULT_Q1_VARIANT)
         T.set_option(T.OPT_CHUNK_COLS, 0)
     assert abs(got[0] - ref[0]) <= 2  # entries within rounding of the 1e-10 threshold may flip
     for a, b in zip(got[1:], ref[1:]):
