@@ -113,9 +113,10 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
 /* ---- tuning ----------------------------------------------------------------------- */
 #define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
 #define LOWDIN_IT_OPT_CHUNK_COLS 2      /* cap on AO-pair columns per chunk of the half-transformed block (0 = from free HBM) */
-#define LOWDIN_IT_OPT_Q1_VARIANT 3      /* fused generation + first quarter: 1 = shared-memory ring, 2 = L1 path without barriers, 3 = warp-specialised (generator warps + DMMA warps, TMA) */
+#define LOWDIN_IT_OPT_Q1_VARIANT 3      /* fused generation + first quarter: 1 = shared-memory ring, 2 = L1 path without barriers, 3 = warp-specialised (8 generator + 8 DMMA warps, TMA), 4 = 4 vectorised generator warps + 8 DMMA warps with register double-buffering */
 #define LOWDIN_IT_OPT_BENCH_GEN 4       /* generator kind used by lowdin_it_kernel_bench kind 2 */
 #define LOWDIN_IT_OPT_GEMM_VARIANT 5    /* quarter-transform GEMM: 1 = cp.async ring + block barrier, 2 = TMA + mbarrier, persistent */
+#define LOWDIN_IT_OPT_SPLIT_ROW_TAIL 6  /* TMA GEMM: 1 (default) = the <= 80-row tail of a few-rows x many-columns product runs as a second, operand-swapped launch instead of a padded 128-row tile */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 
 /* ---- instrumentation -------------------------------------------------------------- */

@@ -106,6 +106,7 @@ struct lowdin_it_ctx {
   int q1_variant = 3;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
+  int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
@@ -233,10 +234,9 @@ cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi
 }
 
 template <class Epi>
-cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
+cudaError_t launch_gemm_one(lowdin_it_handle h, const GemmArgs &g, const Epi &epi, bool tma) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   const int n = g.N;
-  const bool tma = (h->gemm_variant == 2) && tma_eligible(g);
 #define LOWDIN_GEMM_CFG(BM, BN, WM, WN) (tma ? launch_gemm_tma_cfg<BM, BN, WM, WN>(h, g, epi) : launch_gemm_cfg<BM, BN, WM, WN>(h, g, epi))
   if (n <= 8) return LOWDIN_GEMM_CFG(256, 8, 8, 1);
   if (n <= 16) return LOWDIN_GEMM_CFG(256, 16, 8, 1);
@@ -251,6 +251,28 @@ cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
   if (p80 <= p64) return LOWDIN_GEMM_CFG(128, 80, 4, 2);
   return LOWDIN_GEMM_CFG(128, 64, 4, 2);
 #undef LOWDIN_GEMM_CFG
+}
+
+template <class Epi>
+cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  const bool tma = (h->gemm_variant == 2) && tma_eligible(g);
+  if constexpr (Epi::kSplitRowTail) {
+    // Few rows x very many columns (second and fourth quarter: rows = the second-contracted window, e.g. 1350 virtuals):
+    // 128-row tiles would pad 1350 to 1408 (4 % of the DMMAs on zeros).  The full 128-row tiles run as they are; the
+    // row tail (<= 80 rows) runs as a second launch with the operands exchanged, so that the tail becomes the N
+    // dimension and gets an 8..80-wide tile.
+    const int tail = g.M % 128, main = g.M - tail;
+    if (tma && h->split_row_tail && g.N >= 2048 && main >= 128 && tail > 0 && tail <= 80) {
+      GemmArgs gm = g;
+      gm.M = main;
+      cudaError_t e = launch_gemm_one(h, gm, epi, true);
+      if (e != cudaSuccess) return e;
+      GemmArgs gt{g.B, g.A + (int64_t)main * g.lda, g.N, tail, g.K, g.ldb, g.lda, 0, 0};
+      return launch_gemm_one(h, gt, EpiSwapped<Epi>{epi, main}, tma_eligible(gt));
+    }
+  }
+  return launch_gemm_one(h, g, epi, tma);
 }
 
 // ---- plan -------------------------------------------------------------------------------------
@@ -375,7 +397,14 @@ int launch_expand(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_
   if (bc <= 0 || nrows <= 0 || ncols <= 0) return 0;
   if (bc > 65535) return fail(h, "slab batch exceeds gridDim.z");
   dim3 grid((unsigned)ceil_div(ldx, 32), (unsigned)ceil_div(nrows, 32), (unsigned)bc);
-  expand_block_kernel<<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X);
+  if (n >= 65536) return fail(h, "basis too large for the 32-bit pair arithmetic of the expansion kernel");
+  switch (src.kind) {
+    case SRC_SYM_PACKED: expand_block_kernel<SRC_SYM_PACKED><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    case SRC_RECT: expand_block_kernel<SRC_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    case SRC_RECT_BLOCKED: expand_block_kernel<SRC_RECT_BLOCKED><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    case SRC_HASH_SYM: expand_block_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    default: expand_block_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+  }
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -409,19 +438,20 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
                              int nfb, double *T1t, int64_t ldt) {
   constexpr int ST = 6;
   constexpr size_t smem = q1_ws_smem_bytes<TN, ST>();
-  auto kern = q1_gen_ws_kernel<TN, ST, KIND, GEN>;
-  static bool configured = false;
-  if (!configured) {
+  const bool v4 = (h->q1_variant == 4);  // 8 DMMA warps with register double-buffering + 4 vectorised generator warps
+  auto kern = v4 ? q1_gen_ws2_kernel<TN, ST, KIND, GEN> : q1_gen_ws_kernel<TN, ST, KIND, GEN>;
+  static bool configured[2] = {false, false};
+  if (!configured[v4]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[v4] = true;
   }
   CUtensorMap mapB;
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(nc, 128) * (int64_t)bc;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
   Q1WsArgs q{slab0, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
-  kern<<<grid, 512, smem, h->stream>>>(mapB, q);
+  kern<<<grid, v4 ? 384 : 512, smem, h->stream>>>(mapB, q);
   h->launches += 1;
   return cudaGetLastError();
 }
@@ -439,7 +469,7 @@ cudaError_t launch_q1_ws(lowdin_it_handle h, const AoSource &src, int64_t slab0,
 // Cf: coefficient window [nfb][ldc]; Cfs: the same window of the 2^-53-scaled copy (needed by the warp-specialised variant)
 int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, const double *Cfs, int64_t ldc,
                   int nfb, double *T1t, int64_t ldt) {
-  const bool ws = (h->q1_variant == 3) && Cfs && tensor_map_encoder() != nullptr && ((uintptr_t)Cfs % 16 == 0) && (ldc % 2 == 0);
+  const bool ws = (h->q1_variant == 3 || h->q1_variant == 4) && Cfs && tensor_map_encoder() != nullptr && ((uintptr_t)Cfs % 16 == 0) && (ldc % 2 == 0);
   for (int f = 0; f < nfb; f += 64) {
     const int w = std::min(64, nfb - f);
     const int tn = (int)ceil_div(w, 8);
@@ -1072,12 +1102,14 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       if (value < 0) return fail(h, "negative chunk column limit");
       h->chunk_cols_limit = value; return 0;
     case LOWDIN_IT_OPT_Q1_VARIANT:
-      if (value < 1 || value > 3) return fail(h, "q1 variant must be 1, 2 or 3");
+      if (value < 1 || value > 4) return fail(h, "q1 variant must be 1..4");
       h->q1_variant = (int)value; return 0;
     case LOWDIN_IT_OPT_GEMM_VARIANT:
       if (value != 1 && value != 2) return fail(h, "gemm variant must be 1 or 2");
       if (value == 2 && !tensor_map_encoder()) return fail(h, "cuTensorMapEncodeTiled is not available from this driver");
       h->gemm_variant = (int)value; return 0;
+    case LOWDIN_IT_OPT_SPLIT_ROW_TAIL:
+      h->split_row_tail = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_BENCH_GEN:
       if (value != 1 && value != 2) return fail(h, "generator kind must be 1 or 2");
       h->bench_gen = (int)value; return 0;

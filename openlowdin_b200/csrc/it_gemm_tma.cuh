@@ -211,15 +211,14 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       if (m < g.M) {
         double *row = epi.row_ptr(m);
         const int64_t cs = epi.col_stride();
+        // all loads of the warp tile first (the accumulator registers are free by now): 8 TN x 256 bytes in flight per
+        // warp, which is what it takes to cover HBM latency with one CTA per SM; then add and store
+        double t[TN * 8];
 #pragma unroll
-        for (int u0 = 0; u0 < TN * 8; u0 += 8) {
-          double t[8];
+        for (int u = 0; u < TN * 8; ++u) t[u] = (nb + u < g.N) ? row[(int64_t)(nb + u) * cs] : 0.0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) t[u] = (nb + u0 + u < g.N) ? row[(int64_t)(nb + u0 + u) * cs] : 0.0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (nb + u0 + u < g.N) row[(int64_t)(nb + u0 + u) * cs] = t[u] + st[(u0 + u) * TMA_STAGE_LDM + lane];
-        }
+        for (int u = 0; u < TN * 8; ++u)
+          if (nb + u < g.N) row[(int64_t)(nb + u) * cs] = t[u] + st[u * TMA_STAGE_LDM + lane];
       }
       __syncwarp();
     } else {
@@ -401,6 +400,195 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = rb * BM + warp * 16 + i * 8 + grp;
+      if (m >= q.nc) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int f = j * 8 + tig * 2;
+        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+        if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+// =================================================================================================================
+// q1 variant 4: the same two roles, re-balanced after the ncu capture of variant 3 (profiles/r01e_*): there the generator
+// warps idle a third of the time on the "empty" barriers while the FP64 tensor pipe is only 75 % busy, because the DMMA
+// warps spend ~20 % of their time outside DMMAs (fragment loads whose latency nothing covers, barrier polls) and the
+// generator warps run one dependent hash chain at a time (IPC 0.23).  Here
+//   * the 8 DMMA warps double-buffer their fragments in registers: the 128-bit shared loads of the next half k-tile are
+//     issued BEFORE the 28 DMMAs of the current one (170 registers per thread are available with 384 threads, 128 with 512);
+//   * 4 generator warps (one per scheduler) hash 8 values per lane in lock step, stage by stage, so that the eight
+//     independent chains fill the integer pipes (32 rows x 16 k per warp and k-tile).
+// =================================================================================================================
+template <int GEN>
+__device__ __forceinline__ void hash8(uint64_t (&x)[8]) {
+  if (GEN == 2) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] *= 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] ^= x[v] >> 32;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] *= 0xD6E8FEB86659FD93ull;
+  } else {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] += 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = (x[v] ^ (x[v] >> 30)) * 0xBF58476D1CE4E5B9ull;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] = (x[v] ^ (x[v] >> 27)) * 0x94D049BB133111EBull;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) x[v] ^= x[v] >> 31;
+  }
+}
+
+template <int TN, int STAGES, int KIND, int GEN>
+__global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constant__ CUtensorMap mapB, Q1WsArgs q) {
+  constexpr int BK = 16, BM = 128, BN = TN * 8;
+  constexpr int NCW = 8, NGW = 4;  // DMMA warps (16 rows each) / generator warps (32 rows each)
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int KT = (q.nc + BK - 1) / BK;
+  const int row_blocks = (q.nc + BM - 1) / BM;
+  const int ntiles = row_blocks * q.bc;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)KT;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, NGW + 1);         // one arrive per generator warp + the arrive.expect_tx of the TMA issuer
+      mbar_init(bars + 8 * (STAGES + s), NCW);  // one arrive per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&mapB);
+  }
+  __syncthreads();
+
+  const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk tig of a row with (row & 7) == grp; chunk 4+tig is off0 ^ 64
+
+  if (warp >= NCW) {
+    // ============================== generators ==============================
+    const int gw = warp - NCW;
+    const uint32_t n = (uint32_t)q.nc;
+    uint8_t *a_rows = ring + (gw * 32 + grp) * 128;  // rows 32 gw + 8 rg + grp, rg = 0..3
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / row_blocks, rb = tile - z * row_blocks;
+      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
+      uint32_t base_mu[4];
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) base_mu[rg] = pair_base(mu0 + 8u * rg, n);
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const uint32_t s = it % STAGES;
+        if (it >= (uint32_t)STAGES) mbar_wait(bars + 8 * (STAGES + s), ((it / STAGES) & 1u) ^ 1u);
+        if (gw == 0 && lane == 0) {
+          mbar_expect_tx(bars + 8 * s, B_BYTES);
+          tma_load_2d(ring_u + s * STAGE_BYTES + A_BYTES, &mapB, bars + 8 * s, kt * BK, 0);
+        }
+        uint8_t *dst = a_rows + s * STAGE_BYTES;
+        const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
+        const uint32_t nus[4] = {nu0, nu0 + 1u, nu0 + 8u, nu0 + 9u};  // chunks tig and 4 + tig
+        uint32_t base_nu[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base_nu[c] = pair_base(nus[c], n);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two row groups (8 values) at a time, all chains advanced together
+          uint64_t x[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int rg = 2 * hh + (v >> 2), c = v & 3;
+            const uint32_t mu = mu0 + 8u * rg;
+            const uint32_t pair = (nus[c] >= mu) ? base_mu[rg] + nus[c] : base_nu[c] + mu;
+            uint64_t key;
+            if (KIND == SRC_HASH_SYM) {
+              const uint32_t a = min(slab, pair), b = max(slab, pair);
+              key = (uint64_t)b * (uint64_t)q.m32 + a;
+            } else {
+              key = (uint64_t)pair * (uint64_t)q.m32 + slab;
+            }
+            x[v] = q.seed ^ key;
+          }
+          hash8<GEN>(x);
+          double d[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) d[v] = bits_to_unscaled(x[v]);
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            const int rg = 2 * hh + r2;
+            *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + off0) = make_double2(d[4 * r2 + 0], d[4 * r2 + 1]);
+            *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (off0 ^ 64u)) = make_double2(d[4 * r2 + 2], d[4 * r2 + 3]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * s);
+      }
+    }
+    return;
+  }
+
+  // ============================== DMMA warps ==============================
+  if (total_it == 0) return;
+  const uint8_t *a_base = ring + (warp * 16 + grp) * 128;
+  const uint8_t *b_base = ring + A_BYTES + grp * 128;
+  double2 fa[2][2], fb[2][TN];  // [buffer][fragment]
+  auto load_frags = [&](int buf, uint32_t stage, uint32_t off) {
+    const uint8_t *as = a_base + stage * STAGE_BYTES, *bs = b_base + stage * STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) fa[buf][i] = *reinterpret_cast<const double2 *>(as + i * 8 * 128 + off);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) fb[buf][j] = *reinterpret_cast<const double2 *>(bs + j * 8 * 128 + off);
+  };
+  uint32_t it = 0;
+  mbar_wait(bars, 0);  // stage 0 of the first k-tile
+  load_frags(0, 0, off0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int z = tile / row_blocks, rb = tile - z * row_blocks;
+    double acc[2][TN][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const uint32_t s = it % STAGES;
+      // ---- k-half 0 from buffer 0; meanwhile fetch k-half 1 of the same stage into buffer 1 ----
+      load_frags(1, s, off0 ^ 64u);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[0][i].x, fb[0][j].x);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[0][i].y, fb[0][j].y);
+      // ---- k-half 1 from buffer 1; meanwhile fetch k-half 0 of the NEXT k-tile (next stage) into buffer 0 ----
+      if (it + 1u < total_it) {
+        const uint32_t s1 = (it + 1u) % STAGES;
+        mbar_wait(bars + 8 * s1, ((it + 1u) / STAGES) & 1u);
+        load_frags(0, s1, off0);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[1][i].x, fb[1][j].x);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[1][i].y, fb[1][j].y);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));  // both halves of stage s are in registers or consumed
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {

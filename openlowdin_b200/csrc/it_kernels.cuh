@@ -80,25 +80,6 @@ __host__ __device__ __forceinline__ int64_t blocked_offset(int64_t slab, int64_t
   return (blk * rows + slab) * ld + (pair - blk * ld);
 }
 
-__device__ __forceinline__ double ao_value(const AoSource &src, int64_t slab, int64_t pair) {
-  switch (src.kind) {
-    case SRC_SYM_PACKED: {
-      int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
-      return __ldg(src.data + (lo * src.M - (lo * (lo + 1)) / 2 + hi));
-    }
-    case SRC_RECT:
-      return __ldg(src.data + (slab * src.ld + pair));
-    case SRC_RECT_BLOCKED:
-      return __ldg(src.data + blocked_offset(slab, pair, src.ld, src.aux));
-    case SRC_HASH_SYM: {
-      int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
-      return hash_value(src.gen, src.seed, (uint64_t)(hi * src.M + lo));
-    }
-    default:
-      return hash_value(src.gen, src.seed, (uint64_t)(pair * src.aux + slab));
-  }
-}
-
 // 0-based row-wise upper-triangular pair id (== xy(p,q)-1, C.f90:214-221)
 __host__ __device__ __forceinline__ int64_t pair0(int64_t i, int64_t j, int64_t n) {
   if (i > j) { int64_t t = i; i = j; j = t; }
@@ -115,14 +96,50 @@ __host__ __device__ __forceinline__ int64_t pair0(int64_t i, int64_t j, int64_t 
 // with full 32-byte sectors; the tile is written back with 16-byte stores.
 // grid = (ceil(ldx/32), ceil(nrows/32), B), block = 256.
 // ---------------------------------------------------------------------------------------------
+// Source kind as a template parameter (no per-element switch), pair ids in 32-bit arithmetic (n < 65536, so pair ids
+// < 2^31 and i*n < 2^32), slab offset hoisted out of the element loop.
+__device__ __forceinline__ uint32_t pair0_u32(uint32_t i, uint32_t j, uint32_t n) {  // i <= j
+  return i * n - ((i * (i - 1u)) >> 1) + (j - i);
+}
+template <int KIND>
+struct SlabReader {
+  const double *base;  // SRC_RECT: row of the slab; SRC_SYM_PACKED / SRC_RECT_BLOCKED: tensor start
+  int64_t slab, M;
+  uint32_t ld, rows;
+  uint64_t seed;
+  int gen;
+  __device__ __forceinline__ SlabReader(const AoSource &src, int64_t slab_) : slab(slab_), M(src.M), ld((uint32_t)src.ld), rows((uint32_t)src.aux), seed(src.seed), gen(src.gen) {
+    base = (KIND == SRC_RECT) ? src.data + slab_ * src.ld : src.data;
+    if (KIND == SRC_HASH_RECT) M = src.aux;
+  }
+  __device__ __forceinline__ double operator()(int64_t pair) const {
+    if (KIND == SRC_RECT) return __ldg(base + pair);
+    if (KIND == SRC_RECT_BLOCKED) {
+      const uint32_t p = (uint32_t)pair, blk = p / ld;
+      return __ldg(base + ((int64_t)blk * rows + slab) * (int64_t)ld + (p - blk * ld));
+    }
+    if (KIND == SRC_SYM_PACKED) {
+      const int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
+      return __ldg(base + (lo * M - (lo * (lo + 1)) / 2 + hi));
+    }
+    if (KIND == SRC_HASH_SYM) {
+      const int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
+      return hash_value(gen, seed, (uint64_t)(hi * M + lo));
+    }
+    return hash_value(gen, seed, (uint64_t)(pair * M + slab));  // SRC_HASH_RECT: M holds the number of slabs
+  }
+};
+
+template <int KIND>
 __global__ void __launch_bounds__(256) expand_block_kernel(AoSource src, int64_t slab0, int n, int r0, int nrows, int c0, int ncols,
                                                           int64_t colbase, int ldx, double *__restrict__ X) {
   __shared__ double tile[32][33];
   const int64_t b = blockIdx.z;
-  const int64_t slab = slab0 + b;
+  const SlabReader<KIND> rd(src, slab0 + b);
   const int tr0 = blockIdx.y * 32, tc0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grow0 = r0 + tr0, gcol0 = c0 + tc0;
+  const uint32_t un = (uint32_t)n;
   if (grow0 >= gcol0 + 31) {
     // strictly-lower tile: element (row,col) lives at pair(col,row) = base(col) + row - col  -> lanes along rows
     const int row = grow0 + lane;
@@ -130,7 +147,7 @@ __global__ void __launch_bounds__(256) expand_block_kernel(AoSource src, int64_t
     for (int k = 0; k < 4; ++k) {
       const int c = warp + 8 * k, col = gcol0 + c;
       double v = 0.0;
-      if (tr0 + lane < nrows && tc0 + c < ncols) v = ao_value(src, slab, pair0(col, row, n) - colbase);
+      if (tr0 + lane < nrows && tc0 + c < ncols) v = rd((int64_t)pair0_u32((uint32_t)col, (uint32_t)row, un) - colbase);
       tile[lane][c] = v;
     }
   } else {
@@ -139,7 +156,10 @@ __global__ void __launch_bounds__(256) expand_block_kernel(AoSource src, int64_t
     for (int k = 0; k < 4; ++k) {
       const int r = warp + 8 * k, row = grow0 + r;
       double v = 0.0;
-      if (tr0 + r < nrows && tc0 + lane < ncols) v = ao_value(src, slab, pair0(row, col, n) - colbase);
+      if (tr0 + r < nrows && tc0 + lane < ncols) {
+        const uint32_t lo = (uint32_t)min(row, col), hi = (uint32_t)max(row, col);
+        v = rd((int64_t)pair0_u32(lo, hi, un) - colbase);
+      }
       tile[r][lane] = v;
     }
   }
@@ -204,6 +224,7 @@ struct GemmArgs {
 
 // Epilogues -----------------------------------------------------------------------------------
 struct EpiPlain {  // C[z][m][n]
+  static constexpr bool kSplitRowTail = true;
   static constexpr bool kRowCoalesced = false;
   double *C; int64_t ldc, strideC;
   __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { C[z * strideC + (int64_t)m * ldc + n] = v; }
@@ -212,6 +233,7 @@ struct EpiPlain {  // C[z][m][n]
 //   T1t[f][z][mu]  (mu contiguous: the second quarter reads K-contiguous rows; z inside f so that the
 //   second quarter's output columns for one window pair are consecutive AO-pair slabs)
 struct EpiQ1 {
+  static constexpr bool kSplitRowTail = false;
   static constexpr bool kRowCoalesced = false;
   double *T1t; int nc; int bc; int64_t ldt;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
@@ -224,6 +246,7 @@ struct EpiQ1 {
 // semantics, zeroing |t| <= tol (E.f90:1113).  tol < 0 keeps everything.  Consecutive n are consecutive
 // columns of one H row: 64-byte runs per 8x8 accumulator tile.
 struct EpiScatterH {
+  static constexpr bool kSplitRowTail = true;
   static constexpr bool kRowCoalesced = false;
   double *H; int64_t ldh; int64_t col0; const int32_t *slot; int nf; int bc; double tol;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
@@ -235,6 +258,7 @@ struct EpiScatterH {
 // Third quarter, chunked: m = (z, row) over `nrows` rows of each slot's expanded block, n = kf.
 //   T3[slot0+z][kf][roff+row] += v   (accumulated over the AO-pair chunks; mu contiguous for the fourth quarter)
 struct EpiAccT {
+  static constexpr bool kSplitRowTail = false;
   static constexpr bool kRowCoalesced = true;  // consecutive m (mu within one slot) are consecutive in T3
   double *T3; int nrows; int roff; int nf2; int64_t ldt;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
@@ -251,12 +275,22 @@ struct EpiAccT {
 };
 // Fourth quarter: m = ks, n = (z, kf)  ->  OUT[z][ks][kf]
 struct EpiOut {
+  static constexpr bool kSplitRowTail = true;
   static constexpr bool kRowCoalesced = false;
   double *OUT; int ns2, nf2;
   __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
     int zz = n / nf2, kf = n - zz * nf2;
     OUT[((int64_t)zz * ns2 + m) * nf2 + kf] = v;
   }
+};
+
+// Adapter for a GEMM launched with its operands exchanged (C^T = B A^T): element (m, n) of that launch is element
+// (n + row_off, m) of the original problem.  Used for the row tail of a tall-skinny-by-wide product (see launch_gemm).
+template <class Epi>
+struct EpiSwapped {
+  static constexpr bool kRowCoalesced = false;
+  Epi epi; int row_off;
+  __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { epi(z, n + row_off, m, v); }
 };
 
 template <int BM, int BN, int WM, int WN, int STAGES, class Epi>

@@ -11,20 +11,21 @@ T = ol.Transformer(0)
 out = {}
 shapes = [(8192, 8192, 8192), (1350, 28672, 1500), (1350, 89440, 1500), (1350, 8400, 1500), (28672, 56, 1500), (60000, 150, 32),
           (60000, 150, 128), (450, 21000, 500), (4096, 4096, 4096)]
-for gv in (1, 2):
+for gv, split in ((2, 0), (2, 1)):
     T.set_option(T.OPT_GEMM_VARIANT, gv)
+    T.set_option(T.OPT_SPLIT_ROW_TAIL, split)
     for (m, n, k) in shapes:
         try:
             ms, _ = T.kernel_bench(1, m, n, k, iters=3)
         except Exception as e:  # noqa: BLE001
-            print("gemm variant", gv, m, n, k, "FAILED", e, flush=True)
-            out[f"gemm_v{gv}_{m}x{n}x{k}"] = {"error": str(e)}
+            print("gemm variant", gv, "split", split, m, n, k, "FAILED", e, flush=True)
+            out[f"gemm_v{gv}_split{split}_{m}x{n}x{k}"] = {"error": str(e)}
             continue
         tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-        out[f"gemm_v{gv}_{m}x{n}x{k}"] = {"ms": ms, "TFLOP/s": tf}
-        print("gemm variant", gv, m, n, k, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
+        out[f"gemm_v{gv}_split{split}_{m}x{n}x{k}"] = {"ms": ms, "TFLOP/s": tf}
+        print("gemm variant", gv, "split", split, m, n, k, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
 T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
-for variant, gen in [(1, 1), (3, 1), (1, 2), (3, 2)]:
+for variant, gen in [(3, 1), (4, 1), (3, 2), (4, 2)]:
     T.set_option(T.OPT_Q1_VARIANT, variant)
     T.set_option(T.OPT_BENCH_GEN, gen)
     for nc, nfb, bc in [(1500, 56, 512), (1500, 40, 512), (1500, 64, 512), (1500, 32, 512), (1500, 16, 1024), (500, 50, 2048), (1000, 32, 1024)]:

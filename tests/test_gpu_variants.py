@@ -25,7 +25,9 @@ def tma(T, request):
 # every tile configuration (n <= 8, 16, 32, 64, 80-, 128-wide), K tails, row tails, several tiles per CTA, K < 16
 @pytest.mark.parametrize("m,n,k", [(19, 5, 19), (300, 150, 120), (1000, 8, 333), (257, 129, 65), (128, 128, 16), (7, 3, 2),
                                     (513, 81, 1501), (64, 24, 50), (2000, 16, 100), (700, 33, 18), (5000, 56, 130),
-                                    (1350, 700, 96), (40000, 150, 34), (130, 1000, 1), (256, 256, 1600)])
+                                    (1350, 700, 96), (40000, 150, 34), (130, 1000, 1), (256, 256, 1600),
+                                    # few rows x >= 2048 columns: the <= 80-row tail runs as an operand-swapped second launch
+                                    (1350, 2100, 96), (200, 2048, 40), (129, 4096, 33), (450, 3000, 500), (136, 2500, 7)])
 def test_tma_gemm_vs_numpy(tma, m, n, k):
     rng = np.random.default_rng(m * 1000 + n)
     A, B = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (n, k))
@@ -106,7 +108,7 @@ def test_tma_generated_chunked_stream_energy(O, tma, cols):
 
 
 # ---- warp-specialised fused generation + first-quarter kernel (q1 variant 3, q1_gen_ws_kernel) --------------------------------
-@pytest.fixture(params=[1, 3], ids=["single_role", "warp_specialised"])
+@pytest.fixture(params=[1, 3, 4], ids=["single_role", "warp_specialised_8g", "warp_specialised_4g_pipelined"])
 def ws(T, request):
     T.set_option(T.OPT_Q1_VARIANT, request.param)
     yield T
@@ -156,8 +158,9 @@ def test_ws_generated_source_inter_stream(O, ws, gemm_variant):
 
 
 def test_all_new_variants_n500_properties(T):
-    """BASELINE size N=500 (MP2 window, O=50) with the TMA GEMM + warp-specialised first quarter: the reduced sums must
-    agree with the default variants to 1e-9 relative (size-independent property: same transform, different kernels)."""
+    """BASELINE size N=500 (MP2 window, O=50): the reduced sums of the cp.async GEMM + single-role first quarter must agree to
+    1e-9 relative with the TMA GEMM + either warp-specialised first quarter, with and without the row-tail split (450
+    virtuals = 3 x 128 + 66).  Size-independent property: same transform, different kernels."""
     n, occ = 500, 50
     q, _ = np.linalg.qr(np.random.default_rng(n).standard_normal((n, n)))
     eps = np.concatenate([np.linspace(-2.0, -0.5, occ), np.linspace(0.2, 3.0, n - occ)])
@@ -169,13 +172,18 @@ def test_all_new_variants_n500_properties(T):
         T.set_option(T.OPT_GEMM_VARIANT, 1)
         T.set_option(T.OPT_Q1_VARIANT, 1)
         ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
-        T.set_option(T.OPT_GEMM_VARIANT, 2)
-        T.set_option(T.OPT_Q1_VARIANT, 3)
-        got = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
+        got = []
+        for q1v, split in ((3, 1), (4, 1), (4, 0)):
+            T.set_option(T.OPT_GEMM_VARIANT, 2)
+            T.set_option(T.OPT_Q1_VARIANT, q1v)
+            T.set_option(T.OPT_SPLIT_ROW_TAIL, split)
+            got.append(T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps))
     finally:
+        T.set_option(T.OPT_SPLIT_ROW_TAIL, 1)
         T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
         T.set_option(T.OPT_Q1_VARIANT, T.DEFAULT_Q1_VARIANT)
         T.set_option(T.OPT_CHUNK_COLS, 0)
-    assert abs(got[0] - ref[0]) <= 2  # entries within rounding of the 1e-10 threshold may flip
-    for a, b in zip(got[1:], ref[1:]):
-        assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
+    for g in got:
+        assert abs(g[0] - ref[0]) <= 2  # entries within rounding of the 1e-10 threshold may flip
+        for a, b in zip(g[1:], ref[1:]):
+            assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
