@@ -261,9 +261,10 @@ cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
     // Few rows x very many columns (second and fourth quarter: rows = the second-contracted window, e.g. 1350 virtuals):
     // 128-row tiles would pad 1350 to 1408 (4 % of the DMMAs on zeros).  The full 128-row tiles run as they are; the
     // row tail (<= 80 rows) runs as a second launch with the operands exchanged, so that the tail becomes the N
-    // dimension and gets an 8..80-wide tile.
+    // dimension and gets an 8..80-wide tile.  Only when the tail launch itself has >= 3 waves of 128-row tiles: measured
+    // on B200 (profiles/r01f_variant_probe.log) 1350 x 89440 x 1500 gains 1.7 %, 1350 x 8400 x 1500 would lose 11 %.
     const int tail = g.M % 128, main = g.M - tail;
-    if (tma && h->split_row_tail && g.N >= 2048 && main >= 128 && tail > 0 && tail <= 80) {
+    if (tma && h->split_row_tail && ceil_div(g.N, 128) >= 3 * (int64_t)h->num_sms && main >= 128 && tail > 0 && tail <= 80) {
       GemmArgs gm = g;
       gm.M = main;
       cudaError_t e = launch_gemm_one(h, gm, epi, true);
@@ -1267,6 +1268,22 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (check) CK(cudaMemcpy(check, h->T1t.p, sizeof(double), cudaMemcpyDeviceToHost));
+  } else if (kind == 3) {  // probe: TMA GEMM with ONE warp per scheduler (64x128 tile, 4 warps) -- how far a single warp feeds the DMMA pipe
+    const int64_t lda = roundup2(k);
+    CK(h->X.ensure((size_t)m * lda * sizeof(double)));
+    CK(h->T1t.ensure((size_t)n * lda * sizeof(double)));
+    CK(h->OUT.ensure((size_t)m * n * sizeof(double)));
+    CK(cudaMemsetAsync(h->X.p, 0x3f, (size_t)m * lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->T1t.p, 0x3f, (size_t)n * lda * sizeof(double), h->stream));
+    GemmArgs g{h->X.as<double>(), h->T1t.as<double>(), (int)m, (int)n, (int)k, lda, lda, 0, 0};
+    EpiPlain epi{h->OUT.as<double>(), n, 0};
+    CK((launch_gemm_tma_cfg<64, 128, 2, 2>(h, g, epi)));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < iters; ++i) CK((launch_gemm_tma_cfg<64, 128, 2, 2>(h, g, epi)));
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (check) CK(cudaMemcpy(check, h->OUT.p, sizeof(double), cudaMemcpyDeviceToHost));
   } else {  // DGEMM m x n x k on generated operands
     const int64_t lda = roundup2(k);
     CK(h->X.ensure((size_t)m * lda * sizeof(double)));

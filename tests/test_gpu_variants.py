@@ -26,8 +26,8 @@ def tma(T, request):
 @pytest.mark.parametrize("m,n,k", [(19, 5, 19), (300, 150, 120), (1000, 8, 333), (257, 129, 65), (128, 128, 16), (7, 3, 2),
                                     (513, 81, 1501), (64, 24, 50), (2000, 16, 100), (700, 33, 18), (5000, 56, 130),
                                     (1350, 700, 96), (40000, 150, 34), (130, 1000, 1), (256, 256, 1600),
-                                    # few rows x >= 2048 columns: the <= 80-row tail runs as an operand-swapped second launch
-                                    (1350, 2100, 96), (200, 2048, 40), (129, 4096, 33), (450, 3000, 500), (136, 2500, 7)])
+                                    # few rows x >= 3 waves of 128-column tiles: the <= 80-row tail runs as an operand-swapped second launch
+                                    (1350, 2100, 96), (200, 57000, 40), (129, 60000, 33), (450, 58000, 20), (136, 56900, 7)])
 def test_tma_gemm_vs_numpy(tma, m, n, k):
     rng = np.random.default_rng(m * 1000 + n)
     A, B = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (n, k))
