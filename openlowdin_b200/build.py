@@ -32,8 +32,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed building liblowdin_itgpu.so")
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(r.stderr)
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:  # registers / spills / smem per kernel (tracked in git)
+        f.write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
     return LIB
 
 
