@@ -934,11 +934,8 @@ int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t
   while (m < n && p[m] != -1) ++m;  // terminator (C.f90:279-280)
   if (m == 0) return 0;
   const int na = h->sp[h->up_a].n, nb = h->sp[h->up_b].n;
-  const int lim_pq = (h->up_a == h->up_b) ? na : (h->up_swapped ? nb : na);
-  const int lim_rs = (h->up_a == h->up_b) ? na : (h->up_swapped ? na : nb);
-  for (int64_t k = 0; k < m; ++k)
-    if (p[k] < 1 || q[k] < 1 || r[k] < 1 || s[k] < 1 || p[k] > lim_pq || q[k] > lim_pq || r[k] > lim_rs || s[k] > lim_rs)
-      return fail(h, "AO stack entry " + std::to_string(k) + " has an index outside the basis");
+  const unsigned lim_pq = (unsigned)((h->up_a == h->up_b) ? na : (h->up_swapped ? nb : na));
+  const unsigned lim_rs = (unsigned)((h->up_a == h->up_b) ? na : (h->up_swapped ? na : nb));
   CK(cudaSetDevice(h->device));
   CK(h->st_p.ensure(m * 4)); CK(h->st_q.ensure(m * 4)); CK(h->st_r.ensure(m * 4)); CK(h->st_s.ensure(m * 4)); CK(h->st_v.ensure(m * 8));
   CK(cudaMemcpyAsync(h->st_p.p, p, m * 4, cudaMemcpyHostToDevice, h->stream));
@@ -946,6 +943,18 @@ int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t
   CK(cudaMemcpyAsync(h->st_r.p, r, m * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->st_s.p, s, m * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->st_v.p, v, m * 8, cudaMemcpyHostToDevice, h->stream));
+  // Index check on the host while the copies are in flight (pinned callers): branch-free so that it vectorises;
+  // 1-based index i is valid iff (unsigned)(i-1) < limit.  Nothing is scattered from a stack with a bad entry.
+  unsigned bad = 0;
+  for (int64_t k = 0; k < m; ++k)
+    bad |= (unsigned)(((unsigned)p[k] - 1u) >= lim_pq) | (unsigned)(((unsigned)q[k] - 1u) >= lim_pq) |
+           (unsigned)(((unsigned)r[k] - 1u) >= lim_rs) | (unsigned)(((unsigned)s[k] - 1u) >= lim_rs);
+  if (bad) {
+    cudaStreamSynchronize(h->stream);
+    int64_t k = 0;
+    while (k < m && ((unsigned)p[k] - 1u) < lim_pq && ((unsigned)q[k] - 1u) < lim_pq && ((unsigned)r[k] - 1u) < lim_rs && ((unsigned)s[k] - 1u) < lim_rs) ++k;
+    return fail(h, "AO stack entry " + std::to_string(k) + " has an index outside the basis");
+  }
   scatter_stacks_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, h->stream>>>(
       h->st_p.as<int32_t>(), h->st_q.as<int32_t>(), h->st_r.as<int32_t>(), h->st_s.as<int32_t>(), h->st_v.as<double>(), m,
       h->up_a == h->up_b, h->up_swapped, na, nb, h->ao[h->up_a][h->up_b].data.as<double>());
