@@ -15,6 +15,8 @@
  *        -> lowdin_host_ints_filename, lowdin_host_read_ints_file, lowdin_host_write_ints_file
  *   <prefix>moint.dat sequential unformatted records (C.f90:419-456, E.f90:1244-1268)
  *        -> lowdin_host_write_moint_quads / _pairs
+ *   program IntegralsTransformation, species / species-pair loop (IntegralTransformation.f90:171-355)
+ *        -> lowdin_host_plan_program, lowdin_host_run_program
  *
  * Only the functions that take a lowdin_it_handle need a GPU.  Every function returns 0 on success; on error the
  * message is available through lowdin_host_last_error().
@@ -91,6 +93,29 @@ int lowdin_host_atomic_to_molecular_one_species(lowdin_it_handle h, const lowdin
                                                 int64_t *nonzero);
 int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
                                                 const lowdin_host_species *b, int64_t *nonzero);
+
+/* ---- the program's species loop (IntegralTransformation.f90:171-355) and its division among devices ------------
+ * One entry per transformer call the reference program would make, in program order: species i (skipped under PT2 when
+ * IONIZE_SPECIES is set and does not name it, :176-185), then every pair (i, j>i) (skipped under PT2 unless one of the
+ * two is named, :259-269).  Method C passes the species with FEWER occupied orbitals first (:322-334); E keeps (i,j).
+ * Calls are independent (each reads its own .ints streams and writes its own moint.dat), so with several processes,
+ * one per GPU, whole calls are assigned to ranks -- no collective (SURVEY.md 8e "species pairs are scheduled across
+ * devices").  The assignment is longest-processing-time-first on the algorithmic flop count of each call and is a pure
+ * function of the inputs: every rank computes the same plan without communicating. */
+typedef struct lowdin_host_task {
+  int first, second;  /* indices into the species array, in CALL order; second = -1 for a one-species call */
+  int win[8];         /* window table of the call (lowdin_host_windows) */
+  int symmetric;
+  double flops;       /* algorithmic flops: 2 N nf (N+ns) n_slabs + 2 N' nf' (N'+ns') n_pairs */
+  int rank;           /* process / device that runs the call */
+} lowdin_host_task;
+
+int lowdin_host_plan_program(const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies, int nranks,
+                             lowdin_host_task *tasks, int cap, int *ntasks);
+/* Runs the calls of the plan assigned to `rank` (program order) on handle h.  *nonzero = integrals written by this rank,
+ * *ncalls = calls it made. */
+int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies,
+                            int rank, int nranks, int64_t *nonzero, int *ncalls);
 
 #ifdef __cplusplus
 }

@@ -254,7 +254,7 @@ HOST_SYMBOLS = [
     "lowdin_host_last_error", "lowdin_host_partial_transform", "lowdin_host_windows", "lowdin_host_ints_filename",
     "lowdin_host_write_ints_file", "lowdin_host_read_ints_file", "lowdin_host_write_moint_quads",
     "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
-    "lowdin_host_atomic_to_molecular_two_species",
+    "lowdin_host_atomic_to_molecular_two_species", "lowdin_host_plan_program", "lowdin_host_run_program",
 ]
 
 
@@ -269,6 +269,11 @@ class HostSpecies(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("id", C.c_int), ("nao", C.c_int), ("occupation", C.c_int),
                 ("core_orbitals", C.c_int), ("active_orbitals", C.c_int), ("coeff", C.c_void_p), ("ldc", C.c_int),
                 ("ncols", C.c_int)]
+
+
+class HostTask(C.Structure):
+    _fields_ = [("first", C.c_int), ("second", C.c_int), ("win", C.c_int * 8), ("symmetric", C.c_int), ("flops", C.c_double),
+                ("rank", C.c_int)]
 
 
 def host_control(method="C", partial="MP2", stack=30000, nfiles=1, ionize_mo=0, pt_transition_operator=False,
@@ -315,6 +320,8 @@ def _host():
     L.lowdin_host_write_moint_pairs.argtypes = [C.c_char_p, C.c_int, _i64p, _i64p, _f64p, C.c_int64]
     L.lowdin_host_atomic_to_molecular_one_species.argtypes = [C.c_void_p, PC, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
+    L.lowdin_host_plan_program.argtypes = [PC, PS, C.c_int, C.c_int, C.POINTER(HostTask), C.c_int, C.POINTER(C.c_int)]
+    L.lowdin_host_run_program.argtypes = [C.c_void_p, PC, PS, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L._host_ready = True
     return L
 
@@ -378,3 +385,32 @@ def host_transform_two_species(T, ctl, a, b):
     n = C.c_int64()
     _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
     return n.value
+
+
+def _species_array(species):
+    arr = (HostSpecies * len(species))()
+    for i, sp in enumerate(species):
+        C.memmove(C.byref(arr[i]), C.byref(sp), C.sizeof(HostSpecies))
+    arr._keep = list(species)  # coefficient buffers stay alive with the array
+    return arr
+
+
+def host_plan_program(ctl, species, nranks=1):
+    """The transformer calls of the reference program's species loop and the rank each one runs on.
+    Returns a list of dicts: first, second (indices into `species`, call order; second None = one species), win, symmetric,
+    flops, rank."""
+    arr = _species_array(species)
+    cap = len(species) * (len(species) + 1) // 2
+    tasks = (HostTask * max(cap, 1))()
+    n = C.c_int()
+    _hck(_host().lowdin_host_plan_program(C.byref(ctl), arr, len(species), nranks, tasks, cap, C.byref(n)))
+    return [dict(first=t.first, second=(t.second if t.second >= 0 else None), win=list(t.win), symmetric=bool(t.symmetric),
+                 flops=t.flops, rank=t.rank) for t in tasks[:n.value]]
+
+
+def host_run_program(T, ctl, species, rank=0, nranks=1):
+    """Run this rank's share of the program's calls; returns (integrals written, calls made)."""
+    arr = _species_array(species)
+    nz, nc = C.c_int64(), C.c_int()
+    _hck(_host().lowdin_host_run_program(T.h, C.byref(ctl), arr, len(species), rank, nranks, C.byref(nz), C.byref(nc)))
+    return nz.value, nc.value

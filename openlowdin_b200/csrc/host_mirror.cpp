@@ -254,6 +254,68 @@ int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowd
   return 0;
 }
 
+// Algorithmic flops of one call, with the library's rule "smaller window contracted first".
+double call_flops(const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b, const int win[8],
+                  int symmetric) {
+  const lowdin_host_species *sb = b ? b : a;
+  auto cnt = [&](int w) { return (double)std::max(0, win[2 * w + 1] - win[2 * w] + 1); };
+  const double Na = a->nao, Nb = sb->nao, Mb = Nb * (Nb + 1) / 2;
+  const double nf1 = std::min(cnt(0), cnt(1)), ns1 = std::max(cnt(0), cnt(1));
+  const double nf2 = std::min(cnt(2), cnt(3)), ns2 = std::max(cnt(2), cnt(3));
+  double npairs = 0;  // first pairs entering the second half: E keeps q<=p (E.f90:878-884), C skips q<p when symmetric (C.f90:380)
+  for (int x = win[0]; x <= win[1]; ++x)
+    for (int y = win[2]; y <= win[3]; ++y)
+      if ((ctl->method == 'E') ? (y <= x) : !(symmetric && y < x)) npairs += 1;
+  return 2.0 * Na * nf1 * (Na + ns1) * Mb + 2.0 * Nb * nf2 * (Nb + ns2) * npairs;
+}
+
+bool pt2_filter_on(const lowdin_host_control *c) { return is(c, "PT2") && c->n_ionize_species > 0; }
+bool named_for_ionization(const lowdin_host_control *c, const lowdin_host_species *a) {
+  const std::string na = trimmed(a->name, sizeof a->name);
+  for (int s = 0; s < c->n_ionize_species && s < 4; ++s)
+    if (na == trimmed(c->ionize_species[s], 32)) return true;
+  return false;
+}
+
+int plan_program(const lowdin_host_control *ctl, const lowdin_host_species *sp, int n, int nranks, std::vector<lowdin_host_task> &out) {
+  if (check_ctl(ctl)) return 1;
+  if (!sp || n < 1) return hfail("no species");
+  if (nranks < 1) return hfail("nranks < 1");
+  out.clear();
+  auto add = [&](int first, int second) -> int {
+    lowdin_host_task t{};
+    t.first = first; t.second = second; t.rank = 0;
+    const lowdin_host_species *a = &sp[first], *b = second >= 0 ? &sp[second] : nullptr;
+    if (lowdin_host_windows(ctl, a, b, t.win, &t.symmetric)) return 1;
+    t.flops = call_flops(ctl, a, b, t.win, t.symmetric);
+    out.push_back(t);
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    // IntegralTransformation.f90:176-185
+    if (!pt2_filter_on(ctl) || named_for_ionization(ctl, &sp[i])) { if (add(i, -1)) return 1; }
+    for (int j = i + 1; j < n; ++j) {
+      // :259-269
+      if (pt2_filter_on(ctl) && !named_for_ionization(ctl, &sp[i]) && !named_for_ionization(ctl, &sp[j])) continue;
+      // :322-334 -- method C calls with the species of fewer occupied orbitals first
+      const bool keep = (ctl->method != 'C') || (sp[i].occupation <= sp[j].occupation);
+      if (keep ? add(i, j) : add(j, i)) return 1;
+    }
+  }
+  // longest-processing-time-first over the ranks; ties broken by program order and by the lowest rank
+  std::vector<int> order(out.size());
+  for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return out[x].flops > out[y].flops; });
+  std::vector<double> load(nranks, 0.0);
+  for (int k : order) {
+    int best = 0;
+    for (int r = 1; r < nranks; ++r) if (load[r] < load[best]) best = r;
+    out[k].rank = best;
+    load[best] += out[k].flops;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -399,6 +461,43 @@ int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin
                                                 const lowdin_host_species *b, int64_t *nonzero) {
   if (!b) return hfail("second species missing");
   return run_and_write(h, ctl, a, b, nonzero);
+}
+
+int lowdin_host_plan_program(const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies, int nranks,
+                             lowdin_host_task *tasks, int cap, int *ntasks) {
+  std::vector<lowdin_host_task> plan;
+  if (plan_program(ctl, species, nspecies, nranks, plan)) return 1;
+  if (ntasks) *ntasks = (int)plan.size();
+  if (tasks) {
+    if ((int)plan.size() > cap) return hfail("task buffer too small");
+    std::copy(plan.begin(), plan.end(), tasks);
+  }
+  return 0;
+}
+
+int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies,
+                            int rank, int nranks, int64_t *nonzero, int *ncalls) {
+  if (rank < 0 || rank >= nranks) return hfail("bad rank");
+  std::vector<lowdin_host_task> plan;
+  if (plan_program(ctl, species, nspecies, nranks, plan)) return 1;
+  int64_t total = 0;
+  int calls = 0;
+  for (const lowdin_host_task &t : plan) {
+    if (t.rank != rank) continue;
+    const lowdin_host_species *a = &species[t.first], *b = t.second >= 0 ? &species[t.second] : nullptr;
+    if (ctl->verbose) {  // IntegralTransformation.f90:188-191, :272-276
+      const lowdin_host_species *lo = (b && t.second < t.first) ? b : a, *hi = (b && t.second < t.first) ? a : b;  // named in (i, j>i) order
+      if (b) printf("\n Inter-species integrals transformation for: %s/%s\n\n", trimmed(lo->name, 32).c_str(), trimmed(hi->name, 32).c_str());
+      else printf("\n Integrals transformation for: %s\n\n", trimmed(a->name, 32).c_str());
+    }
+    int64_t n = 0;
+    if (run_and_write(h, ctl, a, b, &n)) return 1;
+    total += n;
+    ++calls;
+  }
+  if (nonzero) *nonzero = total;
+  if (ncalls) *ncalls = calls;
+  return 0;
 }
 
 }  // extern "C"

@@ -232,3 +232,104 @@ def test_two_species_file_to_file_both_call_orders(O, T, tmp_path, method):
         Ma, Mb = O.npairs(na), O.npairs(nb)
         assert np.abs(dense_pairs(*got, Ma, Mb) - dense_pairs(*ref, Ma, Mb)).max() <= 1e-10
         assert_lists_match(got[:2], got[2], ref[:2], ref[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# the program's species loop and its division among devices (IntegralTransformation.f90:171-355)
+# ---------------------------------------------------------------------------------------------
+def _apmo_species(coeffs=None):
+    """H2O.APMO shapes: electrons N=19 occ 5, two protons N=50 occ 1 each."""
+    shapes = [("E-", 19, 5), ("H-A_1", 50, 1), ("H-B_1", 50, 1)]
+    return [capi.host_species(nm, i + 1, n, occ, coeff=None if coeffs is None else coeffs[i]) for i, (nm, n, occ) in enumerate(shapes)]
+
+
+def test_program_plan_order_and_method_c_pair_swap():
+    sp = _apmo_species()
+    plan_c = capi.host_plan_program(capi.host_control("C", "MP2"), sp)
+    # program order: species i, then pairs (i, j>i); C calls with the species of fewer occupied orbitals first (:322-334)
+    assert [(t["first"], t["second"]) for t in plan_c] == [(0, None), (1, 0), (2, 0), (1, None), (1, 2), (2, None)]
+    plan_e = capi.host_plan_program(capi.host_control("E", "MP2"), sp)
+    assert [(t["first"], t["second"]) for t in plan_e] == [(0, None), (0, 1), (0, 2), (1, None), (1, 2), (2, None)]
+    for t in plan_c + plan_e:
+        assert t["rank"] == 0 and t["flops"] > 0
+    # windows are those of lowdin_host_windows for the call order
+    assert plan_c[1]["win"] == capi.host_windows(capi.host_control("C", "MP2"), sp[1], sp[0])[0]
+    # flop model (SURVEY.md 8d) of the electronic MP2 call: 2 N Q (N+P) M + 2 N S (N+R) n_ij, transformer-E roles
+    n, occ, M = 19, 5, 190
+    want = 2.0 * n * occ * (n + n - occ) * M + 2.0 * n * occ * (n + n - occ) * (occ * (n - occ))
+    assert plan_e[0]["flops"] == want
+
+
+def test_program_plan_pt2_species_filter():
+    sp = _apmo_species()
+    # PT2 with IONIZE_SPECIES: only the named species and the pairs that contain it (:176-185, :259-269)
+    plan = capi.host_plan_program(capi.host_control("E", "PT2", ionize_species=("H-A_1",)), sp)
+    assert [(t["first"], t["second"]) for t in plan] == [(0, 1), (1, None), (1, 2)]
+    # without IONIZE_SPECIES every species and pair is transformed, also under PT2
+    assert len(capi.host_plan_program(capi.host_control("E", "PT2"), sp)) == 6
+    # the filter applies to PT2 only
+    assert len(capi.host_plan_program(capi.host_control("E", "MP2-PT2", ionize_species=("H-A_1",)), sp)) == 6
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 8])
+def test_program_plan_assignment_is_balanced_and_complete(nranks):
+    sp = _apmo_species()
+    plan = capi.host_plan_program(capi.host_control("C", "MP2"), sp, nranks)
+    load = np.zeros(nranks)
+    for t in plan:
+        assert 0 <= t["rank"] < nranks
+        load[t["rank"]] += t["flops"]
+    total, biggest = load.sum(), max(t["flops"] for t in plan)
+    # longest-processing-time-first: no rank exceeds the mean by more than one call
+    assert load.max() <= total / nranks + biggest
+    if nranks <= len(plan):
+        assert (load > 0).all()
+    # deterministic: a second evaluation gives the same plan (every rank computes it independently)
+    assert plan == capi.host_plan_program(capi.host_control("C", "MP2"), sp, nranks)
+
+
+def test_program_plan_errors():
+    sp = _apmo_species()
+    with pytest.raises(capi.LowdinITError):
+        capi.host_plan_program(capi.host_control("C", "MP2"), sp, 0)
+    with pytest.raises(capi.LowdinITError):
+        capi.host_plan_program(capi.host_control("X", "MP2"), sp, 1)
+
+
+@pytest.mark.gpu
+def test_run_program_apmo_shapes_file_to_file(O, T, tmp_path):
+    """Three species (small stand-ins of the H2O.APMO layout), method E, MP2: the whole species loop through
+    lowdin_host_run_program, every moint.dat against the oracle."""
+    shapes = [("E-", 7, 3), ("H-A_1", 5, 1), ("H-B_1", 4, 1)]
+    S = 40
+    Cs = [O.random_orthonormal(n, 31 + i) for i, (_, n, _) in enumerate(shapes)]
+    sp = [capi.host_species(nm, i + 1, n, occ, coeff=Cs[i]) for i, (nm, n, occ) in enumerate(shapes)]
+    intra, inter = {}, {}
+    for i, (nm, n, _) in enumerate(shapes):
+        intra[i] = O.hash_packed_intra(100 + i, n)
+        _split_to_files(tmp_path, nm, O.canonical_list_intra(intra[i], n), 2, S)
+        for j in range(i + 1, len(shapes)):
+            inter[i, j] = O.hash_rect_inter(200 + 10 * i + j, n, shapes[j][1])
+            _split_to_files(tmp_path, f"{nm}.{shapes[j][0]}", O.canonical_list_inter(inter[i, j], n, shapes[j][1]), 2, S)
+    ctl = capi.host_control("E", "MP2", stack=S, nfiles=2, scratch_dir=str(tmp_path))
+    written, calls = capi.host_run_program(T, ctl, sp)
+    assert calls == 6
+    total = 0
+    for i, (nm, n, occ) in enumerate(shapes):
+        ref = O.transform_e_intra(Cs[i], intra[i], O.windows_e_intra("MP2", n, occ))
+        got = read_moint_pairs(str(tmp_path / f"{nm}moint.dat"), S)
+        M = O.npairs(n)
+        assert np.abs(dense_pairs(*got, M, M) - dense_pairs(*ref, M, M)).max() <= 1e-10
+        total += len(got[2])
+        for j in range(i + 1, len(shapes)):
+            nm2, n2, occ2 = shapes[j]
+            ref = O.transform_e_inter(Cs[i], Cs[j], inter[i, j], O.windows_e_inter("MP2", n, n2, occ, occ2))
+            got = read_moint_pairs(str(tmp_path / f"{nm}.{nm2}moint.dat"), S)
+            assert np.abs(dense_pairs(*got, M, O.npairs(n2)) - dense_pairs(*ref, M, O.npairs(n2))).max() <= 1e-10
+            total += len(got[2])
+    assert total == written
+    # a second "rank" of two runs only its share and the shares are disjoint and complete
+    plan = capi.host_plan_program(ctl, sp, 2)
+    for r in (0, 1):
+        _, c = capi.host_run_program(T, ctl, sp, r, 2)
+        assert c == sum(1 for t in plan if t["rank"] == r)

@@ -116,3 +116,41 @@ def test_shard_plan_properties():
             cover += list(range(lo, hi))
         assert cover == list(range(101))
     assert capi.blocked_offset(2, 7, 5, 4) == (1 * 4 + 2) * 5 + 2
+
+
+def _plan_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openlowdin_b200 import capi
+        shapes = [("E-", 19, 5), ("H-A_1", 50, 1), ("H-B_1", 50, 1)]
+        sp = [capi.host_species(nm, i + 1, n, occ) for i, (nm, n, occ) in enumerate(shapes)]
+        plan = capi.host_plan_program(capi.host_control("C", "MP2"), sp, world)
+        mine = [(t["first"], t["second"]) for t in plan if t["rank"] == rank]
+        work = torch.tensor([sum(t["flops"] for t in plan if t["rank"] == rank)], dtype=torch.float64)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)         # no data-path collective is needed; this one is the test's own check
+        dist.all_reduce(work)
+        if rank == 0:
+            q.put((gathered, float(work[0]), [(t["first"], t["second"]) for t in plan], sum(t["flops"] for t in plan)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_species_pair_calls_are_divided_among_ranks_without_overlap():
+    world, port = 2, 29655
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, work, program, total = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    flat = [c for part in gathered for c in part]
+    assert sorted(flat, key=str) == sorted(program, key=str) and len(set(flat)) == len(program) == 6
+    assert all(len(part) > 0 for part in gathered)
+    assert abs(work - total) <= 1e-6 * total
