@@ -638,3 +638,111 @@ def rankk_mo_block(La, Ca, rows_a, cols_a, Lb=None, Cb=None, rows_b=None, cols_b
     Ta = np.einsum("mp,kmn,nq->kpq", np.asarray(Ca)[:, rows_a], La, np.asarray(Ca)[:, cols_a], optimize=True)
     Tb = np.einsum("mp,kmn,nq->kpq", np.asarray(Cb)[:, rows_b], Lb, np.asarray(Cb)[:, cols_b], optimize=True)
     return np.einsum("kpq,krs->pqrs", Ta, Tb, optimize=True)
+
+
+# ----------------------------------------------------------------------------------------
+# second-order propagator (P2) poles: the consumer of the PT2-window MO integrals
+# ----------------------------------------------------------------------------------------
+def read_pairs_intra(ij, kl, v, n):
+    """ReadTransformedIntegrals_readOneSpecies, method E layout (ReadTransformedIntegrals.f90:302-311): packed array
+    addressed by IndexMapAA (PropagatorTheory.f90:178-193) minus one."""
+    M = npairs(n)
+    packed = np.zeros(M * (M + 1) // 2)
+    lib().orc_reader_pairs_intra(np.ascontiguousarray(ij, np.int64), np.ascontiguousarray(kl, np.int64),
+                                 np.ascontiguousarray(v), len(v), n, packed)
+    return packed
+
+
+def read_pairs_inter(ij, kl, v, na, nb, reversed_pair=False):
+    """ReadTransformedIntegrals_readTwoSpecies, method E layout.  The file holds (A A|B B) pair ids of the pair in
+    molecular-system order; reversed_pair=True is the reader's branch for a caller whose first species is B
+    (ReadTransformedIntegrals.f90:911-922): the result is then addressed M_a*(pair_b-1)+pair_a."""
+    Ma, Mb = npairs(na), npairs(nb)
+    rect = np.zeros(Ma * Mb)
+    lib().orc_reader_pairs_inter(np.ascontiguousarray(ij, np.int64), np.ascontiguousarray(kl, np.int64),
+                                 np.ascontiguousarray(v), len(v), na, nb, rect)
+    return np.ascontiguousarray(rect.reshape(Ma, Mb).T).reshape(-1) if reversed_pair else rect
+
+
+def p2_poles(a, species, aux, ionize_mo=0, factor_ss=1.0, factor_os=1.0, max_iter=50):
+    """PropagatorTheory_secondOrderCorrection (src/PT/PropagatorTheory.f90:459-1177) for species index `a`, without the
+    transition-operator branch: numerators / denominators of the 2ph and 2hp terms (:736-811 intra, :848-915 inter),
+    Newton-Raphson pole search from Koopmans' value until |delta omega| <= 1e-4 (:971-1073), pole strength (:1075).
+
+    species[j] = dict(name, n, occ, charge, lam, eps[, active]); aux[j] = MO integrals as the reader leaves them BEFORE the
+    charge scaling of :664-680: j == a the packed intra array (read_pairs_intra), j != a the rectangular array addressed
+    M_j*(pair_a-1)+pair_j (read_pairs_inter).  Returns [(orbital, koopmans, omega, pole_strength, iterations)] in Hartree for
+    orbital = ionize_mo, or HOMO and LUMO when ionize_mo == 0 (:603-621).
+    The reference's loop condition `residual>1e-4 .or. limit<ni` (:971) never ends once 50 iterations are exceeded; here
+    the search stops and raises instead."""
+    A = species[a]
+    na, oa, la = A["n"], A["occ"], float(A["lam"])
+    acta = A.get("active") or na
+    ea = np.asarray(A["eps"], dtype=np.float64)
+    xya = pair_table(na) + 1                                   # 1-based pair ids, PropagatorTheory.f90:153-160
+    Ma = npairs(na)
+    if ionize_mo:
+        orbitals = [ionize_mo]
+    else:
+        orbitals = list(range(oa if oa else 1, oa + 2))
+    occs = np.arange(1, oa + 1)
+    virs = np.arange(oa + 1, acta + 1)
+    out = []
+    for pa in orbitals:
+        terms = []                                             # (species j, numerators, denominators) for 2ph then 2hp
+        for j, B in enumerate(species):
+            if j == a:
+                vals = np.asarray(aux[j]) * A["charge"] * A["charge"]
+
+                def g(i1, i2, i3, i4):                          # IndexMapAA: ioff(min)+max over pair ids (:178-193)
+                    p1, p2 = xya[i1 - 1, i2 - 1], xya[i3 - 1, i4 - 1]
+                    lo, hi = np.minimum(p1, p2), np.maximum(p1, p2)
+                    return vals[(lo - 1) * Ma - (lo - 1) * lo // 2 + hi - 1]
+                ia, aa, ba = np.meshgrid(occs, virs, virs, indexing="ij")                  # :736-758
+                va, vb = g(pa, aa, ia, ba), g(pa, ba, ia, aa)
+                terms.append((j, "2ph", (va * (la * va - vb)).ravel(), (ea[ia - 1] - ea[aa - 1] - ea[ba - 1]).ravel()))
+                if oa > 1:                                                                   # :760-795
+                    aa, ia, ja = np.meshgrid(virs, occs, occs, indexing="ij")
+                    va, vb = g(pa, ia, ja, aa), g(pa, ja, ia, aa)
+                    terms.append((j, "2hp", (va * (la * va - vb)).ravel(), (ea[aa - 1] - ea[ia - 1] - ea[ja - 1]).ravel()))
+            else:
+                nb, ob, lb = B["n"], B["occ"], float(B["lam"])
+                actb = B.get("active") or nb
+                eb = np.asarray(B["eps"], dtype=np.float64)
+                xyb = pair_table(nb) + 1
+                Mb = npairs(nb)
+                vals = np.asarray(aux[j]) * A["charge"] * B["charge"]
+
+                def gab(i1, i2, i3, i4):                        # IndexMapAB: (ij-1)*M_b+kl (:195-212)
+                    return vals[(xya[i1 - 1, i2 - 1] - 1) * Mb + xyb[i3 - 1, i4 - 1] - 1]
+                occb, virb = np.arange(1, ob + 1), np.arange(ob + 1, actb + 1)
+                ib, aa, ab = np.meshgrid(occb, virs, virb, indexing="ij")                  # diagram A, :866-884
+                va = gab(pa, aa, ib, ab)
+                terms.append((j, "2ph", (la * lb * va ** 2).ravel(), (eb[ib - 1] - ea[aa - 1] - eb[ab - 1]).ravel()))
+                ab, ia, ib = np.meshgrid(virb, occs, occb, indexing="ij")                  # diagram B, :888-915
+                va = gab(pa, ia, ib, ab)
+                terms.append((j, "2hp", (la * lb * va ** 2).ravel(), (eb[ab - 1] - ea[ia - 1] - eb[ib - 1]).ravel()))
+        koop = ea[pa - 1]
+        same_spin = A["name"] in ("E-ALPHA", "E-BETA")
+        omega, it, residual = koop, 0, 1.0
+        while residual > 1.0e-4:                                                             # :971-1071
+            it += 1
+            if it > max_iter:
+                raise RuntimeError("P2 pole search did not converge")
+            last = omega
+            sigma, dsigma = last - koop, 1.0
+            for j, _, num, den in terms:
+                b = den + last
+                e, de = np.sum(num / b), np.sum(num / b ** 2)
+                nameb = species[j]["name"]
+                f = 1.0
+                if same_spin and j == a:
+                    f = factor_ss
+                elif {A["name"], nameb} == {"E-ALPHA", "E-BETA"}:
+                    f = factor_os
+                sigma -= f * e
+                dsigma += f * de
+            omega = last - sigma / dsigma
+            residual = abs(omega - last)
+        out.append((pa, koop, omega, 1.0 / dsigma, it))
+    return out
