@@ -15,6 +15,10 @@
  *        -> lowdin_host_ints_filename, lowdin_host_read_ints_file, lowdin_host_write_ints_file
  *   <prefix>moint.dat sequential unformatted records (C.f90:419-456, E.f90:1244-1268)
  *        -> lowdin_host_write_moint_quads / _pairs
+ *   transformer D's one-integral-per-record moint.dat (TransformIntegralsD.f90:221-236, :447-457)
+ *        -> lowdin_host_write_moint_d_intra / _inter
+ *   lowdin.wfn labelled records (Matrix.f90:697-792, Vector.f90:738-821; IntegralTransformation.f90:193-215)
+ *        -> lowdin_host_wfn_read, lowdin_host_wfn_append, lowdin_host_wfn_load_species
  *   program IntegralsTransformation, species / species-pair loop (IntegralTransformation.f90:171-355)
  *        -> lowdin_host_plan_program, lowdin_host_run_program
  *
@@ -84,6 +88,28 @@ int lowdin_host_read_ints_file(const char *path, int stack_size, int32_t *p, int
 int lowdin_host_write_moint_quads(const char *path, int stack_size, const int32_t *p, const int32_t *q, const int32_t *r,
                                   const int32_t *s, const double *v, int64_t n);
 int lowdin_host_write_moint_pairs(const char *path, int stack_size, const int64_t *ij, const int64_t *kl, const double *v, int64_t n);
+
+/* Transformer-D record layout (TransformIntegralsD.f90:221-236 intra, :447-457 inter, terminator :266 / :484; reader
+ * ReadTransformedIntegrals.f90:255-263): ONE Fortran record per integral, int32 p,q,r,s + real64 value, last record
+ * (-1,0,0,0,0.0).  `ints` is the in-place result of lowdin_it_transform_all / _inter_all (D packing).
+ * intra order: p, q<=p, r<=p, s<=(r, or q when r==p); inter order: p, q>=p, r, s>=r. */
+int lowdin_host_write_moint_d_intra(const char *path, int nao, const double *ints, int64_t *nrecords);
+int lowdin_host_write_moint_d_inter(const char *path, int nao, int onao, const double *ints, int64_t *nrecords);
+
+/* lowdin.wfn: the labelled records the transformation program reads its coefficients from (IntegralTransformation.f90:193-215;
+ * Matrix_getFromFile, Matrix.f90:697-792; Vector_getFromFile, Vector.f90:738-821; written by MultiSCF_saveWfn,
+ * MultiSCF.f90:1346-1389 with character(30) labels).  A block is four sequential unformatted records:
+ * label, species name, int64 element count, real64 values.  lowdin_host_wfn_read scans from the start of the file exactly as the
+ * reference does (first record that STARTS with `label`, accepted when the record after it equals `species`) and copies up
+ * to cap values; *n = the count stored in the file.  lowdin_host_wfn_append writes one block (label_len = declared length of the
+ * writer's labels, 30 in MultiSCF_saveWfn); truncate != 0 starts a new file. */
+int lowdin_host_wfn_read(const char *path, const char *label, const char *species, double *out, int64_t cap, int64_t *n);
+int lowdin_host_wfn_append(const char *path, const char *label, const char *species, int label_len, const double *values, int64_t n,
+                           int truncate);
+/* What the program loads per species (IntegralTransformation.f90:193-215): COEFFICIENTS as rows = nao, columns =
+ * max(nao, occupation) -- a stored count that differs is the reference's "dimensions of the matrix ... are wrong" error --
+ * and ORBITALS (nao eigenvalues; eps may be NULL).  sp->name, nao, occupation must be set; sets sp->coeff/ldc/ncols. */
+int lowdin_host_wfn_load_species(const char *path, lowdin_host_species *sp, double *coeff, double *eps);
 
 /* The transformer calls.  Read <tid><name>.ints (or <tid><A>.<B>.ints) from ctl->scratch_dir, upload, transform on the
  * GPU with the method's semantics and write <name>moint.dat (or <A>.<B>moint.dat).  For method C the caller applies the

@@ -255,6 +255,8 @@ HOST_SYMBOLS = [
     "lowdin_host_write_ints_file", "lowdin_host_read_ints_file", "lowdin_host_write_moint_quads",
     "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
     "lowdin_host_atomic_to_molecular_two_species", "lowdin_host_plan_program", "lowdin_host_run_program",
+    "lowdin_host_write_moint_d_intra", "lowdin_host_write_moint_d_inter", "lowdin_host_wfn_read", "lowdin_host_wfn_append",
+    "lowdin_host_wfn_load_species",
 ]
 
 
@@ -322,6 +324,11 @@ def _host():
     L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_plan_program.argtypes = [PC, PS, C.c_int, C.c_int, C.POINTER(HostTask), C.c_int, C.POINTER(C.c_int)]
     L.lowdin_host_run_program.argtypes = [C.c_void_p, PC, PS, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    L.lowdin_host_write_moint_d_intra.argtypes = [C.c_char_p, C.c_int, _f64p, C.POINTER(C.c_int64)]
+    L.lowdin_host_write_moint_d_inter.argtypes = [C.c_char_p, C.c_int, C.c_int, _f64p, C.POINTER(C.c_int64)]
+    L.lowdin_host_wfn_read.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.lowdin_host_wfn_append.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, _f64p, C.c_int64, C.c_int]
+    L.lowdin_host_wfn_load_species.argtypes = [C.c_char_p, PS, _f64pf, C.c_void_p]
     L._host_ready = True
     return L
 
@@ -414,3 +421,37 @@ def host_run_program(T, ctl, species, rank=0, nranks=1):
     nz, nc = C.c_int64(), C.c_int()
     _hck(_host().lowdin_host_run_program(T.h, C.byref(ctl), arr, len(species), rank, nranks, C.byref(nz), C.byref(nc)))
     return nz.value, nc.value
+
+
+def host_write_moint_d(path, ints, nao, onao=None):
+    """Transformer D's one-integral-per-record moint.dat from the in-place result of transform_all / transform_inter_all."""
+    n = C.c_int64()
+    ints = np.ascontiguousarray(ints, np.float64)
+    if onao is None:
+        _hck(_host().lowdin_host_write_moint_d_intra(path.encode(), nao, ints, C.byref(n)))
+    else:
+        _hck(_host().lowdin_host_write_moint_d_inter(path.encode(), nao, onao, ints, C.byref(n)))
+    return n.value
+
+
+def host_wfn_append(path, label, species, values, label_len=30, truncate=False):
+    v = np.ascontiguousarray(np.asarray(values, np.float64).reshape(-1, order="F"))
+    _hck(_host().lowdin_host_wfn_append(path.encode(), label.encode(), species.encode(), label_len, v, len(v), int(truncate)))
+
+
+def host_wfn_read(path, label, species):
+    n = C.c_int64()
+    _hck(_host().lowdin_host_wfn_read(path.encode(), label.encode(), species.encode(), None, 0, C.byref(n)))
+    out = np.zeros(max(n.value, 1))
+    _hck(_host().lowdin_host_wfn_read(path.encode(), label.encode(), species.encode(), out.ctypes.data, n.value, C.byref(n)))
+    return out[:n.value]
+
+
+def host_wfn_load_species(path, name, sid, nao, occ, core=0, active=0):
+    """A HostSpecies with its coefficients (and .eps) read from lowdin.wfn as the transformation program does."""
+    sp = host_species(name, sid, nao, occ, core, active)
+    coeff = np.zeros((nao, max(nao, occ)), order="F")
+    eps = np.zeros(nao)
+    _hck(_host().lowdin_host_wfn_load_species(path.encode(), C.byref(sp), coeff, eps.ctypes.data))
+    sp._keep, sp.eps = coeff, eps
+    return sp

@@ -463,6 +463,143 @@ int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin
   return run_and_write(h, ctl, a, b, nonzero);
 }
 
+// ---- transformer-D record layout ------------------------------------------------------------------------------
+namespace {
+inline int64_t index2(int64_t i, int64_t j) { return i > j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }  // ReadIntegrals.f90:175-186
+int write_d_record(FILE *f, int32_t p, int32_t q, int32_t r, int32_t s, double v) {
+  unsigned char rec[4 + 24 + 4];
+  const uint32_t len = 24;
+  memcpy(rec, &len, 4); memcpy(rec + 4, &p, 4); memcpy(rec + 8, &q, 4); memcpy(rec + 12, &r, 4); memcpy(rec + 16, &s, 4);
+  memcpy(rec + 20, &v, 8); memcpy(rec + 28, &len, 4);
+  return fwrite(rec, 1, sizeof rec, f) != sizeof rec;
+}
+}  // namespace
+
+int lowdin_host_write_moint_d_intra(const char *path, int nao, const double *ints, int64_t *nrecords) {
+  if (!path || !ints || nao < 1) return hfail("bad arguments");
+  FILE *f = fopen(path, "wb");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  int64_t cnt = 0;
+  int rc = 0;
+  for (int p = 1; p <= nao && !rc; ++p)  // TransformIntegralsD.f90:221-236
+    for (int q = 1; q <= p && !rc; ++q)
+      for (int r = 1; r <= p && !rc; ++r) {
+        const int smax = (p == r) ? q : r;
+        for (int s_ = 1; s_ <= smax && !rc; ++s_) {
+          rc = write_d_record(f, p, q, r, s_, ints[index2(index2(p - 1, q - 1), index2(r - 1, s_ - 1))]);  // ReadIntegrals_index4Intra - 1
+          ++cnt;
+        }
+      }
+  if (!rc) rc = write_d_record(f, -1, 0, 0, 0, 0.0);  // :266
+  fclose(f);
+  if (nrecords) *nrecords = cnt;
+  return rc ? hfail("short write") : 0;
+}
+
+int lowdin_host_write_moint_d_inter(const char *path, int nao, int onao, const double *ints, int64_t *nrecords) {
+  if (!path || !ints || nao < 1 || onao < 1) return hfail("bad arguments");
+  FILE *f = fopen(path, "wb");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  const int64_t osze = (int64_t)onao * (onao + 1) / 2;
+  int64_t cnt = 0;
+  int rc = 0;
+  for (int p = 1; p <= nao && !rc; ++p)  // TransformIntegralsD.f90:447-457
+    for (int q = p; q <= nao && !rc; ++q)
+      for (int r = 1; r <= onao && !rc; ++r)
+        for (int s_ = r; s_ <= onao && !rc; ++s_) {
+          rc = write_d_record(f, p, q, r, s_, ints[index2(p - 1, q - 1) * osze + index2(r - 1, s_ - 1)]);  // ReadIntegrals_index4Inter - 1
+          ++cnt;
+        }
+  if (!rc) rc = write_d_record(f, -1, 0, 0, 0, 0.0);  // :484
+  fclose(f);
+  if (nrecords) *nrecords = cnt;
+  return rc ? hfail("short write") : 0;
+}
+
+// ---- lowdin.wfn labelled records ------------------------------------------------------------------------------
+namespace {
+// One sequential unformatted record (4-byte gfortran markers).  Returns 0 ok, -1 end of file, 1 malformed.
+int read_record(FILE *f, std::vector<unsigned char> &buf) {
+  uint32_t len = 0, tail = 0;
+  if (fread(&len, 4, 1, f) != 1) return -1;
+  if (len > (1u << 31)) return 1;  // split (negative-marker) records: not produced below 2 GiB
+  buf.resize(len);
+  if (len && fread(buf.data(), 1, len, f) != len) return 1;
+  if (fread(&tail, 4, 1, f) != 1 || tail != len) return 1;
+  return 0;
+}
+std::string rtrim(const unsigned char *p, size_t n) {
+  while (n > 0 && (p[n - 1] == ' ' || p[n - 1] == 0)) --n;
+  return std::string((const char *)p, n);
+}
+}  // namespace
+
+int lowdin_host_wfn_read(const char *path, const char *label, const char *species, double *out, int64_t cap, int64_t *n) {
+  if (!path || !label || !species) return hfail("bad arguments");
+  FILE *f = fopen(path, "rb");
+  if (!f) return hfail(std::string("cannot open ") + path);
+  const std::string a1 = rtrim((const unsigned char *)label, strlen(label)), a2 = rtrim((const unsigned char *)species, strlen(species));
+  std::vector<unsigned char> rec;
+  int rc = 0;
+  bool found = false;
+  while (!found) {  // Matrix.f90:712-748
+    long at = ftell(f);
+    rc = read_record(f, rec);
+    if (rc == -1) { fclose(f); return hfail("End of file! " + a1 + " " + a2 + " not in " + path); }
+    if (rc) { fclose(f); return hfail(std::string("malformed record in ") + path); }
+    // read(unit) line(1:len_trim(arguments(1))): the first characters of the record
+    if (rtrim(rec.data(), std::min(rec.size(), a1.size())) != a1) continue;
+    fseek(f, at, SEEK_SET);  // backspace
+    for (int i = 0; i < 2; ++i) {  // every argument is read again in full; the LAST comparison decides (Matrix.f90:730-742)
+      rc = read_record(f, rec);
+      if (rc) { fclose(f); return hfail(rc == -1 ? "End of file! " + a1 + " " + a2 + " not in " + path : std::string("malformed record in ") + path); }
+      found = (rtrim(rec.data(), rec.size()) == (i == 0 ? a1 : a2));
+    }
+  }
+  int64_t total = 0;
+  rc = read_record(f, rec);
+  if (rc || rec.size() != 8) { fclose(f); return hfail("missing element count after " + a1 + " " + a2); }
+  memcpy(&total, rec.data(), 8);
+  rc = read_record(f, rec);
+  fclose(f);
+  if (rc || total < 0 || rec.size() != (size_t)total * 8) return hfail("value record of " + a1 + " " + a2 + " does not hold the stored count");
+  if (n) *n = total;
+  if (out && cap > 0) memcpy(out, rec.data(), (size_t)std::min<int64_t>(cap, total) * 8);
+  return 0;
+}
+
+int lowdin_host_wfn_append(const char *path, const char *label, const char *species, int label_len, const double *values, int64_t n,
+                           int truncate) {
+  if (!path || !label || !species || label_len < 1 || n < 0 || (n && !values)) return hfail("bad arguments");
+  if ((int)strlen(label) > label_len || (int)strlen(species) > label_len) return hfail("label longer than label_len");
+  FILE *f = fopen(path, truncate ? "wb" : "ab");
+  if (!f) return hfail(std::string("cannot create ") + path);
+  auto put_rec = [&](const void *p, size_t len) {
+    const uint32_t m = (uint32_t)len;
+    return fwrite(&m, 4, 1, f) != 1 || (len && fwrite(p, 1, len, f) != len) || fwrite(&m, 4, 1, f) != 1;
+  };
+  std::string l1(label), l2(species);
+  l1.resize(label_len, ' '); l2.resize(label_len, ' ');  // write(unit) arguments(m): the full declared length, blank padded
+  int rc = put_rec(l1.data(), l1.size()) || put_rec(l2.data(), l2.size()) || put_rec(&n, 8) || put_rec(values, (size_t)n * 8);
+  fclose(f);
+  return rc ? hfail("short write") : 0;
+}
+
+int lowdin_host_wfn_load_species(const char *path, lowdin_host_species *sp, double *coeff, double *eps) {
+  if (!sp || !coeff || sp->nao < 1) return hfail("bad arguments");
+  const std::string name = trimmed(sp->name, sizeof sp->name);
+  const int rows = sp->nao, cols = std::max(sp->nao, sp->occupation);  // IntegralTransformation.f90:200-202
+  int64_t n = 0;
+  if (lowdin_host_wfn_read(path, "COEFFICIENTS", name.c_str(), coeff, (int64_t)rows * cols, &n)) return 1;
+  if (n != (int64_t)rows * cols) return hfail("The dimensions of the matrix COEFFICIENTS " + name + " are wrong");  // Matrix.f90:753, :786
+  if (eps) {
+    if (lowdin_host_wfn_read(path, "ORBITALS", name.c_str(), eps, rows, &n)) return 1;
+    if (n != rows) return hfail("The dimensions of the vector ORBITALS " + name + " are wrong");  // Vector.f90:802, :816
+  }
+  sp->coeff = coeff; sp->ldc = rows; sp->ncols = cols;  // values(m) fills column by column (Matrix.f90:773-778): already column-major
+  return 0;
+}
+
 int lowdin_host_plan_program(const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies, int nranks,
                              lowdin_host_task *tasks, int cap, int *ntasks) {
   std::vector<lowdin_host_task> plan;

@@ -333,3 +333,94 @@ def test_run_program_apmo_shapes_file_to_file(O, T, tmp_path):
     for r in (0, 1):
         _, c = capi.host_run_program(T, ctl, sp, r, 2)
         assert c == sum(1 for t in plan if t["rank"] == r)
+
+
+# ---------------------------------------------------------------------------------------------
+# lowdin.wfn labelled records and transformer D's record layout (CPU; scipy's FortranFile is the independent reader/writer)
+# ---------------------------------------------------------------------------------------------
+def _write_wfn_like_multiscf(path, blocks, label_len=30):
+    """MultiSCF_saveWfn (MultiSCF.f90:1346-1389): write(unit) labels(1); write(unit) labels(2); write(unit) int(size,8);
+    write(unit) values -- through scipy.io.FortranFile, i.e. not through the code under test."""
+    from scipy.io import FortranFile
+    f = FortranFile(str(path), "w")
+    for label, species, values in blocks:
+        f.write_record(np.frombuffer(label.ljust(label_len).encode(), dtype="S1"))
+        f.write_record(np.frombuffer(species.ljust(label_len).encode(), dtype="S1"))
+        f.write_record(np.array([np.asarray(values).size], dtype=np.int64))
+        f.write_record(np.asarray(values, dtype=np.float64).reshape(-1, order="F"))
+    f.close()
+
+
+def test_wfn_reader_follows_matrix_get_from_file(tmp_path):
+    rng = np.random.default_rng(3)
+    Ce, Ch = rng.standard_normal((5, 5)), rng.standard_normal((4, 4))
+    ee, eh = np.sort(rng.standard_normal(5)), np.sort(rng.standard_normal(4))
+    path = tmp_path / "lowdin.wfn"
+    _write_wfn_like_multiscf(path, [
+        ("EXCHANGE-CORRELATION", "E-", np.zeros((5, 5))), ("EXCHANGE-CORRELATION-ENERGY", "E-", [0.25]),
+        ("COEFFICIENTS", "E-", Ce), ("DENSITY", "E-", Ce @ Ce.T), ("ORBITALS", "E-", ee),
+        ("COEFFICIENTS", "H_1", Ch), ("DENSITY", "H_1", Ch @ Ch.T), ("ORBITALS", "H_1", eh)])
+    assert np.array_equal(capi.host_wfn_read(str(path), "COEFFICIENTS", "E-").reshape(5, 5, order="F"), Ce)
+    assert np.array_equal(capi.host_wfn_read(str(path), "COEFFICIENTS", "H_1").reshape(4, 4, order="F"), Ch)   # skips the E- block
+    assert np.array_equal(capi.host_wfn_read(str(path), "ORBITALS", "H_1"), eh)
+    assert np.array_equal(capi.host_wfn_read(str(path), "EXCHANGE-CORRELATION-ENERGY", "E-"), [0.25])
+    # the first-record test is a PREFIX test (Matrix.f90:716-722): the matrix block is found because it comes first
+    assert capi.host_wfn_read(str(path), "EXCHANGE-CORRELATION", "E-").size == 25
+    sp = capi.host_wfn_load_species(str(path), "H_1", 2, 4, 1)
+    assert (sp.ldc, sp.ncols) == (4, 4) and np.array_equal(sp._keep, Ch) and np.array_equal(sp.eps, eh)
+    with pytest.raises(capi.LowdinITError, match="End of file"):
+        capi.host_wfn_read(str(path), "COEFFICIENTS", "POSITRON")
+    with pytest.raises(capi.LowdinITError, match="dimensions of the matrix COEFFICIENTS"):
+        capi.host_wfn_load_species(str(path), "H_1", 2, 5, 1)          # asks for 5x5, the file holds 16 values
+
+
+def test_wfn_writer_produces_gfortran_records(tmp_path):
+    from scipy.io import FortranFile
+    path = str(tmp_path / "w.wfn")
+    Cm = np.arange(12.0).reshape(3, 4)
+    capi.host_wfn_append(path, "COEFFICIENTS", "E-ALPHA", Cm, truncate=True)
+    capi.host_wfn_append(path, "ORBITALS", "E-ALPHA", [1.0, 2.0, 3.0])
+    f = FortranFile(path, "r")
+    assert f.read_record("S1").tobytes() == b"COEFFICIENTS".ljust(30)
+    assert f.read_record("S1").tobytes() == b"E-ALPHA".ljust(30)
+    assert f.read_ints(np.int64)[0] == 12
+    assert np.array_equal(f.read_reals(np.float64), Cm.reshape(-1, order="F"))     # column by column (Matrix.f90:599)
+    assert f.read_record("S1").tobytes() == b"ORBITALS".ljust(30)
+    f.close()
+    assert np.array_equal(capi.host_wfn_read(path, "ORBITALS", "E-ALPHA"), [1.0, 2.0, 3.0])
+
+
+def _read_d_records(path):
+    raw = open(path, "rb").read()
+    rec = np.frombuffer(raw, dtype=np.dtype([("h", "<u4"), ("i", "<i4", 4), ("v", "<f8"), ("t", "<u4")]))
+    assert (rec["h"] == 24).all() and (rec["t"] == 24).all()
+    return rec["i"], rec["v"]
+
+
+def test_moint_d_layout_intra_and_inter(O, tmp_path):
+    n, on = 5, 3
+    M, oM = O.npairs(n), O.npairs(on)
+    ints = np.arange(M * (M + 1) // 2, dtype=np.float64) + 0.5
+    path = str(tmp_path / "E-moint.dat")
+    cnt = capi.host_write_moint_d(path, ints, n)
+    idx, v = _read_d_records(path)
+    assert cnt == M * (M + 1) // 2 == len(v) - 1
+    assert list(idx[-1]) == [-1, 0, 0, 0] and v[-1] == 0.0                            # TransformIntegralsD.f90:266
+    want = [(p, q, r, s) for p in range(1, n + 1) for q in range(1, p + 1) for r in range(1, p + 1)
+            for s in range(1, (q if p == r else r) + 1)]                                 # :221-236
+    assert [tuple(x) for x in idx[:-1]] == want
+    L = O.lib()
+    assert all(v[k] == ints[L.orc_d_multi_index(p - 1, q - 1, r - 1, s - 1)] for k, (p, q, r, s) in enumerate(want))
+    rect = np.arange(M * oM, dtype=np.float64) - 7.0
+    path2 = str(tmp_path / "E-.H_1moint.dat")
+    cnt2 = capi.host_write_moint_d(path2, rect, n, on)
+    idx2, v2 = _read_d_records(path2)
+    assert cnt2 == M * oM == len(v2) - 1 and list(idx2[-1]) == [-1, 0, 0, 0]
+    lt = lambda i, j: max(i, j) * (max(i, j) + 1) // 2 + min(i, j)
+    k = 0
+    for p in range(1, n + 1):                                                            # :447-457
+        for q in range(p, n + 1):
+            for r in range(1, on + 1):
+                for s in range(r, on + 1):
+                    assert tuple(idx2[k]) == (p, q, r, s) and v2[k] == rect[lt(p - 1, q - 1) * oM + lt(r - 1, s - 1)]
+                    k += 1
