@@ -87,6 +87,9 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
 int lowdin_it_transform_stream(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv,
                                double drop_tol, int occ_batch, int first_pass, int n_passes,
                                const double *epsA, const double *epsB, double lambda, double sums[4]);
+/* On a communicator (lowdin_it_comm_init, nranks > 1) lowdin_it_transform_stream is COLLECTIVE: every rank makes the same
+ * call with the same arguments.  With occ_batch == 0 so is lowdin_it_stream_num_passes (the ranks agree on the batch that fits
+ * the rank with the least free memory). */
 int lowdin_it_stream_num_passes(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv,
                                 int occ_batch, int *n_passes, int *occ_batch_used);
 

@@ -60,6 +60,7 @@ struct NcclApi {
   int (*GroupEnd)() = nullptr;
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -72,7 +73,7 @@ bool load_nccl(std::string &err) {
   if (!lib) { err = "NCCL not found (dlopen libnccl.so.2)"; return false; }
 #define NSYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return false; }
   NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank") NSYM(CommDestroy, "ncclCommDestroy")
-  NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv")
+  NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv") NSYM(AllReduce, "ncclAllReduce")
   NSYM(GetErrorString, "ncclGetErrorString")
 #undef NSYM
   g_nccl.lib = lib;
@@ -91,7 +92,7 @@ struct lowdin_it_ctx {
   int up_a = -1, up_b = -1, up_swapped = 0;
   DevBuf st_p, st_q, st_r, st_s, st_v;
   // workspaces
-  DevBuf X, T1t, H, H2, OUT, T3, order, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp;
+  DevBuf X, T1t, H, H2, OUT, T3, order, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp, agree;
   // results of the last lowdin_it_transform
   DevBuf r_i0, r_i1, r_i2, r_i3, r_v;
   int64_t count = 0;
@@ -592,6 +593,21 @@ void shard_plan(int nfb, const int *fbeg, int64_t width, int G, int rank, int *o
   *c_hi = std::min<int64_t>(width, *c_lo + *wblk);
 }
 
+// Ranks size their batches from their OWN free memory, which differs by a few MB from rank to rank; everything that
+// decides the shape of the exchange (occupied batch, chunk boundaries) must be the same number everywhere, so the ranks
+// take the minimum (one 8-byte ncclAllReduce on the library's stream).  Single GPU: nothing happens.
+int agree_min(lowdin_it_handle h, int64_t *v) {
+  if (h->nranks <= 1) return 0;
+  if (!h->comm) return fail(h, "multi-GPU transform without a communicator");
+  CK(h->agree.ensure(sizeof(int64_t)));
+  CK(cudaMemcpyAsync(h->agree.p, v, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  const int rc = g_nccl.AllReduce(h->agree.p, h->agree.p, 1, /*ncclInt64*/ 4, /*ncclMin*/ 3, h->comm, h->stream);
+  if (rc != 0) return fail(h, std::string("ncclAllReduce failed: ") + g_nccl.GetErrorString(rc));
+  CK(cudaMemcpyAsync(v, h->agree.p, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 struct Consumer {
   int mode = 0;  // 0: compaction (download), 1: streaming reduce
   double tol = 1e-10;
@@ -650,6 +666,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
                    out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
     const double per_col = (double)pt.nslots * 8.0 + (G > 1 ? 2.0 * (double)nmine * 8.0 : 0.0);
     int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
+    if (agree_min(h, &max_cols)) return 1;  // same chunk boundaries on every rank (the exchange depends on them)
     if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
     if (h->chunk_cols_limit > 0) max_cols = std::min<int64_t>(max_cols, h->chunk_cols_limit);
     // chunks: rows [p0,p1) of the pair triangle, even boundaries, as many rows as fit
@@ -872,7 +889,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
   for (auto &row : h->ao) for (auto &a : row) a.data.release();
   DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
-                    &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp,
+                    &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1060,7 +1077,9 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
   const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
-  int qmax = (int)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f)));
+  int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f)));
+  if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
+  const int qmax = (int)qmax64;
   const int passes = (int)ceil_div(nf, qmax);
   int qb = (int)ceil_div(nf, passes);
   if (qb > 8 && qb < nf) { const int q8 = (qb + 7) & ~7; if (q8 <= qmax) qb = q8; }  // DMMA n-tile granularity
