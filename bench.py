@@ -283,6 +283,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--stored-nbf", type=int, default=120, help="basis size of the stored-AO end-to-end leg (0 = skip)")
+    ap.add_argument("--stored-only", action="store_true", help="run only the stored-AO end-to-end leg and print it (profiling / quick checks)")
     ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
     ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
     ap.add_argument("--gemm-variant", type=int, default=0, help="quarter-transform GEMM variant (0 = library default)")
@@ -298,6 +299,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.stored_only:
+        n_st = args.stored_nbf or 120
+        print(json.dumps({"e2e_stored_ao": stored_ao_e2e(torch, ol, capi, local, n_st, max(1, n_st * 21 // 120), max(1, args.steps))}))
+        return
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
