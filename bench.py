@@ -158,6 +158,38 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
             "same_index_lists_as_generated": same, "max_abs_diff_vs_generated": diff}
 
 
+def transformer_d_leg(ol, n_full=120):
+    """The reference's OWN transformer D (oracle/_ref/libref_d.so, compiled from IntTransfD.cpp) timed on the host cores
+    beside the drop-in lowdin_it_transform_all on the GPU: same call (coeff, ints in place, nao), same host buffers, full
+    transform of a seeded symmetric tensor at the largest of the reference's configurations (C6H6/cc-pVDZ shape, N=120).
+    Part of the cpu_baseline leg (the one place the product arm may run oracle/)."""
+    from oracle import oracle as O
+    R = O.ref()
+    if R is None:
+        return {"unavailable": "oracle/_ref/libref_d.so not built"}
+    blas = O.bind_openblas()
+    n = n_full if blas else 60                      # the 15-line dgemm_ shim is slow: smaller sample without OpenBLAS
+    M = n * (n + 1) // 2
+    eris = np.random.default_rng(n).uniform(-1.0, 1.0, M * (M + 1) // 2)
+    Cm = random_orthonormal(n, n)
+    ref = eris.copy()
+    t0 = time.perf_counter()
+    R.c_integrals_transform_all(Cm, ref, n)
+    t_ref = time.perf_counter() - t0
+    ol.transform_all(Cm, eris.copy())               # warm-up: context, allocations
+    got = eris.copy()
+    t0 = time.perf_counter()
+    ol.transform_all(Cm, got)
+    t_gpu = time.perf_counter() - t0
+    flops = 8.0 * M * float(n) ** 3                 # what transformer D executes (IntTransfD.cpp:145-178)
+    return {"workload": f"N_bf={n} full in-place transform, c_integrals_transform_all(coeff, ints, nao) semantics (IntTransfD.h:66), "
+                        f"{M * (M + 1) // 2} packed integrals in and out through host buffers",
+            "reference_ms": t_ref * 1e3, "reference_gflops": flops / t_ref / 1e9, "reference_cores": os.cpu_count() or 1,
+            "reference_blas": "OpenBLAS dgemm_ (bundled with opencv)" if blas else "naive dgemm_ shim (oracle/blas_shim.c)",
+            "gpu_ms": t_gpu * 1e3, "gpu_gflops": flops / t_gpu / 1e9, "max_abs_diff": float(np.abs(got - ref).max()),
+            "h2d_bytes": int(eris.nbytes + Cm.nbytes), "d2h_bytes": int(eris.nbytes)}
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -455,6 +487,11 @@ def main():
                                               f"AO-pair slabs, full occupied window, {dt:.1f} s"}
     T.close()
     if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:   # the reference's own C++ transformer D beside its GPU drop-in (same call, same buffers)
+                line["cpu_baseline"]["reference_transformer_d"] = transformer_d_leg(ol)
+            except Exception as e:
+                line["cpu_baseline"]["reference_transformer_d"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and args.stored_nbf > 0 and not args.no_e2e:
             # second end-to-end figure: STORED AO integrals through the whole upload -> transform -> download ABI
             try:

@@ -160,3 +160,22 @@ def test_stored_ao_e2e_leg_with_stand_in_context(O, monkeypatch):
     assert fake.calls.count("lowdin_it_ao_push_stacks") == 3 * -(-(total + 1) // 100)
     ref = O.transform_e_intra(O.random_orthonormal(n, n), O.hash_packed_intra(bench.SEED, n), bench.mp2_window_e(n, occ))
     assert np.array_equal(ref[2], fake.res[2])
+
+
+def test_transformer_d_leg_with_stand_in(O):
+    """bench.py's reference-D leg: the reference's own IntTransfD.cpp (oracle/_ref) against a stand-in for the GPU drop-in."""
+    if O.ref() is None:
+        pytest.skip("oracle/_ref not built (no reference tree)")
+    calls = []
+
+    def transform_all(Cm, ints):
+        calls.append(ints.shape)
+        O.lib().orc_transform_d_intra(np.asfortranarray(Cm), ints, Cm.shape[0])
+        return ints
+
+    out = bench.transformer_d_leg(types.SimpleNamespace(transform_all=transform_all), n_full=14)
+    n = 14 if "OpenBLAS" in out["reference_blas"] else 60
+    M = n * (n + 1) // 2
+    assert calls == [(M * (M + 1) // 2,)] * 2                    # one warm-up call, one timed call
+    assert out["max_abs_diff"] <= 1e-10 and out["reference_ms"] > 0 and out["gpu_ms"] > 0
+    assert out["d2h_bytes"] == 8 * M * (M + 1) // 2
