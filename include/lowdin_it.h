@@ -46,7 +46,7 @@ typedef struct lowdin_it_ctx *lowdin_it_handle;
 /* Replaces the per-call malloc/free of IntTransfD.cpp:131-143: device buffers live in the handle. */
 int lowdin_it_create(int device, lowdin_it_handle *out);
 int lowdin_it_destroy(lowdin_it_handle h);
-const char *lowdin_it_last_error(lowdin_it_handle h); /* h may be NULL: last create() error */
+const char *lowdin_it_last_error(lowdin_it_handle h); /* h may be NULL: last error of create() or of the handle-less transformer-D entry points */
 
 /* ---- inputs ----------------------------------------------------------------------- */
 /* Coefficients of one species into slot (0..7).  Replaces the coeff(nao,nao) copy +

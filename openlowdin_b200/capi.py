@@ -383,14 +383,15 @@ def host_write_moint_pairs(path, stack, ij, kl, v):
 
 
 def host_transform_one_species(T, ctl, a):
+    """T may be None for method D, which runs behind the handle-less transformer-D entry points."""
     n = C.c_int64()
-    _hck(_host().lowdin_host_atomic_to_molecular_one_species(T.h, C.byref(ctl), C.byref(a), C.byref(n)))
+    _hck(_host().lowdin_host_atomic_to_molecular_one_species(T.h if T is not None else None, C.byref(ctl), C.byref(a), C.byref(n)))
     return n.value
 
 
 def host_transform_two_species(T, ctl, a, b):
     n = C.c_int64()
-    _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
+    _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h if T is not None else None, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
     return n.value
 
 
@@ -419,7 +420,7 @@ def host_run_program(T, ctl, species, rank=0, nranks=1):
     """Run this rank's share of the program's calls; returns (integrals written, calls made)."""
     arr = _species_array(species)
     nz, nc = C.c_int64(), C.c_int()
-    _hck(_host().lowdin_host_run_program(T.h, C.byref(ctl), arr, len(species), rank, nranks, C.byref(nz), C.byref(nc)))
+    _hck(_host().lowdin_host_run_program(T.h if T is not None else None, C.byref(ctl), arr, len(species), rank, nranks, C.byref(nz), C.byref(nc)))
     return nz.value, nc.value
 
 

@@ -149,6 +149,18 @@ Win win_e_inter(const lowdin_host_control *c, const lowdin_host_species *a, cons
   return w;
 }
 
+// ---- transformer D: TransformIntegralsD.f90:595-700.  Printed, never used (D always transforms everything); the intra
+// table is 0-based (:606-626) and the inter table 1-based (:668-690), as in the reference. ----
+Win win_d(const lowdin_host_control *c, const lowdin_host_species *a, const lowdin_host_species *b) {
+  if (!b) {
+    const int n = a->nao, occ = a->occupation;
+    if (is(c, "MP2")) return Win{0, occ - 1, occ, n - 1, 0, occ - 1, occ, n - 1};
+    return Win{0, n - 1, 0, n - 1, 0, n - 1, 0, n - 1};
+  }
+  if (is(c, "MP2")) return Win{1, a->occupation, a->occupation + 1, a->nao, 1, b->occupation, b->occupation + 1, b->nao};
+  return Win{1, a->nao, 1, a->nao, 1, b->nao, 1, b->nao};
+}
+
 std::string join(const char *dir, const std::string &file) {
   std::string d = trimmed(dir, 512);
   if (d.empty()) return file;
@@ -158,7 +170,7 @@ std::string join(const char *dir, const std::string &file) {
 
 int check_ctl(const lowdin_host_control *c) {
   if (!c) return hfail("null control block");
-  if (c->method != 'C' && c->method != 'E') return hfail("method must be 'C' or 'E'");
+  if (c->method != 'C' && c->method != 'E' && c->method != 'D') return hfail("method must be 'C', 'D' or 'E'");
   if (c->integral_stack_size < 1) return hfail("integral_stack_size < 1");
   if (c->nfiles < 1) return hfail("nfiles < 1");
   return 0;
@@ -216,9 +228,54 @@ int load_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_h
   return 0;
 }
 
+// Method D, file to file (TransformIntegralsD.f90:141-273 intra, :370-490 inter): ReadIntegrals_* scatter the .ints streams into
+// D's packed array on the HOST (ReadIntegrals.f90:23-99, :102-172), the transform runs in place behind the
+// c_integrals_transform_all signature, one record per integral is written.
+inline int64_t d_index2(int64_t i, int64_t j) { return i > j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+int run_and_write_d(const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b, int64_t *nonzero) {
+  if (!a || !a->coeff || (b && !b->coeff)) return hfail("null species / coefficients");
+  const int nao = a->nao, onao = b ? b->nao : 0;
+  if (a->ncols < nao || (b && b->ncols < onao)) return hfail("method D needs the square coefficient matrix");
+  const int64_t sze = (int64_t)nao * (nao + 1) / 2, osze = (int64_t)onao * (onao + 1) / 2;
+  std::vector<double> ints((size_t)(b ? sze * osze : sze * (sze + 1) / 2), 0.0);
+  const std::string na = trimmed(a->name, 32), nb = b ? trimmed(b->name, 32) : std::string();
+  const std::string stem = b ? na + "." + nb : (na == "E-BETA" ? std::string("E-ALPHA") : na);  // ReadIntegrals.f90:64-68; no alias for pairs (:136)
+  for (int tid = 0; tid < ctl->nfiles; ++tid) {
+    bool bad = false;
+    int rc = for_each_stack(join(ctl->scratch_dir, std::to_string(tid) + stem + ".ints"), ctl->integral_stack_size,
+                            [&](const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s, const double *v, int n) {
+                              for (int i = 0; i < n; ++i) {
+                                if (p[i] == -1) break;
+                                const int lim2 = b ? onao : nao;
+                                if (p[i] < 1 || q[i] < 1 || r[i] < 1 || s[i] < 1 || p[i] > nao || q[i] > nao || r[i] > lim2 || s[i] > lim2) { bad = true; return 1; }
+                                const int64_t ij = d_index2(p[i] - 1, q[i] - 1), kl = d_index2(r[i] - 1, s[i] - 1);
+                                ints[(size_t)(b ? ij * osze + kl : d_index2(ij, kl))] = v[i];  // ReadIntegrals_index4Inter / index4Intra, 0-based
+                              }
+                              return 0;
+                            });
+    if (bad) return hfail("AO stack entry with an index outside the basis");
+    if (rc) return rc;
+  }
+  // coeff(j,k) = coefficients%values(j,k), j,k <= nao (TransformIntegralsD.f90:189-196)
+  std::vector<double> ca((size_t)nao * nao), cb((size_t)onao * onao);
+  for (int k = 0; k < nao; ++k) memcpy(&ca[(size_t)k * nao], a->coeff + (size_t)k * a->ldc, sizeof(double) * nao);
+  for (int k = 0; k < onao; ++k) memcpy(&cb[(size_t)k * onao], b->coeff + (size_t)k * b->ldc, sizeof(double) * onao);
+  if (b ? lowdin_it_transform_inter_all(ca.data(), cb.data(), ints.data(), nao, onao) : lowdin_it_transform_all(ca.data(), ints.data(), nao))
+    return hfail(std::string("transformer-D entry point failed: ") + lowdin_it_last_error(nullptr));
+  const std::string path = join(ctl->scratch_dir, (b ? na + "." + nb : na) + "moint.dat");
+  int64_t n = 0;
+  if (b ? lowdin_host_write_moint_d_inter(path.c_str(), nao, onao, ints.data(), &n) : lowdin_host_write_moint_d_intra(path.c_str(), nao, ints.data(), &n))
+    return 1;
+  if (ctl->verbose) printf(" Non zero transformed repulsion integrals: %lld\n", (long long)n);  // D.f90:269
+  if (nonzero) *nonzero = n;
+  return 0;
+}
+
 int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b,
                   int64_t *nonzero) {
   if (check_ctl(ctl)) return 1;
+  if (ctl->method == 'D') return run_and_write_d(ctl, a, b, nonzero);
   if (!h || !a || !a->coeff) return hfail("null handle / species");
   int win[8], symmetric = 0;
   if (lowdin_host_windows(ctl, a, b, win, &symmetric)) return 1;
@@ -258,8 +315,10 @@ int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowd
 double call_flops(const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b, const int win[8],
                   int symmetric) {
   const lowdin_host_species *sb = b ? b : a;
-  auto cnt = [&](int w) { return (double)std::max(0, win[2 * w + 1] - win[2 * w] + 1); };
   const double Na = a->nao, Nb = sb->nao, Mb = Nb * (Nb + 1) / 2;
+  if (ctl->method == 'D')  // two similarity transforms per pair vector, whatever the printed windows say: 8 M N^3 intra (IntTransfD.cpp:145-178)
+    return 4.0 * Na * Na * Na * Mb + 4.0 * Nb * Nb * Nb * (Na * (Na + 1) / 2);
+  auto cnt = [&](int w) { return (double)std::max(0, win[2 * w + 1] - win[2 * w] + 1); };
   const double nf1 = std::min(cnt(0), cnt(1)), ns1 = std::max(cnt(0), cnt(1));
   const double nf2 = std::min(cnt(2), cnt(3)), ns2 = std::max(cnt(2), cnt(3));
   double npairs = 0;  // first pairs entering the second half: E keeps q<=p (E.f90:878-884), C skips q<p when symmetric (C.f90:380)
@@ -340,6 +399,7 @@ int lowdin_host_windows(const lowdin_host_control *ctl, const lowdin_host_specie
   int sym = 1;
   Win w;
   if (ctl->method == 'C') w = b ? win_c_inter(ctl, a, b, &sym) : win_c_intra(ctl, a, &sym);
+  else if (ctl->method == 'D') { w = win_d(ctl, a, b); sym = 0; }
   else { w = b ? win_e_inter(ctl, a, b) : win_e_intra(ctl, a); sym = 0; }
   put(w, win);
   if (symmetric) *symmetric = sym;

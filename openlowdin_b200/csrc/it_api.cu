@@ -898,7 +898,12 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   return 0;
 }
 
-const char *lowdin_it_last_error(lowdin_it_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+const char *lowdin_it_last_error(lowdin_it_handle h) {
+  if (h) return h->err.c_str();
+  // no handle: the handle-less entry points (lowdin_it_create, lowdin_it_transform_all / _inter_all)
+  if (g_create_error.empty() && g_dcompat && !g_dcompat->err.empty()) return g_dcompat->err.c_str();
+  return g_create_error.c_str();
+}
 
 int lowdin_it_set_species(lowdin_it_handle h, int slot, int nao, const double *C, int ldc, int ncols) {
   if (!h) return 1;
@@ -1170,7 +1175,8 @@ int lowdin_it_timers(lowdin_it_handle h, double out[8]) {
 
 // ---- transformer-D compatible entry points --------------------------------------------------
 static int dcompat_ctx() {
-  if (g_dcompat) return 0;
+  g_create_error.clear();
+  if (g_dcompat) { g_dcompat->err.clear(); return 0; }
   return lowdin_it_create(0, &g_dcompat);
 }
 

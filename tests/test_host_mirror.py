@@ -424,3 +424,79 @@ def test_moint_d_layout_intra_and_inter(O, tmp_path):
                 for s in range(r, on + 1):
                     assert tuple(idx2[k]) == (p, q, r, s) and v2[k] == rect[lt(p - 1, q - 1) * oM + lt(r - 1, s - 1)]
                     k += 1
+
+
+# ---------------------------------------------------------------------------------------------
+# method D through the host mirror
+# ---------------------------------------------------------------------------------------------
+def test_method_d_window_tables_and_plan():
+    e = capi.host_species("E-", 1, 19, 5)
+    h = capi.host_species("H_1", 2, 50, 1)
+    # TransformIntegralsD.f90:606-626: the intra table is 0-based; :668-690: the inter table is 1-based
+    assert capi.host_windows(capi.host_control("D", "MP2"), e) == ([0, 4, 5, 18, 0, 4, 5, 18], False)
+    assert capi.host_windows(capi.host_control("D", "ALL"), e) == ([0, 18, 0, 18, 0, 18, 0, 18], False)
+    assert capi.host_windows(capi.host_control("D", "MP2"), e, h) == ([1, 5, 6, 19, 1, 1, 2, 50], False)
+    assert capi.host_windows(capi.host_control("D", "BOUNDS"), e, h) == ([1, 19, 1, 19, 1, 50, 1, 50], False)
+    plan = capi.host_plan_program(capi.host_control("D", "MP2"), [e, h])
+    assert [(t["first"], t["second"]) for t in plan] == [(0, None), (0, 1), (1, None)]
+    # D transforms everything whatever the windows say: 8 M N^3 (SURVEY.md 8d, F_full)
+    assert plan[0]["flops"] == 8.0 * 190 * 19 ** 3 and plan[2]["flops"] == 8.0 * 1275 * 50 ** 3
+
+
+def test_method_d_without_gpu_fails_loudly(O, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    n = 5
+    capi.host_write_ints_file(str(tmp_path / "0E-.ints"), 16, *O.canonical_list_intra(O.hash_packed_intra(1, n), n))
+    sp = capi.host_species("E-", 1, n, 2, coeff=O.random_orthonormal(n, 3))
+    with pytest.raises(capi.LowdinITError, match="no CUDA device"):
+        capi.host_transform_one_species(None, capi.host_control("D", "ALL", stack=16, scratch_dir=str(tmp_path)), sp)
+
+
+def _read_d_file(path):
+    raw = open(path, "rb").read()
+    rec = np.frombuffer(raw, dtype=np.dtype([("h", "<u4"), ("i", "<i4", 4), ("v", "<f8"), ("t", "<u4")]))
+    assert (rec["h"] == 24).all() and (rec["t"] == 24).all() and rec["i"][-1][0] == -1
+    return rec["i"][:-1], rec["v"][:-1]
+
+
+@pytest.mark.gpu
+def test_method_d_file_to_file(O, tmp_path):
+    """.ints streams -> ReadIntegrals packing on the host -> lowdin_it_transform_all / _inter_all -> D's record file, against the
+    reference's own transformer D (oracle/_ref) on the same packed array."""
+    n, on, S = 9, 6, 32
+    M, oM = O.npairs(n), O.npairs(on)
+    Ca, Cb = O.random_orthonormal(n, 5), O.random_orthonormal(on, 6)
+    packed = O.hash_packed_intra(41, n)
+    lst = O.canonical_list_intra(packed, n)
+    _split_to_files(tmp_path, "E-", lst, 2, S)
+    rect = O.hash_rect_inter(42, n, on)
+    lsti = O.canonical_list_inter(rect, n, on)
+    _split_to_files(tmp_path, "E-.H_1", lsti, 2, S)
+    ctl = capi.host_control("D", "ALL", stack=S, nfiles=2, scratch_dir=str(tmp_path))
+    A, B = capi.host_species("E-", 1, n, 3, coeff=Ca), capi.host_species("H_1", 2, on, 1, coeff=Cb)
+    use_ref = O.ref() is not None
+    lt = lambda i, j: np.maximum(i, j) * (np.maximum(i, j) + 1) // 2 + np.minimum(i, j)
+    # intra
+    cnt = capi.host_transform_one_species(None, ctl, A)
+    assert cnt == M * (M + 1) // 2
+    eris = np.zeros(M * (M + 1) // 2)
+    p, q, r, s, v = [np.asarray(x) for x in lst]
+    eris[lt(lt(p - 1, q - 1), lt(r - 1, s - 1))] = v                  # ReadIntegrals_index4Intra
+    want = O.transform_d_intra(Ca, eris, use_reference=use_ref)
+    idx, val = _read_d_file(str(tmp_path / "E-moint.dat"))
+    got = np.zeros_like(want)
+    got[lt(lt(idx[:, 0] - 1, idx[:, 1] - 1), lt(idx[:, 2] - 1, idx[:, 3] - 1))] = val
+    assert np.abs(got - want).max() <= 1e-10
+    # inter
+    cnt = capi.host_transform_two_species(None, ctl, A, B)
+    assert cnt == M * oM
+    er = np.zeros(M * oM)
+    p, q, r, s, v = [np.asarray(x) for x in lsti]
+    er[lt(p - 1, q - 1) * oM + lt(r - 1, s - 1)] = v                   # ReadIntegrals_index4Inter
+    want = O.transform_d_inter(Ca, Cb, er, use_reference=use_ref)
+    idx, val = _read_d_file(str(tmp_path / "E-.H_1moint.dat"))
+    got = np.zeros_like(want)
+    got[lt(idx[:, 0] - 1, idx[:, 1] - 1) * oM + lt(idx[:, 2] - 1, idx[:, 3] - 1)] = val
+    assert np.abs(got - want).max() <= 1e-10
