@@ -15,6 +15,65 @@ from openlowdin_b200 import capi  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
+def species_pairs_across_ranks(rank, world, local, dev):
+    """SURVEY 8e, "species pairs are scheduled across devices": the calls of the program's species loop are divided among
+    the ranks (lowdin_host_run_program, no communicator); every moint.dat is then checked against the oracle by rank 0."""
+    import tempfile
+    shapes = [("E-", 7, 3), ("H-A_1", 5, 1), ("H-B_1", 4, 1)]
+    S = 40
+    d = [tempfile.mkdtemp(prefix="lowdin_it_mgpu_") if rank == 0 else None]
+    dist.broadcast_object_list(d, src=0)
+    d = d[0]
+    Cs = [O.random_orthonormal(n, 31 + i) for i, (_, n, _) in enumerate(shapes)]
+    intra = {i: O.hash_packed_intra(100 + i, n) for i, (_, n, _) in enumerate(shapes)}
+    inter = {(i, j): O.hash_rect_inter(200 + 10 * i + j, shapes[i][1], shapes[j][1]) for i in range(3) for j in range(i + 1, 3)}
+    if rank == 0:
+        for i, (nm, n, _) in enumerate(shapes):
+            capi.host_write_ints_file(os.path.join(d, f"0{nm}.ints"), S, *O.canonical_list_intra(intra[i], n))
+            for j in range(i + 1, 3):
+                capi.host_write_ints_file(os.path.join(d, f"0{nm}.{shapes[j][0]}.ints"), S, *O.canonical_list_inter(inter[i, j], n, shapes[j][1]))
+    dist.barrier()
+    sp = [capi.host_species(nm, i + 1, n, occ, coeff=Cs[i]) for i, (nm, n, occ) in enumerate(shapes)]
+    ctl = capi.host_control("E", "MP2", stack=S, nfiles=1, scratch_dir=d)
+    T2 = ol.Transformer(local)
+    written, calls = capi.host_run_program(T2, ctl, sp, rank, world)
+    T2.close()
+    tot = torch.tensor([float(written), float(calls)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot)
+    dist.barrier()
+    good = True
+    if rank == 0:
+        import struct
+
+        def read_pairs(path):  # E record layout: int64 ij[S], kl[S], real64 v[S] per record, terminator ij = -1
+            raw = open(path, "rb").read()
+            ij, kl, v, o = [], [], [], 0
+            while o < len(raw):
+                (ln,) = struct.unpack_from("<I", raw, o)
+                a = np.frombuffer(raw, np.int64, S, o + 4); b = np.frombuffer(raw, np.int64, S, o + 4 + 8 * S)
+                c = np.frombuffer(raw, np.float64, S, o + 4 + 16 * S)
+                m = int(np.argmax(a == -1)) if (a == -1).any() else S
+                ij.append(a[:m]); kl.append(b[:m]); v.append(c[:m])
+                o += ln + 8
+            return np.concatenate(ij), np.concatenate(kl), np.concatenate(v)
+        count = 0
+        for i, (nm, n, occ) in enumerate(shapes):
+            M = O.npairs(n)
+            ref = O.transform_e_intra(Cs[i], intra[i], O.windows_e_intra("MP2", n, occ))
+            got = read_pairs(os.path.join(d, f"{nm}moint.dat"))
+            good = good and np.abs(O.pairs_to_dense(*got, M, M) - O.pairs_to_dense(*ref, M, M)).max() <= 1e-10
+            count += len(got[2])
+            for j in range(i + 1, 3):
+                nm2, n2, occ2 = shapes[j]
+                ref = O.transform_e_inter(Cs[i], Cs[j], inter[i, j], O.windows_e_inter("MP2", n, n2, occ, occ2))
+                got = read_pairs(os.path.join(d, f"{nm}.{nm2}moint.dat"))
+                good = good and np.abs(O.pairs_to_dense(*got, M, O.npairs(n2)) - O.pairs_to_dense(*ref, M, O.npairs(n2))).max() <= 1e-10
+                count += len(got[2])
+        good = bool(good) and count == int(tot[0].item()) and int(tot[1].item()) == 6
+        print(f"species pairs across {world} ranks: 6 calls, {count} integrals written -> {'ok' if good else 'MISMATCH'}", flush=True)
+    return good
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -61,6 +120,7 @@ def main():
                 print(f"{kind} n={n} chunk_cols={cols} occ_batch={qb}: got {got} want {want} -> {'ok' if good else 'MISMATCH'}", flush=True)
     T.set_option(T.OPT_CHUNK_COLS, 0)
     T.close()
+    ok = species_pairs_across_ranks(rank, world, local, dev) and ok
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_CHECK_OK" if ok else "MGPU_CHECK_FAILED", flush=True)
