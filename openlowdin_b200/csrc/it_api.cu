@@ -664,7 +664,9 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     out_need = std::max(out_need, (double)pl.max_slots_per_f * per_out * 8.0);
     double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->OUT.cap + (double)h->X.cap + (double)h->T1t.cap) -
                    out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
-    const double per_col = (double)pt.nslots * 8.0 + (G > 1 ? 2.0 * (double)nmine * 8.0 : 0.0);
+    // bytes per chunk column: one rank holds H[all slots][its 1/G of the columns] and, after the exchange, H2[its slots][all
+    // columns] (counted twice: headroom for NCCL's own buffers) -- the same 3/G of a full column pick_occ_batch assumes
+    const double per_col = (G > 1) ? (double)pt.nslots * 8.0 / G + 2.0 * (double)nmine * 8.0 : (double)pt.nslots * 8.0;
     int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
     if (agree_min(h, &max_cols)) return 1;  // same chunk boundaries on every rank (the exchange depends on them)
     if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
