@@ -63,3 +63,22 @@ def test_product_does_not_import_the_oracle():
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
             src = open(path).read()
             assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, path
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both headers compile as C99 with a C compiler (no C++ types, no torch), and a C program
+    that references every declared function links against the library."""
+    syms = declared_symbols()
+    src = tmp_path / "abi_check.c"
+    body = "\n".join(f"  p[{i}] = (fn)&{s};" for i, s in enumerate(syms))
+    src.write_text('#include "lowdin_it.h"\n#include "lowdin_it_host.h"\n#include <stdio.h>\n'
+                   f"typedef void (*fn)(void);\nint main(void) {{\n  fn p[{len(syms)}];\n{body}\n  printf(\"%d\\n\", (int)(sizeof p / sizeof p[0]));\n  return p[0] == 0;\n}}\n")
+    from openlowdin_b200 import capi
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(capi.lib_path())
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-llowdin_itgpu", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and int(r.stdout) == len(syms)
