@@ -402,7 +402,8 @@ def main():
     # Every step re-uploads what a caller of this size owns on the host (coefficients from pinned memory, orbital
     # energies) and reads the reduced result back; the 5 TB AO tensor of N=1500 cannot exist on a host, so its values
     # stay a pure function of the canonical index evaluated where they are consumed.
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
+    # the same passes as the timed region above, at most one whole transform (npass passes)
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, npass))
     pinned = torch.from_numpy(np.ascontiguousarray(Cm.T)).pin_memory()  # column-major C(mu,p) == row-major C^T
     Cpin = pinned.numpy().T
     barrier()
