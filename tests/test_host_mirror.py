@@ -14,6 +14,38 @@ from helpers import assert_lists_match, dense_pairs, dense_quads
 MODES = ["MP2", "PT2", "MP2-PT2", "ALL", "ALLACTIVE", "BOUNDS"]
 
 
+class _MockContext:
+    """A handle of tests/mock/libmock_host.so: the host mirror (product source, unchanged) linked against a CPU stand-in of the
+    device library that answers with the oracle.  Exercises the mirror's orchestration on CPU; the CUDA path is the `gpu` param."""
+
+    def __init__(self, L):
+        import ctypes as C
+        self.L, self.h = L, C.c_void_p()
+        L.lowdin_it_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.lowdin_it_destroy.argtypes = [C.c_void_p]
+        assert L.lowdin_it_create(0, C.byref(self.h)) == 0
+
+    def close(self):
+        self.L.lowdin_it_destroy(self.h)
+
+
+@pytest.fixture(params=["cpu_mock", pytest.param("gpu", marks=pytest.mark.gpu)])
+def HT(request, monkeypatch):
+    """The device context the file-to-file tests run on: the real CUDA library (-m gpu) or the CPU mock (-m "not gpu")."""
+    if request.param == "gpu":
+        yield request.getfixturevalue("T")
+        return
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "mock"))
+    import build_mock
+    L = build_mock.load()
+    monkeypatch.setattr(capi, "_lib", L)          # every capi.host_* call of the test goes to the mock-linked mirror
+    ctx = _MockContext(L)
+    yield ctx
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # integer host logic (CPU)
 # ---------------------------------------------------------------------------------------------
@@ -161,9 +193,9 @@ def _split_to_files(tmp_path, name, lst, nfiles, S):
         capi.host_write_ints_file(str(tmp_path / f"{t}{name}.ints"), S, *part)
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("method,mode", [("C", "MP2"), ("C", "ALL"), ("C", "PT2"), ("E", "MP2"), ("E", "MP2-PT2")])
-def test_one_species_file_to_file(O, T, tmp_path, method, mode):
+def test_one_species_file_to_file(O, HT, tmp_path, method, mode):
+    T = HT
     n, occ, S, nfiles = 13, 4, 64, 3
     packed = O.hash_packed_intra(61, n)
     Cm = O.random_orthonormal(n, n)
@@ -195,9 +227,9 @@ def test_one_species_file_to_file(O, T, tmp_path, method, mode):
         assert abs(e_got - e_ref) <= 1e-9          # downstream energy read back from the file
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("method", ["C", "E"])
-def test_two_species_file_to_file_both_call_orders(O, T, tmp_path, method):
+def test_two_species_file_to_file_both_call_orders(O, HT, tmp_path, method):
+    T = HT
     na, nb, oa, ob, S = 9, 7, 3, 1, 50
     rect = O.hash_rect_inter(17, na, nb)                       # stored (rs_B, pq_A)
     Ca, Cb = O.random_orthonormal(na, 5), O.random_orthonormal(nb, 6)
@@ -296,8 +328,8 @@ def test_program_plan_errors():
         capi.host_plan_program(capi.host_control("X", "MP2"), sp, 1)
 
 
-@pytest.mark.gpu
-def test_run_program_apmo_shapes_file_to_file(O, T, tmp_path):
+def test_run_program_apmo_shapes_file_to_file(O, HT, tmp_path):
+    T = HT
     """Three species (small stand-ins of the H2O.APMO layout), method E, MP2: the whole species loop through
     lowdin_host_run_program, every moint.dat against the oracle."""
     shapes = [("E-", 7, 3), ("H-A_1", 5, 1), ("H-B_1", 4, 1)]
@@ -461,8 +493,7 @@ def _read_d_file(path):
     return rec["i"][:-1], rec["v"][:-1]
 
 
-@pytest.mark.gpu
-def test_method_d_file_to_file(O, tmp_path):
+def test_method_d_file_to_file(O, HT, tmp_path):
     """.ints streams -> ReadIntegrals packing on the host -> lowdin_it_transform_all / _inter_all -> D's record file, against the
     reference's own transformer D (oracle/_ref) on the same packed array."""
     n, on, S = 9, 6, 32
