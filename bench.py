@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
     ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
     ap.add_argument("--gemm-variant", type=int, default=0, help="quarter-transform GEMM variant (0 = library default)")
+    ap.add_argument("--frag-perm", type=int, default=0, help="1 = conflict-free fragment-row permutation of the TMA kernels (experimental)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -362,6 +363,8 @@ def main():
         T.set_option(T.OPT_Q1_VARIANT, args.q1_variant)
     if args.gemm_variant:
         T.set_option(T.OPT_GEMM_VARIANT, args.gemm_variant)
+    if args.frag_perm:
+        T.set_option(T.OPT_FRAG_PERM, 1)
     T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 

@@ -120,6 +120,7 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
 #define LOWDIN_IT_OPT_BENCH_GEN 4       /* generator kind used by lowdin_it_kernel_bench kind 2 */
 #define LOWDIN_IT_OPT_GEMM_VARIANT 5    /* quarter-transform GEMM: 1 = cp.async ring + block barrier, 2 = TMA + mbarrier, persistent */
 #define LOWDIN_IT_OPT_SPLIT_ROW_TAIL 6  /* TMA GEMM: 1 (default) = the <= 80-row tail of a few-rows x many-columns product runs as a second, operand-swapped launch instead of a padded 128-row tile */
+#define LOWDIN_IT_OPT_FRAG_PERM 7       /* TMA kernels: 1 = fragment rows permuted so that the 128-bit shared loads of a quarter-warp are conflict-free (default 0 until measured on a GPU) */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 
 /* ---- instrumentation -------------------------------------------------------------- */

@@ -175,7 +175,7 @@ class Transformer:
 
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
-    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL = 1, 2, 3, 4, 5, 6
+    OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT = 3, 2  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):

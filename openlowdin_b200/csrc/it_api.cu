@@ -108,6 +108,7 @@ struct lowdin_it_ctx {
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
+  int frag_perm = 0;                         // TMA kernels: 1 = conflict-free fragment-row permutation (it_gemm_tma.cuh, frag_row); not yet validated on a GPU
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
@@ -218,12 +219,13 @@ cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi
   constexpr int ST = ST_RAW > 8 ? 8 : ST_RAW;
   constexpr size_t smem = tma_gemm_smem_bytes<BM, BN, ST>(staged ? WM * WN : 0, TNW);
   static_assert(smem <= 232448, "shared memory per CTA");
-  auto kern = dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi>;
-  static bool configured = false;
-  if (!configured) {
+  const int perm = h->frag_perm ? 1 : 0;
+  auto kern = perm ? dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, true> : dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[perm]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[perm] = true;
   }
   CUtensorMap mapA, mapB;
   if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda, BM) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, BN)) return cudaErrorInvalidValue;
@@ -441,12 +443,15 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
   constexpr int ST = 6;
   constexpr size_t smem = q1_ws_smem_bytes<TN, ST>();
   const bool v4 = (h->q1_variant == 4);  // 8 DMMA warps with register double-buffering + 4 vectorised generator warps
-  auto kern = v4 ? q1_gen_ws2_kernel<TN, ST, KIND, GEN> : q1_gen_ws_kernel<TN, ST, KIND, GEN>;
-  static bool configured[2] = {false, false};
-  if (!configured[v4]) {
+  const bool perm = h->frag_perm != 0;
+  auto kern = v4 ? (perm ? q1_gen_ws2_kernel<TN, ST, KIND, GEN, true> : q1_gen_ws2_kernel<TN, ST, KIND, GEN, false>)
+                 : (perm ? q1_gen_ws_kernel<TN, ST, KIND, GEN, true> : q1_gen_ws_kernel<TN, ST, KIND, GEN, false>);
+  static bool configured[4] = {false, false, false, false};
+  const int ci = (v4 ? 2 : 0) + (perm ? 1 : 0);
+  if (!configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[v4] = true;
+    configured[ci] = true;
   }
   CUtensorMap mapB;
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
@@ -1149,6 +1154,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->gemm_variant = (int)value; return 0;
     case LOWDIN_IT_OPT_SPLIT_ROW_TAIL:
       h->split_row_tail = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_FRAG_PERM:
+      h->frag_perm = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_BENCH_GEN:
       if (value != 1 && value != 2) return fail(h, "generator kind must be 1 or 2");
       h->bench_gen = (int)value; return 0;

@@ -75,6 +75,23 @@ struct TmaGemmShape {
   int M, N, K;
 };
 
+// Fragment-row permutation (PERM template parameter of the kernels below; LOWDIN_IT_OPT_FRAG_PERM).
+// A 128-bit shared load is served one quarter-warp (8 lanes, 128 bytes) per cycle.  With lane (grp,tig) on row grp of an 8-row
+// group, the lanes of quarter-warp p sit on rows 2p and 2p+1; under the 128-byte swizzle (chunk ^= row & 7) both rows put
+// their four chunks into the SAME half of the 128-byte line, i.e. every quarter-warp has a 2-way bank conflict and every
+// fragment load takes 8 wavefronts instead of 4 (ncu: 50 % excessive shared wavefronts, profiles/r01e_ncu_full_q1ws_n1500).
+// rho(grp) = (grp >> 1) | ((grp & 1) << 2) puts the two lane groups of a quarter-warp on rows p and p + 4, whose swizzle keys
+// differ in bit 2: their chunks fall into different halves of the line and the conflict is gone.  The MMA then computes the
+// 8x8 tile with its rows AND columns permuted by rho: accumulator element [0]/[1] of lane (grp,tig) is output element
+// (m = rho(grp), n = rho(2 tig) = tig / rho(2 tig + 1) = tig + 4) instead of (grp, 2 tig / 2 tig + 1); the epilogues index
+// accordingly.  Shared-memory contents, TMA maps and the k order are unchanged, so results are bit-identical.
+template <bool PERM>
+__device__ __forceinline__ int frag_row(int grp) { return PERM ? ((grp >> 1) | ((grp & 1) << 2)) : grp; }
+template <bool PERM>
+__device__ __forceinline__ int frag_col0(int tig) { return PERM ? tig : 2 * tig; }      // column of accumulator element [0]
+template <bool PERM>
+__device__ __forceinline__ int frag_col1(int tig) { return PERM ? tig + 4 : 2 * tig + 1; }  // column of accumulator element [1]
+
 constexpr int TMA_STAGE_LDM = 34;  // staged epilogue: [n][34] doubles per warp (32 rows + padding)
 template <int BM, int BN, int STAGES>
 constexpr size_t tma_gemm_smem_bytes(int warps = 0, int tn = 0) {
@@ -82,7 +99,7 @@ constexpr size_t tma_gemm_smem_bytes(int warps = 0, int tn = 0) {
   return (size_t)STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024 + (size_t)warps * tn * 8 * TMA_STAGE_LDM * 8;
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, class Epi>
+template <int BM, int BN, int WM, int WN, int STAGES, class Epi, bool PERM = false>
 __global__ void __launch_bounds__(WM *WN * 32, 1)
     dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaGemmShape g, Epi epi) {
   constexpr int BK = 16;
@@ -137,7 +154,8 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
     for (; prod_it < total_it && prod_it < (uint32_t)STAGES; ++prod_it) issue(prod_it);  // fresh slots
 
   const int wm = warp / WN, wn = warp % WN;
-  const int grp = lane >> 2, tig = lane & 3;
+  const int tig = lane & 3;
+  const int grp = frag_row<PERM>(lane >> 2);           // row of the 8-row group this lane's fragments come from
   const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk of k-half 0; half 1 is off0 ^ 64
   const uint8_t *a_base = ring + (wm * TM * 8 + grp) * 128;
   const uint8_t *b_base = ring + A_BYTES + (wn * TN * 8 + grp) * 128;
@@ -202,8 +220,13 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          st[(j * 8 + tig * 2) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][0];
-          st[(j * 8 + tig * 2 + 1) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][1];
+          if constexpr (PERM) {
+            st[(j * 8 + tig) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][0];
+            st[(j * 8 + tig + 4) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][1];
+          } else {
+            st[(j * 8 + tig * 2) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][0];
+            st[(j * 8 + tig * 2 + 1) * TMA_STAGE_LDM + i * 8 + grp] = acc[i][j][1];
+          }
         }
       __syncwarp();
       const int m = m0 + wm * 32 + lane;
@@ -228,9 +251,15 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
         if (m >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
-          if (n < g.N) epi(0, m, n, acc[i][j][0]);
-          if (n + 1 < g.N) epi(0, m, n + 1, acc[i][j][1]);
+          if constexpr (PERM) {
+            const int n = n0 + wn * TN * 8 + j * 8 + tig;
+            if (n < g.N) epi(0, m, n, acc[i][j][0]);
+            if (n + 4 < g.N) epi(0, m, n + 4, acc[i][j][1]);
+          } else {
+            const int n = n0 + wn * TN * 8 + j * 8 + tig * 2;
+            if (n < g.N) epi(0, m, n, acc[i][j][0]);
+            if (n + 1 < g.N) epi(0, m, n + 1, acc[i][j][1]);
+          }
         }
       }
     }
@@ -293,7 +322,7 @@ constexpr size_t q1_ws_smem_bytes() {
   return (size_t)STAGES * (128 + TN * 8) * 128 + 2 * STAGES * 8 + 1024;
 }
 
-template <int TN, int STAGES, int KIND, int GEN>
+template <int TN, int STAGES, int KIND, int GEN, bool PERM = false>
 __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant__ CUtensorMap mapB, Q1WsArgs q) {
   constexpr int BK = 16, BM = 128, BN = TN * 8;
   constexpr int NCW = 8, NGW = 8;  // consumer / generator warps
@@ -304,7 +333,8 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
   const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = lane >> 2, tig = lane & 3;
+  const int tig = lane & 3;
+  const int grp = frag_row<PERM>(lane >> 2);  // generators WRITE and consumers READ row grp of each 8-row group (see frag_row)
   const int KT = (q.nc + BK - 1) / BK;
   const int row_blocks = (q.nc + BM - 1) / BM;
   const int ntiles = row_blocks * q.bc;
@@ -407,9 +437,15 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
       if (m >= q.nc) continue;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        const int f = j * 8 + tig * 2;
-        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
-        if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        if constexpr (PERM) {
+          const int f = j * 8 + tig;
+          if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+          if (f + 4 < q.nfb) q.T1t[((int64_t)(f + 4) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        } else {
+          const int f = j * 8 + tig * 2;
+          if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+          if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        }
       }
     }
   }
@@ -446,7 +482,7 @@ __device__ __forceinline__ void hash8(uint64_t (&x)[8]) {
   }
 }
 
-template <int TN, int STAGES, int KIND, int GEN>
+template <int TN, int STAGES, int KIND, int GEN, bool PERM = false>
 __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constant__ CUtensorMap mapB, Q1WsArgs q) {
   constexpr int BK = 16, BM = 128, BN = TN * 8;
   constexpr int NCW = 8, NGW = 4;  // DMMA warps (16 rows each) / generator warps (32 rows each)
@@ -457,7 +493,8 @@ __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constan
   const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = lane >> 2, tig = lane & 3;
+  const int tig = lane & 3;
+  const int grp = frag_row<PERM>(lane >> 2);
   const int KT = (q.nc + BK - 1) / BK;
   const int row_blocks = (q.nc + BM - 1) / BM;
   const int ntiles = row_blocks * q.bc;
@@ -596,9 +633,15 @@ __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constan
       if (m >= q.nc) continue;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
-        const int f = j * 8 + tig * 2;
-        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
-        if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        if constexpr (PERM) {
+          const int f = j * 8 + tig;
+          if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+          if (f + 4 < q.nfb) q.T1t[((int64_t)(f + 4) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        } else {
+          const int f = j * 8 + tig * 2;
+          if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+          if (f + 1 < q.nfb) q.T1t[((int64_t)(f + 1) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+        }
       }
     }
   }

@@ -38,4 +38,29 @@ for variant, gen in [(3, 1), (4, 1), (3, 2), (4, 2)]:
         tf = 2.0 * bc * nc * nc * nfb / (ms * 1e-3) / 1e12
         out[f"q1_v{variant}_g{gen}_n{nc}_f{nfb}_b{bc}"] = {"ms": ms, "TFLOP/s": tf}
         print("q1 variant", variant, "gen", gen, nc, nfb, bc, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
+# fragment-row permutation (LOWDIN_IT_OPT_FRAG_PERM): conflict-free 128-bit fragment loads, same kernels otherwise
+T.set_option(T.OPT_GEMM_VARIANT, T.DEFAULT_GEMM_VARIANT)
+T.set_option(T.OPT_SPLIT_ROW_TAIL, 1)
+T.set_option(T.OPT_BENCH_GEN, 1)
+for perm in (0, 1):
+    T.set_option(T.OPT_FRAG_PERM, perm)
+    for (m, n, k) in [(8192, 8192, 8192), (1350, 89440, 1500), (28672, 56, 1500), (60000, 150, 128)]:
+        try:
+            ms, _ = T.kernel_bench(1, m, n, k, iters=3)
+            tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+            out[f"perm{perm}_gemm_{m}x{n}x{k}"] = {"ms": ms, "TFLOP/s": tf}
+            print("perm", perm, "gemm", m, n, k, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("perm", perm, "gemm", m, n, k, "FAILED", e, flush=True)
+    for variant in (3, 4):
+        T.set_option(T.OPT_Q1_VARIANT, variant)
+        for nc, nfb, bc in [(1500, 56, 512), (1500, 48, 512), (1500, 40, 512), (500, 50, 2048)]:
+            try:
+                ms, _ = T.kernel_bench(2, nc, nfb, bc, iters=3)
+                tf = 2.0 * bc * nc * nc * nfb / (ms * 1e-3) / 1e12
+                out[f"perm{perm}_q1_v{variant}_n{nc}_f{nfb}"] = {"ms": ms, "TFLOP/s": tf}
+                print("perm", perm, "q1 variant", variant, nc, nfb, bc, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
+            except Exception as e:  # noqa: BLE001
+                print("perm", perm, "q1 variant", variant, nc, nfb, bc, "FAILED", e, flush=True)
+T.set_option(T.OPT_FRAG_PERM, 0)
 json.dump(out, open(f"gpurun_out/{tag}_variant_probe.json", "w"), indent=1)
