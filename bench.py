@@ -282,7 +282,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "4-index transform FP64 GFLOP/s", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"N_bf={n} MP2 window O={occ}, kind-H synthetic AO, random orthonormal C", "nbf": n, "occ": occ},
+            "config": {"workload": f"N_bf={n} MP2 window O={occ} (transformer-E roles), kind-H synthetic AO, random orthonormal C; "
+                                   f"step = a bounded sample of {per_step} AO-pair slabs of the same transform on the host cores",
+                       "nbf": n, "occ": occ},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
