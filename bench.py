@@ -376,9 +376,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # Watchdog: a pass that does not come back (ranks out of step inside a collective, a wedged kernel) must end the
+    # process instead of holding the box until the caller's limit; torchrun then takes the other ranks down.
+    import threading
+    last_beat = [time.monotonic()]
+    limit_s = float(os.environ.get("LOWDIN_BENCH_STEP_LIMIT_S", "900"))
+
+    def watchdog():
+        while True:
+            time.sleep(5.0)
+            if time.monotonic() - last_beat[0] > limit_s:
+                sys.stderr.write(f"bench.py watchdog: rank {rank}: no step finished for {limit_s:.0f} s, aborting\n")
+                sys.stderr.flush()
+                os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+
     def one_pass(i, with_eps=True):
-        return T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, first_pass=i % npass, n_passes=1,
-                                  epsA=eps if with_eps else None)
+        out = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=qb, first_pass=i % npass, n_passes=1,
+                                 epsA=eps if with_eps else None)
+        last_beat[0] = time.monotonic()
+        return out
 
     for i in range(args.warmup):
         one_pass(i)
@@ -485,6 +503,7 @@ def main():
                         "note": "C-ABI calls with host buffers: coefficients (pinned) + orbital energies up, reduced sums down; "
                                 "AO values generated on the device from the canonical index (a 5 TB host tensor cannot exist)"},
                 "gpu_launches": int(launches), "clocks": clocks}
+        last_beat[0] = time.monotonic() + 3600.0   # the CPU legs below are bounded by their own sampling, not by the watchdog
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
             v, dt, nsl = cpu_sample_timed(n, occ, nthreads, 15.0)
