@@ -9,6 +9,10 @@ mkdir -p gpurun_out
 O=gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -q -x > $O/${TAG}_pytest_gpu.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest_gpu.log ); tail -6 $O/${TAG}_pytest_gpu.log
 ( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "exit $?" >> $O/${TAG}_smoke.log ); tail -2 $O/${TAG}_smoke.log
+# the opt-in conflict-free fragment mapping (never run on a GPU in round 1): parity first, then kernels alone, then one pass
+( LOWDIN_IT_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_variants.py -m gpu -q -k perm > $O/${TAG}_pytest_perm.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest_perm.log ); tail -4 $O/${TAG}_pytest_perm.log
+timeout 400 python scripts/variant_probe.py $TAG > $O/${TAG}_variant_probe.log 2>&1; grep "^perm" $O/${TAG}_variant_probe.log
+timeout 200 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --frag-perm 1 > $O/${TAG}_bench_n1500_perm.json 2> $O/${TAG}_bench_n1500_perm.err; tail -c 1500 $O/${TAG}_bench_n1500_perm.json
 timeout 600 python bench.py --steps 3 --warmup 3 > $O/${TAG}_bench_n1500.json 2> $O/${TAG}_bench_n1500.err; tail -c 3000 $O/${TAG}_bench_n1500.json; tail -3 $O/${TAG}_bench_n1500.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; cat $O/${TAG}_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_launches_n1500.csv \
