@@ -155,7 +155,37 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
             "h2d_bytes_per_step": int(total * 24 + n * n * 8), "d2h_bytes_per_step": int(kept * 24), "mo_integrals_kept": int(kept),
             "device_ms": {"ao_upload_scatter": tm["ao_upload"] * 1e3, "first_half": tm["first_half"] * 1e3,
                           "second_half": tm["second_half"] * 1e3, "compaction": tm["consume"] * 1e3, "download": tm["download"] * 1e3},
-            "same_index_lists_as_generated": same, "max_abs_diff_vs_generated": diff}
+            "same_index_lists_as_generated": same, "max_abs_diff_vs_generated": diff,
+            "_result": (o_ij[:kept].copy(), o_kl[:kept].copy(), stored)}
+
+
+def whole_transform_cpu_leg(n, occ, gpu_result=None):
+    """Part of the cpu_baseline leg: the oracle's restatements of the reference's transformers E (one thread, as in the reference)
+    and C (OpenMP over p, as in the reference) on the WHOLE stored-AO workload of e2e_stored_ao, timed from packed AO integrals
+    in memory to the MO-integral list, and the largest difference between the GPU's list and transformer E's."""
+    from oracle import oracle as O
+    Cm = O.random_orthonormal(n, n)
+    packed = O.hash_packed_intra(SEED, n)
+    we = mp2_window_e(n, occ)
+    t0 = time.perf_counter()
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, we)
+    te = time.perf_counter() - t0
+    wc, sym = O.windows_c_intra("MP2", n, occ)
+    t0 = time.perf_counter()
+    rc = O.transform_c_intra(Cm, packed, wc, sym)
+    tc = time.perf_counter() - t0
+    P, M = n - occ, n * (n + 1) // 2
+    flops = 2.0 * n * occ * (n + P) * M + 2.0 * n * occ * (n + P) * (P * occ)
+    out = {"workload": f"N_bf={n} MP2 window O={occ}, whole transform from packed AO integrals in memory to the MO-integral list",
+           "transformer_e_port_s": te, "transformer_e_port_gflops": flops / te / 1e9, "transformer_e_threads": 1,
+           "transformer_c_port_s": tc, "transformer_c_port_gflops_same_flop_count": flops / tc / 1e9,
+           "transformer_c_threads": min(os.cpu_count() or 1, occ), "mo_integrals_e": int(len(rv)), "mo_integrals_c": int(len(rc[4]))}
+    if gpu_result is not None:
+        gij, gkl, gv = gpu_result
+        ref = np.zeros((M, M)); ref[rij - 1, rkl - 1] = rv
+        got = np.zeros((M, M)); got[gij - 1, gkl - 1] = gv
+        out["max_abs_diff_gpu_vs_transformer_e"] = float(np.abs(got - ref).max())
+    return out
 
 
 def transformer_d_leg(ol, n_full=120):
@@ -336,7 +366,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.stored_only:
         n_st = args.stored_nbf or 120
-        print(json.dumps({"e2e_stored_ao": stored_ao_e2e(torch, ol, capi, local, n_st, max(1, n_st * 21 // 120), max(1, args.steps))}))
+        res = stored_ao_e2e(torch, ol, capi, local, n_st, max(1, n_st * 21 // 120), max(1, args.steps))
+        res.pop("_result", None)
+        print(json.dumps({"e2e_stored_ao": res}))
         return
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -519,10 +551,18 @@ def main():
                 line["cpu_baseline"]["reference_transformer_d"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and args.stored_nbf > 0 and not args.no_e2e:
             # second end-to-end figure: STORED AO integrals through the whole upload -> transform -> download ABI
+            occ_st = max(1, args.stored_nbf * 21 // 120)
+            gpu_result = None
             try:
-                line["e2e_stored_ao"] = stored_ao_e2e(torch, ol, capi, local, args.stored_nbf, max(1, args.stored_nbf * 21 // 120), 3)
+                line["e2e_stored_ao"] = stored_ao_e2e(torch, ol, capi, local, args.stored_nbf, occ_st, 3)
+                gpu_result = line["e2e_stored_ao"].pop("_result", None)
             except Exception as e:  # never lose the main line to the secondary leg
                 line["e2e_stored_ao"] = {"value": None, "error": f"{type(e).__name__}: {e}"}
+            if not args.no_cpu_baseline and args.stored_nbf <= 160:
+                try:   # the same workload on the host: restated transformers E and C, and GPU-vs-E parity of the stored path
+                    line["cpu_baseline"]["port_whole_transform"] = whole_transform_cpu_leg(args.stored_nbf, occ_st, gpu_result)
+                except Exception as e:
+                    line["cpu_baseline"]["port_whole_transform"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

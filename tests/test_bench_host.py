@@ -160,6 +160,12 @@ def test_stored_ao_e2e_leg_with_stand_in_context(O, monkeypatch):
     assert fake.calls.count("lowdin_it_ao_push_stacks") == 3 * -(-(total + 1) // 100)
     ref = O.transform_e_intra(O.random_orthonormal(n, n), O.hash_packed_intra(bench.SEED, n), bench.mp2_window_e(n, occ))
     assert np.array_equal(ref[2], fake.res[2])
+    # the host-side comparison leg takes the GPU list (here: the stand-in's) and finds it identical to transformer E's
+    cpu = bench.whole_transform_cpu_leg(n, occ, out.pop("_result"))
+    assert cpu["max_abs_diff_gpu_vs_transformer_e"] == 0.0 and cpu["mo_integrals_e"] == out["mo_integrals_kept"]
+    assert cpu["transformer_e_port_s"] > 0 and cpu["transformer_c_port_s"] > 0
+    import json
+    json.dumps(out), json.dumps(cpu)          # everything that reaches the bench line is JSON-serialisable
 
 
 def test_transformer_d_leg_with_stand_in(O):
