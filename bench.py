@@ -538,7 +538,7 @@ def main():
         last_beat[0] = time.monotonic() + 3600.0   # the CPU legs below are bounded by their own sampling, not by the watchdog
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
-            v, dt, nsl = cpu_sample_timed(n, occ, nthreads, 15.0)
+            v, dt, nsl = cpu_sample_timed(n, occ, nthreads, 10.0)
             line["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": nthreads, "kind": "port",
                                     "sample": f"first half of transformer E (oracle port of E.f90:1043-1132) on {nsl} of {n*(n+1)//2} "
                                               f"AO-pair slabs, full occupied window, {dt:.1f} s"}
