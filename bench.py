@@ -97,12 +97,34 @@ def canonical_ao_list(seed, n, out=None):
     return p, q, r, s, v
 
 
-def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 20):
+def raw_ints_blocks(lst, total, S, out):
+    """The five list arrays as the bytes of a .ints stream (blocks of int32 p[S],q[S],r[S],s[S]; float64 v[S], the last block
+    carrying p = -1 after its last entry; Libint2Iface.cpp:3414-3426) into the uint8 buffer `out` of (total // S + 1) * 24 S bytes."""
+    nblk = total // S + 1
+    blk = out[:nblk * 24 * S].reshape(nblk, 24 * S)
+    for k in range(4):
+        dst = blk[:, 4 * S * k:4 * S * (k + 1)].view(np.int32)
+        full = (total // S) * S
+        dst[:total // S] = lst[k][:full].reshape(-1, S)
+        dst[total // S] = 0
+        dst[total // S, :total - full] = lst[k][full:total]
+    dst = blk[:, 16 * S:].view(np.float64)
+    full = (total // S) * S
+    dst[:total // S] = lst[4][:full].reshape(-1, S)
+    dst[total // S] = 0.0
+    dst[total // S, :total - full] = lst[4][full:total]
+    blk[:, :4 * S].view(np.int32)[total // S, total - full] = -1
+    return nblk
+
+
+def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 20, mode="stacks", stack_size=30000):
     """End to end through the C ABI with HOST buffers, stored AO integrals (the reference's own data flow): per step
     coefficients + the whole canonical AO list go host->device in the .ints stack layout (lowdin_it_ao_begin /
     _push_stacks / _end -> scatter), the transform runs (lowdin_it_transform, E convention, MP2 window) and every kept MO
     integral comes back (lowdin_it_download_pairs).  All host buffers are pinned.  The same transform with the AO values
-    generated on the device from the same keys is run once, untimed, as a consistency check of the upload path."""
+    generated on the device from the same keys is run once, untimed, as a consistency check of the upload path.
+    mode "stacks": the list as five arrays, push_entries per lowdin_it_ao_push_stacks call; mode "blocks": the same list as the
+    raw bytes of a .ints file (stacks of stack_size entries) in ONE lowdin_it_ao_push_blocks call."""
     import ctypes as C
     M = n * (n + 1) // 2
     total = M * (M + 1) // 2
@@ -118,13 +140,19 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
     T = ol.Transformer(dev_index)
     L, h = T.L, T.h
     cnt = C.c_int64()
+    if mode == "blocks":
+        raw = pin((total // stack_size + 1) * 24 * stack_size, torch.uint8)
+        nblk = raw_ints_blocks(lst, total, stack_size, raw)
 
     def step():
         T.set_species(0, Cpin)
         T._ck(L.lowdin_it_ao_begin(h, 0, 0, 0))
-        for a in range(0, total + 1, push_entries):
-            b = min(total + 1, a + push_entries)
-            T._ck(L.lowdin_it_ao_push_stacks(h, lst[0][a:b], lst[1][a:b], lst[2][a:b], lst[3][a:b], lst[4][a:b], b - a))
+        if mode == "blocks":
+            T._ck(L.lowdin_it_ao_push_blocks(h, raw.ctypes.data, nblk, stack_size))
+        else:
+            for a in range(0, total + 1, push_entries):
+                b = min(total + 1, a + push_entries)
+                T._ck(L.lowdin_it_ao_push_stacks(h, lst[0][a:b], lst[1][a:b], lst[2][a:b], lst[3][a:b], lst[4][a:b], b - a))
         T._ck(L.lowdin_it_ao_end(h))
         T._ck(L.lowdin_it_transform(h, 0, 0, win, capi.CONV_E, 0, 1e-10))
         T._ck(L.lowdin_it_result_count(h, C.byref(cnt)))
@@ -152,11 +180,66 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
     return {"value": flops / dt / 1e9, "unit": "GFLOP/s", "steps": steps, "ms_per_step": dt * 1e3,
             "workload": f"N_bf={n} MP2 window O={occ} (C6H6/cc-pVDZ shape when N=120), kind-H AO list of {total} canonical integrals "
                         "pushed from pinned host memory in the .ints stack layout, all kept MO integrals downloaded",
+            "push": ("raw .ints bytes, one lowdin_it_ao_push_blocks call" if mode == "blocks"
+                     else f"five arrays, {push_entries} entries per lowdin_it_ao_push_stacks call"),
+            "upload_gb_per_s": total * 24 / max(tm["ao_upload"], 1e-12) / 1e9,
             "h2d_bytes_per_step": int(total * 24 + n * n * 8), "d2h_bytes_per_step": int(kept * 24), "mo_integrals_kept": int(kept),
             "device_ms": {"ao_upload_scatter": tm["ao_upload"] * 1e3, "first_half": tm["first_half"] * 1e3,
                           "second_half": tm["second_half"] * 1e3, "compaction": tm["consume"] * 1e3, "download": tm["download"] * 1e3},
             "same_index_lists_as_generated": same, "max_abs_diff_vs_generated": diff,
             "_result": (o_ij[:kept].copy(), o_kl[:kept].copy(), stored)}
+
+
+def stored_resident_leg(ol, dev_index, n, all_mode=False, hbm_gbs=6549.4, fp64_peak=None):
+    """The STORED-AO kernels at scale: the packed kind-H tensor of an n-function basis (63 GB at N=500) is filled on the device
+    (lowdin_it_ao_materialize: as if its list had been uploaded) and the whole MP2-window transform runs from it -- expansion of
+    packed rows into dense slabs, the four quarter transforms, the device-side MP2 consumer.  Reports the per-kernel table and the
+    agreement of the streamed sums with the generated-source path on the same keys."""
+    occ = n // 10
+    P, M = n - occ, n * (n + 1) // 2
+    win = mp2_window_e(n, occ)
+    Cm = random_orthonormal(n, n)
+    eps = synthetic_eps(occ, n)
+    T = ol.Transformer(dev_index)
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, SEED, GEN_KIND)
+    s_gen = T.transform_stream(0, 0, win, ol.CONV_E, epsA=eps)
+    t0 = time.perf_counter()
+    T.materialize(0, 0)
+    fill_s = time.perf_counter() - t0
+    out = {"workload": f"N_bf={n} MP2 window O={occ}, packed AO tensor of {M * (M + 1) // 2} doubles ({M * (M + 1) * 4 / 1e9:.1f} GB) resident in HBM",
+           "fill_on_device_s": fill_s}
+
+    def run(w, label):
+        T.transform_stream(0, 0, w, ol.CONV_E, epsA=eps if label == "mp2" else None)       # warm-up
+        T.set_profiling(True)
+        sm = T.transform_stream(0, 0, w, ol.CONV_E, epsA=eps if label == "mp2" else None)
+        tm, st = T.timers(), T.kernel_stats()
+        T.set_profiling(False)
+        sec = tm["first_half"] + tm["exchange"] + tm["second_half"] + tm["consume"]
+        kern = {}
+        for c, v in st.items():
+            if v["launches"]:
+                gem = c in ("q1", "q2", "q3", "q4")
+                kern[c] = {"ms": round(v["ms"], 3), "launches": v["launches"], ("TFLOP/s" if gem else "GB/s"): v["work"] / (v["ms"] * 1e-3) / (1e12 if gem else 1e9)}
+        res = {"value": tm["flops"] / sec / 1e9, "unit": "GFLOP/s", "ms_per_transform": sec * 1e3, "kernels": kern, "gpu_launches": tm["launches"]}
+        if "expand1" in kern:
+            res["roofline_expand1"] = {"bound": "hbm", "achieved": kern["expand1"]["GB/s"], "peak": hbm_gbs, "unit": "GB/s",
+                                       "frac": kern["expand1"]["GB/s"] / hbm_gbs,
+                                       "algorithmic_bytes": "8 M read + 8 N^2 written per slab (E.f90:1047-1063)"}
+        if "q1" in kern and fp64_peak:
+            res["roofline_q1"] = {"bound": "tensor", "achieved": kern["q1"]["TFLOP/s"], "peak": fp64_peak, "unit": "TFLOP/s",
+                                  "frac": kern["q1"]["TFLOP/s"] / fp64_peak}
+        return res, sm
+
+    out["mp2"], s_st = run(win, "mp2")
+    scale = np.array([1.0, np.sqrt(s_gen[0] * s_gen[2]), s_gen[2], max(abs(s_gen[3]), 1e-300)])
+    out["mp2"]["sums"] = list(map(float, s_st))
+    out["mp2"]["vs_generated_source"] = {"count_equal": bool(s_st[0] == s_gen[0]), "max_rel_diff": float((np.abs(s_st - s_gen) / scale)[1:].max())}
+    if all_mode:
+        out["all"], _ = run([1, n] * 4, "all")
+    T.close()
+    return out
 
 
 def whole_transform_cpu_leg(n, occ, gpu_result=None):
@@ -279,6 +362,22 @@ def cpu_sample(n, occ, nslabs, nthreads):
     return flops / dt / 1e9, dt, chk
 
 
+def first_half_parity(T, ol, n, occ, gen, nthreads, nslabs=8):
+    """Half-transformed integrals (i a|pq) of the first and the last `nslabs` AO-pair slabs: device (lowdin_it_debug_first_half, the
+    kernels of the timed path) against the oracle port of E.f90:1043-1132 on the same slabs."""
+    from oracle import oracle as O
+    Cm = O.random_orthonormal(n, n)
+    win = mp2_window_e(n, occ)
+    M = n * (n + 1) // 2
+    worst, cnt = 0.0, 0
+    for pq0 in (0, M - nslabs):
+        got = T.debug_first_half(0, 0, win, ol.CONV_E, pq0, nslabs)
+        ref = O.e_first_half_values(SEED, Cm, win, pq0, nslabs, nthreads, gen_kind=gen)
+        worst = max(worst, float(np.abs(got - ref).max()))
+        cnt += got.size
+    return {"max_abs_diff": worst, "values_compared": cnt, "slabs": f"first and last {nslabs} of {M}", "tolerance": 1e-10, "ok": worst <= 1e-10}
+
+
 def cpu_sample_timed(n, occ, nthreads, target_s):
     """Calibrate on one slab per thread, then run a sample sized for about target_s seconds."""
     v, dt, _ = cpu_sample(n, occ, max(1, nthreads), nthreads)
@@ -348,6 +447,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--stored-nbf", type=int, default=120, help="basis size of the stored-AO end-to-end leg (0 = skip)")
     ap.add_argument("--stored-only", action="store_true", help="run only the stored-AO end-to-end leg and print it (profiling / quick checks)")
+    ap.add_argument("--push-mode", default="blocks", help="--stored-only: 'blocks' (raw .ints bytes) or 'stacks' (five arrays)")
+    ap.add_argument("--resident-nbf", type=int, default=500, help="basis size of the stored-AO-resident leg (packed tensor filled on the device; 0 = skip)")
+    ap.add_argument("--resident-all", action="store_true", help="resident leg: also the ALL (full) window")
+    ap.add_argument("--resident-only", action="store_true", help="run only the stored-AO-resident leg and print it")
     ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
     ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
     ap.add_argument("--gemm-variant", type=int, default=0, help="quarter-transform GEMM variant (0 = library default)")
@@ -364,9 +467,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.resident_only:
+        print(json.dumps({"stored_ao_resident": stored_resident_leg(ol, local, args.resident_nbf or 500, args.resident_all)}))
+        return
     if args.stored_only:
         n_st = args.stored_nbf or 120
-        res = stored_ao_e2e(torch, ol, capi, local, n_st, max(1, n_st * 21 // 120), max(1, args.steps))
+        res = stored_ao_e2e(torch, ol, capi, local, n_st, max(1, n_st * 21 // 120), max(1, args.steps), mode=args.push_mode)
         res.pop("_result", None)
         print(json.dumps({"e2e_stored_ao": res}))
         return
@@ -430,8 +536,35 @@ def main():
         last_beat[0] = time.monotonic()
         return out
 
+    golden = {}
+    try:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_sums.json")))
+    except (OSError, ValueError):
+        pass
+    parity = {}
+    if world > 1 and "small" in golden:
+        # N>1 ranks: before anything is timed, a small collective transform whose sums the CPU oracle computed offline
+        # (tests/golden/bench_sums.json, oracle/make_bench_golden.py): the exchange of THIS communicator, checked.
+        g = golden["small"]
+        Cs = random_orthonormal(g["n"], g["n"])
+        T.set_species(1, Cs)
+        T.set_generator(1, 1, g["seed"], 1)
+        worst = 0.0
+        for cols, qb in ((0, 0), (60, 4), (1, 2)):
+            T.set_option(T.OPT_CHUNK_COLS, cols)
+            sm = torch.tensor(T.transform_stream(1, 1, mp2_window_e(g["n"], g["occ"]), ol.CONV_E, occ_batch=qb,
+                                                 epsA=synthetic_eps(g["occ"], g["n"])), dtype=torch.float64, device=dev)
+            dist.all_reduce(sm)
+            sm = sm.tolist()
+            worst = max(worst, abs(sm[0] - g["sums"][0]), *[abs(a - b) for a, b in zip(sm[1:], g["sums"][1:])])
+        T.set_option(T.OPT_CHUNK_COLS, 0)
+        parity["small_collective_transform"] = {"n": g["n"], "ranks": world, "max_abs_diff_vs_oracle_golden": worst, "ok": worst <= 1e-9}
+        if worst > 1e-9:
+            raise SystemExit(f"bench.py: the {world}-rank transform of the small golden case differs from the oracle by {worst}")
+
+    pass_sums = {}
     for i in range(args.warmup):
-        one_pass(i)
+        pass_sums[i % npass] = one_pass(i)
 
     # ---------------- timed region: `value` (inputs resident in HBM) ----------------
     sampler = ClockSampler(local)
@@ -442,7 +575,7 @@ def main():
     t0 = time.perf_counter()
     dev_s, flops, launches = 0.0, 0.0, 0
     for i in range(args.steps):
-        one_pass(args.warmup + i)
+        pass_sums[(args.warmup + i) % npass] = one_pass(args.warmup + i)
         tm = T.timers()
         dev_s += tm["first_half"] + tm["exchange"] + tm["second_half"] + tm["consume"]
         flops += tm["flops"]
@@ -479,6 +612,24 @@ def main():
         f = torch.tensor([flops, e2e_flops, float(launches)], dtype=torch.float64, device=dev)
         dist.all_reduce(f, op=dist.ReduceOp.SUM)
         flops, e2e_flops, launches = f.tolist()
+
+    # results of the passes that ran (every pass of the transform when warmup + steps >= npass), summed over ranks
+    covered = sorted(pass_sums)
+    tot = np.sum([pass_sums[k] for k in covered], axis=0)
+    if dist is not None:
+        tt = torch.tensor(tot, dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        tot = np.array(tt.tolist())
+    parity["passes_covered"] = f"{len(covered)} of {npass}"
+    parity["sums"] = {"count": tot[0], "sum": tot[1], "sum_sq": tot[2], "mp2_pair_energy": tot[3]}
+    key = f"n{n}_gen{args.gen}"
+    if len(covered) == npass and key in golden:
+        ref = np.array(golden[key]["sums"])
+        scale = np.array([1.0, np.sqrt(ref[0] * ref[2]), ref[2], max(abs(ref[3]), 1e-300)])
+        rel = np.abs(tot - ref) / scale
+        parity["whole_transform_vs_reference_sums"] = {"reference": golden[key]["sums"], "source": golden[key].get("source"),
+                                                       "count_equal": bool(tot[0] == ref[0]), "max_rel_diff": float(rel[1:].max()),
+                                                       "ok": bool(tot[0] == ref[0] and rel[1:].max() <= 1e-9)}
 
     if rank == 0:
         value = flops / dev_s / 1e9
@@ -525,7 +676,7 @@ def main():
                 "config": {"workload": f"N_bf={n} MP2 window O={occ} (transformer-E roles), kind-H synthetic AO generated on device, "
                                        f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
                                        f"({npass} passes = the whole transform)",
-                           "nbf": n, "occ": occ, "occ_batch": qb, "passes_per_transform": npass,
+                           "nbf": n, "occ": occ, "gen": args.gen, "occ_batch": qb, "passes_per_transform": npass,
                            "l2": "working set larger than L2 (each pass re-streams the third-quarter accumulators and chunk buffers, tens of GB)",
                            "flops_per_step": flops / args.steps, "fp64_pct_of_cublas_dgemm_per_gpu": 100.0 * value / 1e3 / fp64_peak / world,
                            "fp64_pct_of_nominal_37tf_per_gpu": 100.0 * value / 37000.0 / world, "cublas_dgemm_tflops_measured": fp64_peak, "wall_ms_per_step": wall_s / args.steps * 1e3},
@@ -534,7 +685,7 @@ def main():
                         "h2d_bytes_per_step": int(n * n * 8 + n * 8), "d2h_bytes_per_step": 32,
                         "note": "C-ABI calls with host buffers: coefficients (pinned) + orbital energies up, reduced sums down; "
                                 "AO values generated on the device from the canonical index (a 5 TB host tensor cannot exist)"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "clocks": clocks, "parity": parity}
         last_beat[0] = time.monotonic() + 3600.0   # the CPU legs below are bounded by their own sampling, not by the watchdog
         if world == 1 and not args.no_cpu_baseline:
             nthreads = os.cpu_count() or 1
@@ -542,6 +693,10 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "GFLOP/s", "cores": nthreads, "kind": "port",
                                     "sample": f"first half of transformer E (oracle port of E.f90:1043-1132) on {nsl} of {n*(n+1)//2} "
                                               f"AO-pair slabs, full occupied window, {dt:.1f} s"}
+            try:   # the same CPU port as the checker of the device's first half at THIS size (first and last slabs of the tensor)
+                line["cpu_baseline"]["first_half_parity"] = first_half_parity(T, ol, n, occ, args.gen, nthreads)
+            except Exception as e:
+                line["cpu_baseline"]["first_half_parity"] = {"error": f"{type(e).__name__}: {e}"}
     T.close()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -549,13 +704,20 @@ def main():
                 line["cpu_baseline"]["reference_transformer_d"] = transformer_d_leg(ol)
             except Exception as e:
                 line["cpu_baseline"]["reference_transformer_d"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and args.resident_nbf > 0 and not args.no_e2e:
+            try:
+                line["stored_ao_resident"] = stored_resident_leg(ol, local, args.resident_nbf, args.resident_all, fp64_peak=fp64_peak)
+            except Exception as e:
+                line["stored_ao_resident"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and args.stored_nbf > 0 and not args.no_e2e:
             # second end-to-end figure: STORED AO integrals through the whole upload -> transform -> download ABI
             occ_st = max(1, args.stored_nbf * 21 // 120)
             gpu_result = None
             try:
-                line["e2e_stored_ao"] = stored_ao_e2e(torch, ol, capi, local, args.stored_nbf, occ_st, 3)
+                line["e2e_stored_ao"] = stored_ao_e2e(torch, ol, capi, local, args.stored_nbf, occ_st, 3, mode="blocks")
                 gpu_result = line["e2e_stored_ao"].pop("_result", None)
+                five = stored_ao_e2e(torch, ol, capi, local, args.stored_nbf, occ_st, 2, mode="stacks")
+                line["e2e_stored_ao"]["five_array_push"] = {k: five[k] for k in ("value", "ms_per_step", "push", "upload_gb_per_s")}
             except Exception as e:  # never lose the main line to the secondary leg
                 line["e2e_stored_ao"] = {"value": None, "error": f"{type(e).__name__}: {e}"}
             if not args.no_cpu_baseline and args.stored_nbf <= 160:

@@ -41,6 +41,7 @@ typedef struct lowdin_it_ctx *lowdin_it_handle;
 /* Synthetic AO generators (benchmark inputs). */
 #define LOWDIN_IT_GEN_HASH 1 /* kind H: value = 2u-1, u = (splitmix64(seed ^ key) >> 11) * 2^-53 */
 #define LOWDIN_IT_GEN_FOLD 2 /* kind F: same, with mulfold64(x) = ((x*K1) ^ ((x*K1)>>32)) * K2 instead of splitmix64 */
+#define LOWDIN_IT_GEN_RANKK 3 /* kind K: (mu nu|lam sig) = sum_{k<K} La^k[mu nu] Lb^k[lam sig], K <= 8 (lowdin_it_ao_set_rankk) */
 
 /* ---- lifetime --------------------------------------------------------------------- */
 /* Replaces the per-call malloc/free of IntTransfD.cpp:131-143: device buffers live in the handle. */
@@ -58,11 +59,26 @@ int lowdin_it_set_species(lowdin_it_handle h, int slot, int nao, const double *C
  * ReadIntegrals.f90:23-99.  slotB == slotA means intra-species.  `swapped` != 0 restates the
  * reversed-pair branch TransformIntegralsC.f90:906-972: the stacks are (B B|A A). */
 int lowdin_it_ao_begin(lowdin_it_handle h, int slotA, int slotB, int swapped);
+/* n entries as five arrays.  The terminator test (p = -1 ends the stream of THIS call, C.f90:279-280), the index
+ * range check and the scatter all run on the device; the call returns when its host buffers have been copied
+ * (they may be reused), not when the scatter is done.  An entry with an index outside the basis makes
+ * lowdin_it_ao_end fail (the AO set stays unusable). */
 int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int32_t *r,
                              const int32_t *s, const double *v, int64_t n);
+/* The same entries as RAW .ints bytes: nblocks blocks of `int32 p[S],q[S],r[S],s[S]; real64 v[S]` (24 S bytes each,
+ * Libint2Iface.cpp:3414-3426; what `read(unit) pp,qq,rr,ss,shellIntegrals` consumes, C.f90:258-262), e.g. a whole file
+ * or a memory-mapped range of it: one host-to-device copy per staging buffer, decoded on the device. */
+int lowdin_it_ao_push_blocks(lowdin_it_handle h, const void *blocks, int64_t nblocks, int stack_size);
 int lowdin_it_ao_end(lowdin_it_handle h);
 /* Instead of an upload: slabs generated on the device on the fly (no N^4/8 array). */
 int lowdin_it_ao_set_generator(lowdin_it_handle h, int slotA, int slotB, int kind, uint64_t seed);
+/* Kind K: rank-K separable tensor, the one synthetic input whose MO integrals have a closed form
+ * (p q|r s) = sum_k (Ca^T La^k Ca)[p,q] (Cb^T Lb^k Cb)[r,s], i.e. an O(K N^3) oracle at any N.  La: host [K][M_a] values of the
+ * K symmetric matrices at the pairs (mu<=nu) in xy order; Lb likewise for species B (ignored for slotB == slotA). */
+int lowdin_it_ao_set_rankk(lowdin_it_handle h, int slotA, int slotB, int K, const double *La, const double *Lb);
+/* Turn a generated AO set into a STORED one on the device (packed M(M+1)/2 / rectangular M_b x M_a), as if its whole
+ * list had been uploaded: the stored-AO kernels at sizes whose list no host could hold (bench leg, tests). */
+int lowdin_it_ao_materialize(lowdin_it_handle h, int slotA, int slotB);
 
 /* ---- the transform ---------------------------------------------------------------- */
 /* One species (slotB==slotA) or species pair.  Replaces
@@ -112,6 +128,10 @@ int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_width, int nran
 int64_t lowdin_it_blocked_offset(int64_t row, int64_t col, int64_t wblk, int64_t rows);
 int lowdin_it_comm_unique_id(char id[128]);
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]);
+/* The same collective semantics for handles of ONE process (rank r = handles[r], each then driven by its own host thread):
+ * the all-to-all is a set of direct peer copies ordered by CUDA events.  The handles may share a device, which is how the
+ * multi-rank division of work is parity-tested on a one-GPU box. */
+int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks);
 
 /* ---- tuning ----------------------------------------------------------------------- */
 #define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
@@ -121,6 +141,8 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
 #define LOWDIN_IT_OPT_GEMM_VARIANT 5    /* quarter-transform GEMM: 1 = cp.async ring + block barrier, 2 = TMA + mbarrier, persistent */
 #define LOWDIN_IT_OPT_SPLIT_ROW_TAIL 6  /* TMA GEMM: 1 (default) = the <= 80-row tail of a few-rows x many-columns product runs as a second, operand-swapped launch instead of a padded 128-row tile */
 #define LOWDIN_IT_OPT_FRAG_PERM 7       /* TMA kernels: 1 = fragment rows permuted so that the 128-bit shared loads of a quarter-warp are conflict-free (default 0 until measured on a GPU) */
+#define LOWDIN_IT_OPT_ASYNC_PUSH 8      /* 1 = the caller leaves pushed host buffers untouched until lowdin_it_ao_end: pushes return without waiting for their copies */
+#define LOWDIN_IT_OPT_STAGING_BYTES 9   /* size of each of the two device staging buffers of the AO upload (default 96 MiB) */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 
 /* ---- instrumentation -------------------------------------------------------------- */
@@ -142,6 +164,10 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
  * DMMA kernel; dense expansion of nb slabs of an uploaded / generated AO set to host X[nb][n][n]. */
 int lowdin_it_debug_gemm(lowdin_it_handle h, const double *A, const double *B, double *C, int m, int n, int k);
 int lowdin_it_debug_expand(lowdin_it_handle h, int slotA, int slotB, int64_t slab0, int nb, double *X);
+/* First half only (TransformIntegralsE.f90:1043-1132) of AO-pair slabs [slab0, slab0+nslabs): out[k][z] for the k-th window
+ * pair in convention order (E: ijmap order) -- the oracle check of the first half at sizes no CPU transforms whole. */
+int lowdin_it_debug_first_half(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv, double drop_tol,
+                               int64_t slab0, int nslabs, double *out, int64_t *npairs);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CONV_C, CONV_E = 0, 1
-GEN_HASH, GEN_FOLD = 1, 2
+GEN_HASH, GEN_FOLD, GEN_RANKK = 1, 2, 3
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
@@ -23,6 +23,8 @@ ABI_SYMBOLS = [
     "lowdin_it_stream_num_passes", "lowdin_it_transform_all", "lowdin_it_transform_inter_all",
     "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_shard_plan", "lowdin_it_blocked_offset", "lowdin_it_timers", "lowdin_it_kernel_bench",
     "lowdin_it_set_profiling", "lowdin_it_set_option", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
+    "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
+    "lowdin_it_debug_first_half",
 ]
 
 
@@ -81,6 +83,12 @@ def load():
     L.lowdin_it_kernel_stats.argtypes = [H, _f64p, _f64p, _f64p]
     L.lowdin_it_debug_gemm.argtypes = [H, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_int]
     L.lowdin_it_debug_expand.argtypes = [H, C.c_int, C.c_int, C.c_int64, C.c_int, _f64p]
+    L.lowdin_it_ao_push_blocks.argtypes = [H, C.c_void_p, C.c_int64, C.c_int]
+    L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
+    L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
+    L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_debug_first_half.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p,
+                                             C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -129,8 +137,33 @@ class Transformer:
             self._ck(self.L.lowdin_it_ao_push_stacks(self.h, pp, qq, rr, ss, vv, stack))
         self._ck(self.L.lowdin_it_ao_end(self.h))
 
+    def upload_ao_blocks(self, a, b, raw, stack, swapped=False):
+        """Push raw .ints bytes (blocks of int32 p[S],q[S],r[S],s[S]; float64 v[S]) -- what a file read returns."""
+        raw = np.ascontiguousarray(np.frombuffer(raw, np.uint8) if not isinstance(raw, np.ndarray) else raw.view(np.uint8))
+        assert raw.size % (24 * stack) == 0, "not a whole number of stacks"
+        self._ck(self.L.lowdin_it_ao_begin(self.h, a, b, int(swapped)))
+        self._ck(self.L.lowdin_it_ao_push_blocks(self.h, raw.ctypes.data, raw.size // (24 * stack), stack))
+        self._ck(self.L.lowdin_it_ao_end(self.h))
+
     def set_generator(self, a, b, seed, kind=GEN_HASH):
         self._ck(self.L.lowdin_it_ao_set_generator(self.h, a, b, kind, seed))
+
+    def set_rankk(self, a, b, La, Lb=None):
+        """Kind K: La [K][M_a] pair vectors (xy order) of the K symmetric factor matrices; Lb for species b (inter)."""
+        La = np.ascontiguousarray(La, dtype=np.float64)
+        Lb = np.ascontiguousarray(Lb, dtype=np.float64) if Lb is not None else None
+        self._ck(self.L.lowdin_it_ao_set_rankk(self.h, a, b, La.shape[0], La, Lb.ctypes.data if Lb is not None else None))
+
+    def materialize(self, a, b):
+        self._ck(self.L.lowdin_it_ao_materialize(self.h, a, b))
+
+    def debug_first_half(self, a, b, win, conv, slab0, nslabs, tol=1e-10):
+        w = np.ascontiguousarray(win, dtype=np.int32)
+        npairs = C.c_int64()
+        self._ck(self.L.lowdin_it_debug_first_half(self.h, a, b, w, conv, tol, slab0, nslabs, None, C.byref(npairs)))
+        out = np.zeros((npairs.value, nslabs))
+        self._ck(self.L.lowdin_it_debug_first_half(self.h, a, b, w, conv, tol, slab0, nslabs, out.ctypes.data, C.byref(npairs)))
+        return out
 
     def transform(self, a, b, win, conv, symmetric=False, tol=1e-10):
         w = np.ascontiguousarray(win, dtype=np.int32)
@@ -176,6 +209,7 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES = 8, 9
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT = 3, 2  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):
@@ -205,6 +239,35 @@ class Transformer:
         X = np.zeros((nb, n, n))
         self._ck(self.L.lowdin_it_debug_expand(self.h, a, b, slab0, nb, X))
         return X
+
+
+def local_group(transformers):
+    """Make the given Transformers (one process, any devices) ranks 0..n-1 of an in-process group; each must then be driven
+    by its own thread making the same collective calls."""
+    arr = (C.c_void_p * len(transformers))(*[t.h for t in transformers])
+    if load().lowdin_it_comm_init_local(arr, len(transformers)):
+        raise LowdinITError(load().lowdin_it_last_error(None).decode())
+
+
+def run_ranks(transformers, fn):
+    """Run fn(rank, transformer) on one thread per rank (collective calls of an in-process group); returns the results."""
+    import threading
+    out, err = [None] * len(transformers), [None] * len(transformers)
+
+    def work(r):
+        try:
+            out[r] = fn(r, transformers[r])
+        except BaseException as e:  # noqa: BLE001
+            err[r] = e
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(transformers))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 def shard_plan(fbeg, chunk_width, nranks, rank):

@@ -11,8 +11,13 @@
 
 #include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,6 +52,7 @@ struct AoSet {
   bool valid = false;
   AoSource src{};
   DevBuf data;
+  DevBuf fa, fb;  // kind K: pair-vector factors [RANKK][M_a], [RANKK][M_b]
 };
 
 // NCCL, resolved lazily so that single-GPU use has no link-time dependency on it.
@@ -80,6 +86,33 @@ bool load_nccl(std::string &err) {
   return true;
 }
 
+// In-process rank group (lowdin_it_comm_init_local): the ranks are handles of ONE process, each driven by its own host thread;
+// the all-to-all is a set of direct device-to-device (peer) copies, ordered by CUDA events, and the host threads meet at a barrier.
+// The same collective semantics as the NCCL communicator, usable on a single device: the multi-rank logic (slab and slot
+// division, chunk agreement, blocked layout) is then exercised by the GPU tests of a one-GPU box.
+struct LocalGroup {
+  int n = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0;
+  uint64_t gen = 0;
+  int64_t agree[16] = {};
+  const double *H[16] = {};
+  int device[16] = {};
+  cudaEvent_t ready[16] = {}, done[16] = {};
+  bool failed = false;
+  // false: a rank did not arrive within 5 minutes (it failed before the collective); the group is then unusable
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    if (failed) return false;
+    const uint64_t g = gen;
+    if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return true; }
+    if (!cv.wait_for(lk, std::chrono::seconds(300), [&] { return gen != g || failed; }) || failed) { failed = true; cv.notify_all(); return false; }
+    return true;
+  }
+  ~LocalGroup() { for (int i = 0; i < 16; ++i) { if (ready[i]) cudaEventDestroy(ready[i]); if (done[i]) cudaEventDestroy(done[i]); } }
+};
+
 }  // namespace
 
 struct lowdin_it_ctx {
@@ -90,7 +123,14 @@ struct lowdin_it_ctx {
   AoSet ao[8][8];
   // AO upload state
   int up_a = -1, up_b = -1, up_swapped = 0;
-  DevBuf st_p, st_q, st_r, st_s, st_v;
+  DevBuf st[2], up_state;                    // two device staging buffers (copy of piece i+1 overlaps the scatter of piece i); {terminator, bad entry}
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {}, ev_scattered[2] = {};
+  bool st_busy[2] = {false, false};
+  int up_piece = 0;
+  int64_t up_pos = 0;                        // entries pushed so far in this upload (error positions)
+  int async_push = 0;                        // 1: pushed host buffers stay untouched until ao_end -> pushes do not wait for their copies
+  size_t staging_bytes = (size_t)96 << 20;   // per staging buffer
   // workspaces
   DevBuf X, T1t, H, H2, OUT, T3, order, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp, agree;
   // results of the last lowdin_it_transform
@@ -102,7 +142,8 @@ struct lowdin_it_ctx {
   cudaEvent_t ev[6] = {};
   // multi-GPU
   int rank = 0, nranks = 1;
-  void *comm = nullptr;
+  void *comm = nullptr;                      // NCCL communicator (one process per GPU)
+  std::shared_ptr<LocalGroup> lgroup;        // or: in-process group of handles
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
   int q1_variant = 3;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
@@ -124,6 +165,11 @@ namespace {
 
 int fail(lowdin_it_handle h, const std::string &msg) {
   if (h) h->err = msg; else g_create_error = msg;
+  if (h && h->lgroup) {  // a rank of an in-process group that fails releases its peers from the next collective
+    std::lock_guard<std::mutex> lk(h->lgroup->m);
+    h->lgroup->failed = true;
+    h->lgroup->cv.notify_all();
+  }
   return 1;
 }
 #define CK(call)                                                                                     \
@@ -133,6 +179,19 @@ int fail(lowdin_it_handle h, const std::string &msg) {
   } while (0)
 
 inline int64_t npairs(int64_t n) { return n * (n + 1) / 2; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: every call site keeps one bit per device
+// (handles on several GPUs of one process each get the opt-in), set under a mutex (handles may live on different threads).
+std::mutex g_attr_mutex;
+template <class K>
+cudaError_t ensure_dyn_smem(K kern, size_t smem, int device, uint64_t &done_mask) {
+  std::lock_guard<std::mutex> lk(g_attr_mutex);
+  const uint64_t bit = 1ull << (device & 63);
+  if (done_mask & bit) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done_mask |= bit;
+  return e;
+}
 inline int64_t roundup2(int64_t x) { return (x + 1) & ~int64_t(1); }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -169,12 +228,8 @@ cudaError_t launch_gemm_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &ep
   constexpr int ST = 3;
   constexpr size_t smem = (size_t)ST * (BM + BN) * 20 * sizeof(double);
   auto kern = dgemm_tn_kernel<BM, BN, WM, WN, ST, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static uint64_t configured = 0;
+  if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured); e != cudaSuccess) return e;
   dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), 1);
   kern<<<grid, WM * WN * 32, smem, h->stream>>>(g, epi);
   h->launches += 1;
@@ -221,12 +276,8 @@ cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi
   static_assert(smem <= 232448, "shared memory per CTA");
   const int perm = h->frag_perm ? 1 : 0;
   auto kern = perm ? dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, true> : dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[perm]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured[perm] = true;
-  }
+  static uint64_t configured[2] = {0, 0};
+  if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured[perm]); e != cudaSuccess) return e;
   CUtensorMap mapA, mapB;
   if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda, BM) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, BN)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
@@ -407,6 +458,7 @@ int launch_expand(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_
     case SRC_RECT: expand_block_kernel<SRC_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     case SRC_RECT_BLOCKED: expand_block_kernel<SRC_RECT_BLOCKED><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     case SRC_HASH_SYM: expand_block_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    case SRC_RANKK: expand_block_kernel<SRC_RANKK><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     default: expand_block_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
   }
   h->launches += 1;
@@ -422,12 +474,8 @@ cudaError_t launch_q1_gen_cfg(lowdin_it_handle h, const AoSource &src, int64_t s
     constexpr int ST = 4;
     constexpr size_t smem = (size_t)ST * (TN * 8) * 20 * sizeof(double);
     auto kern = q1_gen_smem_kernel<TN, ST>;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = true;
-    }
+    static uint64_t configured = 0;
+    if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured); e != cudaSuccess) return e;
     kern<<<grid, 256, smem, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
   } else {
     q1_gen_kernel<TN><<<grid, 256, 0, h->stream>>>(src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
@@ -446,13 +494,9 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
   const bool perm = h->frag_perm != 0;
   auto kern = v4 ? (perm ? q1_gen_ws2_kernel<TN, ST, KIND, GEN, true> : q1_gen_ws2_kernel<TN, ST, KIND, GEN, false>)
                  : (perm ? q1_gen_ws_kernel<TN, ST, KIND, GEN, true> : q1_gen_ws_kernel<TN, ST, KIND, GEN, false>);
-  static bool configured[4] = {false, false, false, false};
+  static uint64_t configured[4] = {0, 0, 0, 0};
   const int ci = (v4 ? 2 : 0) + (perm ? 1 : 0);
-  if (!configured[ci]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured[ci] = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured[ci]); e != cudaSuccess) return e;
   CUtensorMap mapB;
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(nc, 128) * (int64_t)bc;
@@ -603,6 +647,16 @@ void shard_plan(int nfb, const int *fbeg, int64_t width, int G, int rank, int *o
 // take the minimum (one 8-byte ncclAllReduce on the library's stream).  Single GPU: nothing happens.
 int agree_min(lowdin_it_handle h, int64_t *v) {
   if (h->nranks <= 1) return 0;
+  if (h->lgroup) {
+    LocalGroup &L = *h->lgroup;
+    L.agree[h->rank] = *v;
+    if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the collective");
+    int64_t m = L.agree[0];
+    for (int g = 1; g < L.n; ++g) m = std::min(m, L.agree[g]);
+    if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the collective");  // everyone has read before anyone writes the next value
+    *v = m;
+    return 0;
+  }
   if (!h->comm) return fail(h, "multi-GPU transform without a communicator");
   CK(h->agree.ensure(sizeof(int64_t)));
   CK(cudaMemcpyAsync(h->agree.p, v, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
@@ -638,6 +692,18 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     CK(cudaMemsetAsync(h->sums.p, 0, 4 * sizeof(double), h->stream));
   }
   h->count = 0;
+  if (cons.mode == 0) {
+    // An empty window (e.g. a one-function species under MP2: virtual window 2..1) is a valid transform with no
+    // integrals: the reference writes a terminator-only moint.dat (C.f90:450-456, E.f90:1263-1268).
+    h->res_conv = pl.conv;
+    CK(h->overflow.ensure(sizeof(int)));
+    CK(cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream));
+  }
+  if (pl.pairs_s.empty() || h2.nf <= 0 || h2.ns <= 0) {  // an empty window: no integrals, nothing to run
+    if (cons.mode == 1 && sums_out) sums_out[0] = sums_out[1] = sums_out[2] = sums_out[3] = 0.0;
+    h->timers[6] = 0; h->timers[7] = 0;
+    return 0;
+  }
   double flops = 0.0;
   const int n2 = h2.nc, nf2 = h2.nf, ns2 = h2.ns;
   const int64_t ldt2 = roundup2(n2);
@@ -763,7 +829,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
                          pl.win[0] == pl.win[4] && pl.win[2] == pl.win[6]) ? 1 : 0;
           ra.lambda = cons.lambda; ra.tol = cons.tol;
           ProfScope ps(h, 6, (double)gn * per_out * 8.0);
-          reduce_block_kernel<<<148 * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
+          reduce_block_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(ra, h->sums.as<double>());
           h->launches += 1;
           CK(cudaGetLastError());
         }
@@ -786,9 +852,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         CK(h->blockcount.ensure(nblk * sizeof(unsigned)));
         CK(h->blockoff.ensure(nblk * sizeof(int64_t)));
         CK(h->running.ensure(sizeof(unsigned long long)));
-        CK(h->overflow.ensure(sizeof(int)));
         CK(cudaMemsetAsync(h->running.p, 0, sizeof(unsigned long long), h->stream));
-        CK(cudaMemsetAsync(h->overflow.p, 0, sizeof(int), h->stream));
         select_count_kernel<<<(unsigned)nblk, SEL_THREADS, 0, h->stream>>>(sa, ncand, h->blockcount.as<unsigned>());
         select_scan_kernel<<<1, 1024, 0, h->stream>>>(h->blockcount.as<unsigned>(), nblk, h->blockoff.as<int64_t>(),
                                                       h->running.as<unsigned long long>());
@@ -813,7 +877,6 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         h->launches += 1;
         CK(cudaGetLastError());
       }
-      h->res_conv = pl.conv;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -839,9 +902,29 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
 // blocks [g][slot_local][wblk], which the chunk expansion reads in place (SRC_RECT_BLOCKED).
 int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out) {
   const int G = h->nranks;
-  if (!h->comm) return fail(h, "multi-GPU transform without a communicator");
+  if (!h->comm && !h->lgroup) return fail(h, "multi-GPU transform without a communicator");
   const int mine = own[h->rank + 1] - own[h->rank];
   CK(h->H2.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
+  if (h->lgroup) {
+    // in-process group: every rank PULLS its slots' rows from every peer's H with peer copies on its own stream
+    LocalGroup &L = *h->lgroup;
+    const int r = h->rank;
+    L.H[r] = h->H.as<double>();
+    CK(cudaEventRecord(L.ready[r], h->stream));  // my first half of this chunk is complete behind this event
+    if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the exchange");
+    for (int g = 0; g < G; ++g) {
+      CK(cudaStreamWaitEvent(h->stream, L.ready[g], 0));
+      if (mine > 0 && wblk > 0)
+        CK(cudaMemcpyPeerAsync(h->H2.as<double>() + (size_t)g * mine * wblk, h->device, L.H[g] + (size_t)own[r] * wblk, L.device[g],
+                               (size_t)mine * wblk * sizeof(double), h->stream));
+    }
+    CK(cudaEventRecord(L.done[r], h->stream));
+    if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the exchange");
+    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->stream, L.done[g], 0));  // my H is rewritten only after every peer has pulled
+    h->launches += 1;
+    *src_out = AoSource{SRC_RECT_BLOCKED, h->H2.as<double>(), src_out->M, wblk, (int64_t)mine, 0};
+    return 0;
+  }
   int rc = g_nccl.GroupStart();
   for (int g = 0; g < G && rc == 0; ++g) {
     const size_t send_n = (size_t)(own[g + 1] - own[g]) * wblk;   // rows own[g]..own[g+1] of H (row stride wblk)
@@ -856,7 +939,10 @@ int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk
   return 0;
 }
 
-lowdin_it_handle g_dcompat = nullptr;  // context behind the transformer-D compatible entry points
+// Contexts behind the handle-less transformer-D compatible entry points: one per device, on the device selected by
+// LOWDIN_IT_DEVICE or else the calling thread's current CUDA device (a multi-GPU host binds each process/thread to its GPU).
+lowdin_it_handle g_dcompat_dev[64] = {};
+thread_local lowdin_it_handle g_dcompat = nullptr;
 
 }  // namespace
 
@@ -894,12 +980,15 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
-  for (auto &row : h->ao) for (auto &a : row) a.data.release();
-  DevBuf *bufs[] = {&h->st_p, &h->st_q, &h->st_r, &h->st_s, &h->st_v, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
+  for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); }
+  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : h->prof_pool) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -950,58 +1039,118 @@ int lowdin_it_ao_begin(lowdin_it_handle h, int a, int b, int swapped) {
   S.src = (a == b) ? AoSource{SRC_SYM_PACKED, S.data.as<double>(), Ma, 0, 0, 0} : AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
   S.valid = false;
   h->up_a = a; h->up_b = b; h->up_swapped = swapped;
+  h->up_pos = 0; h->up_piece = 0; h->st_busy[0] = h->st_busy[1] = false;
+  CK(h->up_state.ensure(2 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(h->up_state.p, 0xff, sizeof(unsigned long long), h->stream));                              // no terminator yet
+  CK(cudaMemsetAsync(h->up_state.as<unsigned long long>() + 1, 0xff, sizeof(unsigned long long), h->stream));   // no bad entry yet
   CK(cudaEventRecord(h->ev[5], h->stream));
   h->timers[0] = 0;
   return 0;
 }
 
+namespace {
+// One piece of an upload: `cnt` entries (a whole number of stacks of S entries, or one partial stack) whose five arrays start at
+// host pointers p..v, stack t at + t*stride.  The bytes go to a staging buffer on the copy stream; terminator search, index check
+// and scatter run on the library's stream behind them (it_kernels.cuh, scatter_stacks_kernel).
+int push_piece(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s, const double *v, int64_t S,
+               int64_t nstk, int64_t cnt, bool raw_blocks, int64_t call_pos) {
+  const int slot = h->up_piece & 1;
+  ++h->up_piece;
+  if (h->st_busy[slot]) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_scattered[slot], 0));  // the staging buffer's previous piece is scattered
+  uint8_t *st = h->st[slot].as<uint8_t>();
+  StackView w{};
+  if (raw_blocks) {  // contiguous blocks of 24 S bytes: one copy
+    CK(cudaMemcpyAsync(st, p, (size_t)nstk * 24 * S, cudaMemcpyHostToDevice, h->copy_stream));
+    w.p = (const int32_t *)st; w.q = w.p + S; w.r = w.p + 2 * S; w.s = w.p + 3 * S; w.v = (const double *)(st + 16 * S);
+    w.stride_i = 6 * S; w.stride_v = 3 * S;
+  } else {           // five separate arrays, one (partial) stack
+    const int64_t sp = roundup2(cnt);
+    CK(cudaMemcpyAsync(st, p, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(st + 4 * sp, q, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(st + 8 * sp, r, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(st + 12 * sp, s, cnt * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(st + 16 * sp, v, cnt * 8, cudaMemcpyHostToDevice, h->copy_stream));
+    w.p = (const int32_t *)st; w.q = w.p + sp; w.r = w.p + 2 * sp; w.s = w.p + 3 * sp; w.v = (const double *)(st + 16 * sp);
+    w.stride_i = 0; w.stride_v = 0;
+  }
+  w.S = S; w.total = cnt; w.pos0 = call_pos;
+  CK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+  const int na = h->sp[h->up_a].n, nb = h->sp[h->up_b].n;
+  ScatterDst d{h->ao[h->up_a][h->up_b].data.as<double>(), h->up_a == h->up_b, h->up_swapped, na, nb, 0, 0, 1, 0};
+  unsigned long long *state = h->up_state.as<unsigned long long>();
+  const unsigned grid = (unsigned)ceil_div(cnt, 256);
+  find_terminator_kernel<<<grid, 256, 0, h->stream>>>(w, state);
+  scatter_stacks_kernel<<<grid, 256, 0, h->stream>>>(w, d, state);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev_scattered[slot], h->stream));
+  h->st_busy[slot] = true;
+  if (!h->async_push) CK(cudaEventSynchronize(h->ev_copied[slot]));  // the caller may reuse its buffers
+  return 0;
+}
+
+int push_begin_call(lowdin_it_handle h) {
+  if (h->up_a < 0) return fail(h, "ao_push without ao_begin");
+  CK(cudaSetDevice(h->device));
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_scattered[i], cudaEventDisableTiming));
+    }
+  }
+  for (int i = 0; i < 2; ++i) CK(h->st[i].ensure(h->staging_bytes));
+  // the terminator ends the stream of THIS call (one file, C.f90:279-280); the next call is the next file
+  CK(cudaMemsetAsync(h->up_state.p, 0xff, sizeof(unsigned long long), h->stream));
+  return 0;
+}
+}  // namespace
+
 int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s,
                              const double *v, int64_t n) {
   if (!h) return 1;
-  if (h->up_a < 0) return fail(h, "ao_push_stacks without ao_begin");
-  int64_t m = 0;
-  while (m < n && p[m] != -1) ++m;  // terminator (C.f90:279-280)
-  if (m == 0) return 0;
-  const int na = h->sp[h->up_a].n, nb = h->sp[h->up_b].n;
-  const unsigned lim_pq = (unsigned)((h->up_a == h->up_b) ? na : (h->up_swapped ? nb : na));
-  const unsigned lim_rs = (unsigned)((h->up_a == h->up_b) ? na : (h->up_swapped ? na : nb));
-  CK(cudaSetDevice(h->device));
-  CK(h->st_p.ensure(m * 4)); CK(h->st_q.ensure(m * 4)); CK(h->st_r.ensure(m * 4)); CK(h->st_s.ensure(m * 4)); CK(h->st_v.ensure(m * 8));
-  CK(cudaMemcpyAsync(h->st_p.p, p, m * 4, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->st_q.p, q, m * 4, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->st_r.p, r, m * 4, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->st_s.p, s, m * 4, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->st_v.p, v, m * 8, cudaMemcpyHostToDevice, h->stream));
-  // Index check on the host while the copies are in flight (pinned callers): branch-free so that it vectorises;
-  // 1-based index i is valid iff (unsigned)(i-1) < limit.  Nothing is scattered from a stack with a bad entry.
-  unsigned bad = 0;
-  for (int64_t k = 0; k < m; ++k)
-    bad |= (unsigned)(((unsigned)p[k] - 1u) >= lim_pq) | (unsigned)(((unsigned)q[k] - 1u) >= lim_pq) |
-           (unsigned)(((unsigned)r[k] - 1u) >= lim_rs) | (unsigned)(((unsigned)s[k] - 1u) >= lim_rs);
-  if (bad) {
-    cudaStreamSynchronize(h->stream);
-    int64_t k = 0;
-    while (k < m && ((unsigned)p[k] - 1u) < lim_pq && ((unsigned)q[k] - 1u) < lim_pq && ((unsigned)r[k] - 1u) < lim_rs && ((unsigned)s[k] - 1u) < lim_rs) ++k;
-    return fail(h, "AO stack entry " + std::to_string(k) + " has an index outside the basis");
+  if (n < 0 || (n > 0 && (!p || !q || !r || !s || !v))) return fail(h, "ao_push_stacks: bad arguments");
+  if (push_begin_call(h)) return 1;
+  const int64_t cap = (int64_t)(h->staging_bytes / 24) - 2;
+  for (int64_t o = 0; o < n; o += cap) {
+    const int64_t cnt = std::min<int64_t>(cap, n - o);
+    if (push_piece(h, p + o, q + o, r + o, s + o, v + o, cnt, 1, cnt, false, o)) return 1;
   }
-  scatter_stacks_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, h->stream>>>(
-      h->st_p.as<int32_t>(), h->st_q.as<int32_t>(), h->st_r.as<int32_t>(), h->st_s.as<int32_t>(), h->st_v.as<double>(), m,
-      h->up_a == h->up_b, h->up_swapped, na, nb, h->ao[h->up_a][h->up_b].data.as<double>());
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+  h->up_pos += n;
+  return 0;
+}
+
+int lowdin_it_ao_push_blocks(lowdin_it_handle h, const void *blocks, int64_t nblocks, int stack_size) {
+  if (!h) return 1;
+  if (nblocks < 0 || stack_size < 1 || (nblocks > 0 && !blocks)) return fail(h, "ao_push_blocks: bad arguments");
+  if ((size_t)stack_size * 24 > h->staging_bytes) return fail(h, "ao_push_blocks: stack larger than the staging buffer");
+  if (push_begin_call(h)) return 1;
+  const int64_t S = stack_size, per = (int64_t)(h->staging_bytes / (24 * (size_t)S));
+  const uint8_t *src = (const uint8_t *)blocks;
+  for (int64_t t = 0; t < nblocks; t += per) {
+    const int64_t nb_ = std::min<int64_t>(per, nblocks - t);
+    if (push_piece(h, (const int32_t *)(src + (size_t)t * 24 * S), nullptr, nullptr, nullptr, nullptr, S, nb_, nb_ * S, true, t * S)) return 1;
+  }
+  h->up_pos += nblocks * S;
   return 0;
 }
 
 int lowdin_it_ao_end(lowdin_it_handle h) {
   if (!h) return 1;
   if (h->up_a < 0) return fail(h, "ao_end without ao_begin");
+  CK(cudaSetDevice(h->device));
+  unsigned long long state[2] = {0, 0};
+  CK(cudaMemcpyAsync(state, h->up_state.p, sizeof(state), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[0], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[0]));
   h->timers[0] = ms * 1e-3;
-  h->ao[h->up_a][h->up_b].valid = true;
+  const int a = h->up_a, b = h->up_b;
   h->up_a = h->up_b = -1;
+  if (state[1] != ~0ull)  // nothing of a list with a bad entry is trusted
+    return fail(h, "AO stack entry " + std::to_string(state[1]) + " (1-based, counted within its push call) has an index outside the basis");
+  h->ao[a][b].valid = true;
   return 0;
 }
 
@@ -1013,6 +1162,54 @@ int lowdin_it_ao_set_generator(lowdin_it_handle h, int a, int b, int kind, uint6
   S.data.release();
   S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed, kind} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed, kind};
   S.valid = true;
+  return 0;
+}
+
+int lowdin_it_ao_set_rankk(lowdin_it_handle h, int a, int b, int K, const double *La, const double *Lb) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].n || !h->sp[b].n) return fail(h, "ao_set_rankk: species not set");
+  if (K < 1 || K > RANKK || !La || (a != b && !Lb)) return fail(h, "ao_set_rankk: 1 <= K <= 8 factor sets required");
+  CK(cudaSetDevice(h->device));
+  AoSet &S = h->ao[a][b];
+  S.data.release();
+  const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  CK(S.fa.ensure((size_t)RANKK * Ma * sizeof(double)));
+  CK(cudaMemsetAsync(S.fa.p, 0, (size_t)RANKK * Ma * sizeof(double), h->stream));
+  CK(cudaMemcpyAsync(S.fa.p, La, (size_t)K * Ma * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const double *fb = S.fa.as<double>();
+  if (a != b) {
+    CK(S.fb.ensure((size_t)RANKK * Mb * sizeof(double)));
+    CK(cudaMemsetAsync(S.fb.p, 0, (size_t)RANKK * Mb * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(S.fb.p, Lb, (size_t)K * Mb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    fb = S.fb.as<double>();
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  S.src = AoSource{SRC_RANKK, S.fa.as<double>(), Ma, 0, (a == b) ? Ma : Mb, 0, LOWDIN_IT_GEN_RANKK, fb};
+  S.valid = true;
+  return 0;
+}
+
+int lowdin_it_ao_materialize(lowdin_it_handle h, int a, int b) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->ao[a][b].valid) return fail(h, "ao_materialize: AO set not available");
+  CK(cudaSetDevice(h->device));
+  AoSet &S = h->ao[a][b];
+  const AoSource src = S.src;
+  if (src.kind != SRC_HASH_SYM && src.kind != SRC_HASH_RECT && src.kind != SRC_RANKK) return fail(h, "ao_materialize: the AO set is not a generated one");
+  const bool intra = (a == b);
+  const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  const size_t count = intra ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb);
+  CK(S.data.ensure(count * sizeof(double)));
+  const unsigned grid = (unsigned)std::min<int64_t>(Mb, (int64_t)h->num_sms * 16);
+  double *dst = S.data.as<double>();
+  switch (src.kind) {
+    case SRC_HASH_SYM: materialize_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(src, 1, Ma, Ma, dst); break;
+    case SRC_HASH_RECT: materialize_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(src, 0, Ma, Mb, dst); break;
+    default: materialize_kernel<SRC_RANKK><<<grid, 256, 0, h->stream>>>(src, intra ? 1 : 0, Ma, intra ? Ma : Mb, dst); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  S.src = intra ? AoSource{SRC_SYM_PACKED, dst, Ma, 0, 0, 0} : AoSource{SRC_RECT, dst, Ma, Ma, Mb, 0};
   return 0;
 }
 
@@ -1051,7 +1248,8 @@ int lowdin_it_download_pairs(lowdin_it_handle h, int64_t *ij, int64_t *kl, doubl
   CK(cudaEventRecord(h->ev[1], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timers[5] = ms * 1e-3;
-  int ov = 0; CK(cudaMemcpy(&ov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
+  int ov = 0;
+  if (h->overflow.p) CK(cudaMemcpy(&ov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
   if (ov) return fail(h, "result buffer overflow");
   return 0;
 }
@@ -1071,6 +1269,9 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
   CK(cudaEventRecord(h->ev[1], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->timers[5] = ms * 1e-3;
+  int ov = 0;
+  if (h->overflow.p) CK(cudaMemcpy(&ov, h->overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ov) return fail(h, "result buffer overflow");
   return 0;
 }
 
@@ -1156,6 +1357,12 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->split_row_tail = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_FRAG_PERM:
       h->frag_perm = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_ASYNC_PUSH:
+      h->async_push = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_STAGING_BYTES:
+      if (value < (1 << 16)) return fail(h, "staging buffer too small");
+      if (h->up_a >= 0) return fail(h, "staging size cannot change during an upload");
+      h->staging_bytes = (size_t)value; h->st[0].release(); h->st[1].release(); return 0;
     case LOWDIN_IT_OPT_BENCH_GEN:
       if (value != 1 && value != 2) return fail(h, "generator kind must be 1 or 2");
       h->bench_gen = (int)value; return 0;
@@ -1185,8 +1392,15 @@ int lowdin_it_timers(lowdin_it_handle h, double out[8]) {
 // ---- transformer-D compatible entry points --------------------------------------------------
 static int dcompat_ctx() {
   g_create_error.clear();
-  if (g_dcompat) { g_dcompat->err.clear(); return 0; }
-  return lowdin_it_create(0, &g_dcompat);
+  int dev = 0;
+  if (const char *e = getenv("LOWDIN_IT_DEVICE")) dev = atoi(e);
+  else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (dev < 0 || dev >= 64) return fail(nullptr, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_attr_mutex);
+  if (!g_dcompat_dev[dev] && lowdin_it_create(dev, &g_dcompat_dev[dev])) return 1;
+  g_dcompat = g_dcompat_dev[dev];
+  g_dcompat->err.clear();
+  return 0;
 }
 
 int lowdin_it_transform_all(const double *coeff, double *ints, int nao) {
@@ -1273,7 +1487,60 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
   return 0;
 }
 
+int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks) {
+  if (!handles || nranks < 1 || nranks > 16) return fail(nullptr, "comm_init_local: 1..16 handles required");
+  for (int r = 0; r < nranks; ++r) if (!handles[r]) return fail(nullptr, "comm_init_local: null handle");
+  if (nranks == 1) { handles[0]->rank = 0; handles[0]->nranks = 1; handles[0]->lgroup.reset(); return 0; }
+  auto L = std::make_shared<LocalGroup>();
+  L->n = nranks;
+  for (int r = 0; r < nranks; ++r) {
+    lowdin_it_handle h = handles[r];
+    if (h->comm) return fail(h, "comm_init_local: the handle already belongs to an NCCL communicator");
+    CK(cudaSetDevice(h->device));
+    L->device[r] = h->device;
+    CK(cudaEventCreateWithFlags(&L->ready[r], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&L->done[r], cudaEventDisableTiming));
+    for (int o = 0; o < r; ++o)
+      if (handles[o]->device != h->device) {  // direct peer access where the topology has it (the copies work either way)
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, h->device, handles[o]->device);
+        if (can) { cudaDeviceEnablePeerAccess(handles[o]->device, 0); cudaGetLastError(); }
+        cudaSetDevice(handles[o]->device);
+        cudaDeviceCanAccessPeer(&can, handles[o]->device, h->device);
+        if (can) { cudaDeviceEnablePeerAccess(h->device, 0); cudaGetLastError(); }
+        cudaSetDevice(h->device);
+      }
+  }
+  for (int r = 0; r < nranks; ++r) { handles[r]->rank = r; handles[r]->nranks = nranks; handles[r]->lgroup = L; }
+  return 0;
+}
+
 // ---- stand-alone kernel timing / debug --------------------------------------------------------
+// First half only (E.f90:1043-1132) of slabs [slab0, slab0 + nslabs): out[k][z] = half-transformed value of the k-th window pair
+// (convention order: ijmap order for E) and slab slab0 + z, with E's |t| <= drop_tol -> 0.  Parity checks of the first half at
+// sizes where no CPU can run the whole transform (bench.py compares a sample of slabs with the oracle at N_bf = 1500).
+int lowdin_it_debug_first_half(lowdin_it_handle h, int a, int b, const int win[8], int conv, double drop_tol, int64_t slab0, int nslabs,
+                               double *out, int64_t *npairs_out) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  Plan pl;
+  if (build_plan(h, a, b, win, conv, 0, pl)) return 1;
+  if (slab0 < 0 || nslabs < 1 || slab0 + nslabs > pl.nslabs1) return fail(h, "debug_first_half: slab range out of bounds");
+  PassTables pt;
+  build_pass(pl, 0, std::max(pl.h1.nf, 1), pt);
+  if (npairs_out) *npairs_out = pt.nslots;
+  if (pt.nslots == 0 || !out) return 0;
+  if (upload_i32(h, h->tab, pt.table)) return 1;
+  CK(h->H.ensure((size_t)pt.nslots * nslabs * sizeof(double)));
+  CK(cudaMemsetAsync(h->H.p, 0, (size_t)pt.nslots * nslabs * sizeof(double), h->stream));
+  if (first_half(h, pl, pt, slab0, nslabs, h->H.as<double>(), nslabs, 0, conv == LOWDIN_IT_CONV_E ? drop_tol : -1.0)) return 1;
+  std::vector<double> tmp((size_t)pt.nslots * nslabs);
+  CK(cudaMemcpyAsync(tmp.data(), h->H.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < pt.nslots; ++k) memcpy(out + (size_t)k * nslabs, tmp.data() + (size_t)pt.order[k] * nslabs, (size_t)nslabs * sizeof(double));
+  return 0;
+}
+
 int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, int64_t k, int iters, double *ms_per_launch, double *check) {
   if (!h) return 1;
   CK(cudaSetDevice(h->device));

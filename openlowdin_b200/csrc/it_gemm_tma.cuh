@@ -56,11 +56,24 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol error becomes a kernel fault (reported through the C ABI) instead of a hung device.
+// Bounded wait: a protocol error becomes a kernel fault (reported through the C ABI) instead of a hung device.  The bound
+// is ELAPSED TIME (20 s of %globaltimer, looked at every 2^16 failed polls), not a poll count: a legitimately long stall
+// (time-slicing under MPS, a profiler replay, a debugger) must not kill the context.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity))
-    if (++spins > (1u << 24)) __trap();
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xffffu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),

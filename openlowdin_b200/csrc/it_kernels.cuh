@@ -28,9 +28,12 @@ enum SrcKind : int {
   SRC_RECT = 1,        // data[slab*ld + pair]   (inter AO storage (rs-1)*M_a+pq, C.f90:882; and the half-transformed H)
   SRC_HASH_SYM = 2,    // generated, key = hi*M + lo
   SRC_HASH_RECT = 3,   // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
-  SRC_RECT_BLOCKED = 4 // data[((pair/ld)*aux + slab)*ld + pair%ld]: the half-transformed chunk as it arrives from the
+  SRC_RECT_BLOCKED = 4,// data[((pair/ld)*aux + slab)*ld + pair%ld]: the half-transformed chunk as it arrives from the
                        // all-to-all, one [slots][ld] block per sending rank (aux = slots per block)
+  SRC_RANKK = 5        // generated, kind K: (slab | pair) = sum_{k<8} data2[k*aux + slab] * data[k*M + pair]
+                       // (rank-8 separable tensor with closed-form MO integrals; intra: data2 == data, aux == M)
 };
+constexpr int RANKK = 8;  // number of separable terms of kind K (shorter expansions are zero padded)
 
 struct AoSource {
   int kind;
@@ -39,7 +42,8 @@ struct AoSource {
   int64_t ld;   // SRC_RECT row stride
   int64_t aux;  // SRC_HASH_RECT: number of slabs (M_b)
   uint64_t seed;
-  int gen;      // generated sources: 1 = splitmix64 (kind H), 2 = mul-fold-mul (kind F)
+  int gen;      // generated sources: 1 = splitmix64 (kind H), 2 = mul-fold-mul (kind F), 3 = rank-K separable (kind K)
+  const double *data2;  // SRC_RANKK: pair-vector factors of the SLAB species [RANKK][aux]
 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -108,11 +112,22 @@ struct SlabReader {
   uint32_t ld, rows;
   uint64_t seed;
   int gen;
+  double coef[KIND == SRC_RANKK ? RANKK : 1];  // SRC_RANKK: the slab's factor of every separable term
   __device__ __forceinline__ SlabReader(const AoSource &src, int64_t slab_) : slab(slab_), M(src.M), ld((uint32_t)src.ld), rows((uint32_t)src.aux), seed(src.seed), gen(src.gen) {
     base = (KIND == SRC_RECT) ? src.data + slab_ * src.ld : src.data;
     if (KIND == SRC_HASH_RECT) M = src.aux;
+    if (KIND == SRC_RANKK) {
+#pragma unroll
+      for (int k = 0; k < RANKK; ++k) coef[k] = __ldg(src.data2 + (int64_t)k * src.aux + slab_);
+    }
   }
   __device__ __forceinline__ double operator()(int64_t pair) const {
+    if (KIND == SRC_RANKK) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < RANKK; ++k) v = fma(coef[k], __ldg(base + (int64_t)k * M + pair), v);
+      return v;
+    }
     if (KIND == SRC_RECT) return __ldg(base + pair);
     if (KIND == SRC_RECT_BLOCKED) {
       const uint32_t p = (uint32_t)pair, blk = p / ld;
@@ -176,25 +191,95 @@ __global__ void __launch_bounds__(256) expand_block_kernel(AoSource src, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// AO list scatter (C.f90:262-273 intra; :879-883 / :947-951 inter)
+// AO list scatter (C.f90:262-273 intra; :879-883 / :947-951 inter).  Everything the reference's reader does per
+// entry happens here, on the device: the terminator test (p = -1 ends the stream, C.f90:279-280), the index range
+// check and the store to the packed position.  The host only moves bytes.
+//   StackView: `nstk` stacks of S entries each; stack t's arrays are p/q/r/s/v + t*stride_{i,v}: one view covers both
+//   the five separate arrays of lowdin_it_ao_push_stacks (one stack of n entries) and the raw .ints blocks
+//   (int32 p[S] q[S] r[S] s[S]; real64 v[S] per block, Libint2Iface.cpp:3414-3426) of lowdin_it_ao_push_blocks.
+//   state[0] = first terminator position seen so far (entries at or after it are ignored), state[1] = 1-based position
+//   of an entry with an index outside the basis (0: none).
 // ---------------------------------------------------------------------------------------------
-__global__ void scatter_stacks_kernel(const int32_t *__restrict__ p, const int32_t *__restrict__ q,
-                                      const int32_t *__restrict__ r, const int32_t *__restrict__ s,
-                                      const double *__restrict__ v, int64_t n, int intra, int swapped, int na, int nb,
-                                      double *__restrict__ dst) {
-  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const int64_t Ma = (int64_t)na * (na + 1) / 2;
-  if (intra) {
-    int64_t pq = pair0(p[k] - 1, q[k] - 1, na), rs = pair0(r[k] - 1, s[k] - 1, na);
-    int64_t lo = pq < rs ? pq : rs, hi = pq < rs ? rs : pq;
-    dst[lo * Ma - (lo * (lo + 1)) / 2 + hi] = v[k];
-  } else if (!swapped) {
-    int64_t pq = pair0(p[k] - 1, q[k] - 1, na), rs = pair0(r[k] - 1, s[k] - 1, nb);
-    dst[rs * Ma + pq] = v[k];
+struct StackView {
+  const int32_t *p, *q, *r, *s;
+  const double *v;
+  int64_t stride_i, stride_v;  // per stack, in elements of the respective type
+  int64_t S, total;            // entries per stack, entries in the view
+  int64_t pos0;                // position of the view's first entry in the whole upload (for the error report)
+};
+struct ScatterDst {
+  double *dst;
+  int intra, swapped, na, nb;
+  // row-sharded storage (multi-GPU): a rank keeps full M-vectors of the slabs it owns; see SlabOwner
+  int sharded, logB, G, rank;
+};
+__device__ __forceinline__ void stack_entry(const StackView &w, int64_t k, int &p, int &q, int &r, int &s, double &v) {
+  const int64_t t = k / w.S, e = k - t * w.S;
+  p = __ldg(w.p + t * w.stride_i + e); q = __ldg(w.q + t * w.stride_i + e);
+  r = __ldg(w.r + t * w.stride_i + e); s = __ldg(w.s + t * w.stride_i + e);
+  v = __ldg(w.v + t * w.stride_v + e);
+}
+// pass 1: position of the first terminator of the view (atomicMin into state[0])
+__global__ void __launch_bounds__(256) find_terminator_kernel(StackView w, unsigned long long *__restrict__ state) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= w.total) return;
+  const int64_t t = k / w.S, e = k - t * w.S;
+  if (__ldg(w.p + t * w.stride_i + e) == -1) atomicMin(state, (unsigned long long)(w.pos0 + k));
+}
+// Owner of a slab under the block-cyclic distribution of the multi-GPU first half (blocks of 2^logB consecutive slabs,
+// block b on rank b % G), and its row in the owner's local storage.
+__host__ __device__ __forceinline__ int slab_owner(int64_t slab, int logB, int G) { return (int)((slab >> logB) % G); }
+__host__ __device__ __forceinline__ int64_t slab_local(int64_t slab, int logB, int G) {
+  return (((slab >> logB) / G) << logB) + (slab & ((1ll << logB) - 1));
+}
+__host__ __device__ __forceinline__ int64_t slab_global(int64_t local, int logB, int G, int rank) {
+  return ((((local >> logB) * G) + rank) << logB) + (local & ((1ll << logB) - 1));
+}
+// pass 2: scatter the entries before the terminator
+__global__ void __launch_bounds__(256) scatter_stacks_kernel(StackView w, ScatterDst d, unsigned long long *__restrict__ state) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= w.total) return;
+  if ((unsigned long long)(w.pos0 + k) >= state[0]) return;
+  int p, q, r, s; double v;
+  stack_entry(w, k, p, q, r, s, v);
+  const unsigned lim_pq = (unsigned)(d.intra ? d.na : (d.swapped ? d.nb : d.na));
+  const unsigned lim_rs = (unsigned)(d.intra ? d.na : (d.swapped ? d.na : d.nb));
+  if ((unsigned)(p - 1) >= lim_pq || (unsigned)(q - 1) >= lim_pq || (unsigned)(r - 1) >= lim_rs || (unsigned)(s - 1) >= lim_rs) {
+    atomicMin(state + 1, (unsigned long long)(w.pos0 + k + 1));
+    return;
+  }
+  const int64_t Ma = (int64_t)d.na * (d.na + 1) / 2;
+  if (d.intra) {
+    const int64_t pq = pair0(p - 1, q - 1, d.na), rs = pair0(r - 1, s - 1, d.na);
+    if (!d.sharded) {
+      const int64_t lo = pq < rs ? pq : rs, hi = pq < rs ? rs : pq;
+      d.dst[lo * Ma - (lo * (lo + 1)) / 2 + hi] = v;
+    } else {  // full rows of the owned slabs: the entry lands in row pq (if owned) and in row rs (if owned)
+      if (slab_owner(pq, d.logB, d.G) == d.rank) d.dst[slab_local(pq, d.logB, d.G) * Ma + rs] = v;
+      if (slab_owner(rs, d.logB, d.G) == d.rank) d.dst[slab_local(rs, d.logB, d.G) * Ma + pq] = v;
+    }
   } else {
-    int64_t pq = pair0(p[k] - 1, q[k] - 1, nb), rs = pair0(r[k] - 1, s[k] - 1, na);
-    dst[pq * Ma + rs] = v[k];
+    int64_t slab, pair;  // inter AO storage: slab = pair id on species b, pair = pair id on species a (C.f90:882, :947-951)
+    if (!d.swapped) { pair = pair0(p - 1, q - 1, d.na); slab = pair0(r - 1, s - 1, d.nb); }
+    else { slab = pair0(p - 1, q - 1, d.nb); pair = pair0(r - 1, s - 1, d.na); }
+    if (!d.sharded) d.dst[slab * Ma + pair] = v;
+    else if (slab_owner(slab, d.logB, d.G) == d.rank) d.dst[slab_local(slab, d.logB, d.G) * Ma + pair] = v;
+  }
+}
+
+// Generated AO set -> stored layout on the device (tests and the stored-AO bench leg at sizes whose list cannot come from a host):
+// intra: packed row `slab` holds pairs slab..M-1; inter: rectangular [slab][pair].  grid.x strides over slabs.
+template <int KIND>
+__global__ void __launch_bounds__(256) materialize_kernel(AoSource src, int intra, int64_t Ma, int64_t nslabs, double *__restrict__ dst) {
+  for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+    const SlabReader<KIND> rd(src, slab);
+    if (intra) {
+      double *row = dst + (slab * Ma - (slab * (slab + 1)) / 2);
+      for (int64_t pair = slab + threadIdx.x; pair < Ma; pair += blockDim.x) row[pair] = rd(pair);
+    } else {
+      double *row = dst + slab * Ma;
+      for (int64_t pair = threadIdx.x; pair < Ma; pair += blockDim.x) row[pair] = rd(pair);
+    }
   }
 }
 

@@ -568,3 +568,38 @@ double orc_e_first_half_sample(uint64_t seed, int n, const double *C, int ldc, c
   free(x1); free(x2); free(ijmap);
   return chk;
 }
+
+/* The same first half, returning the values: out[ij * npq + z] for window pair ij (ijmap order, E.f90:878-884) and slab
+ * pq0 + z, with |t| <= 1e-10 -> 0 (the values E would not write to its bucket file, E.f90:1113).  gen_kind 1 = kind H,
+ * 2 = kind F.  Checked against the device's first half at N_bf = 1500 (bench.py) and in the GPU tests. */
+int64_t orc_e_first_half_values(int gen_kind, uint64_t seed, int n, const double *C, int ldc, const int *win, int64_t pq0,
+                                int64_t npq, int nthreads, double *out) {
+  int64_t M = (int64_t)n * (n + 1) / 2;
+  int32_t *x1 = malloc(sizeof(int32_t) * M), *x2 = malloc(sizeof(int32_t) * M);
+  build_xypair(n, x1, x2);
+  int64_t nij = build_pairmap(win[0], win[1], win[2], win[3], n, NULL);
+  int64_t *ijmap = malloc(sizeof(int64_t) * (nij + 1));
+  build_pairmap(win[0], win[1], win[2], win[3], n, ijmap);
+  if (nthreads < 1) nthreads = 1;
+  if (out) {
+#pragma omp parallel num_threads(nthreads)
+    {
+      double *slab = malloc(sizeof(double) * M), *tB = malloc(sizeof(double) * n * n),
+             *tBC = calloc((size_t)n * n, sizeof(double)), *res = malloc(sizeof(double) * (nij + 1));
+#pragma omp for schedule(dynamic)
+      for (int64_t z = 0; z < npq; ++z) {
+        int64_t pq = pq0 + z + 1;
+        if (pq > M) continue;
+        for (int64_t rs = 1; rs <= M; ++rs) {
+          int64_t hi = pq >= rs ? pq : rs, lo = pq >= rs ? rs : pq;
+          slab[rs - 1] = orc_gen_value(gen_kind, seed, (uint64_t)((hi - 1) * M + (lo - 1)));
+        }
+        e_half_slab(n, C, ldc, slab, x1, x2, win[2], win[3], ijmap, nij, tB, tBC, res);
+        for (int64_t ij = 0; ij < nij; ++ij) out[ij * npq + z] = fabs(res[ij]) > 1e-10 ? res[ij] : 0.0;
+      }
+      free(slab); free(tB); free(tBC); free(res);
+    }
+  }
+  free(x1); free(x2); free(ijmap);
+  return nij;
+}

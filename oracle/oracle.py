@@ -94,6 +94,8 @@ def lib():
         L.orc_gen_value.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
         L.orc_e_first_half_sample.restype = C.c_double
         L.orc_e_first_half_sample.argtypes = [C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int]
+        L.orc_e_first_half_values.restype = C.c_int64
+        L.orc_e_first_half_values.argtypes = [C.c_int, C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.orc_reader_pairs_intra.restype = None
         L.orc_reader_pairs_intra.argtypes = [_i64p, _i64p, _f64p, C.c_int64, C.c_int, _f64p]
         L.orc_reader_quads_intra.restype = None
@@ -607,6 +609,32 @@ def e_first_half_sample(seed, Cm, win, pq0, npq, nthreads=1):
     """CPU baseline sample: first half of transformer E on npq slabs of the kind-H tensor."""
     n = Cm.shape[0]
     return lib().orc_e_first_half_sample(seed, n, np.asfortranarray(Cm), n, _win(win), pq0, npq, nthreads)
+
+
+def e_first_half_values(seed, Cm, win, pq0, npq, nthreads=1, gen_kind=1):
+    """First half of transformer E (E.f90:1043-1132) on slabs [pq0, pq0+npq) of the kind-H/F tensor: array [n_ij, npq]
+    in ijmap order, |t| <= 1e-10 zeroed (E.f90:1113)."""
+    n = Cm.shape[0]
+    Cf = np.asfortranarray(Cm)
+    nij = lib().orc_e_first_half_values(gen_kind, seed, n, Cf, n, _win(win), pq0, npq, nthreads, None)
+    out = np.zeros((nij, npq))
+    lib().orc_e_first_half_values(gen_kind, seed, n, Cf, n, _win(win), pq0, npq, nthreads, out.ctypes.data)
+    return out
+
+
+def rankk_factors(seed, n, K=8):
+    """The K symmetric N x N factor matrices of a kind-K tensor and their pair vectors [K, M] in xy order (mu <= nu)."""
+    rng = np.random.default_rng(seed)
+    L = rng.uniform(-1, 1, (K, n, n))
+    L = 0.5 * (L + L.transpose(0, 2, 1))
+    iu = np.triu_indices(n)
+    return L, np.ascontiguousarray(L[:, iu[0], iu[1]])
+
+
+def rankk_mo_factors(L, Cm, rows, cols):
+    """T^k[p,q] = (C^T L^k C)[rows, cols]: the closed-form factors of the MO integrals of a kind-K tensor, [K, len(rows), len(cols)]."""
+    Cm = np.asarray(Cm)
+    return np.stack([Cm[:, rows].T @ (Lk @ Cm[:, cols]) for Lk in L])
 
 
 # ----------------------------------------------------------------------------------------

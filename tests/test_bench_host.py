@@ -48,7 +48,7 @@ class _FakePinned:
 
 
 class _FakeTorch:
-    int32, int64, float64 = np.int32, np.int64, np.float64
+    int32, int64, float64, uint8 = np.int32, np.int64, np.float64, np.uint8
 
     @staticmethod
     def empty(n, dtype):
@@ -95,6 +95,18 @@ class _FakeLib:
         while m < n and p[m] != -1:
             m += 1
         for dst, src in zip(self.list, a[1:6]):
+            dst.append(np.array(src[:m]))
+        return 0
+
+    def lowdin_it_ao_push_blocks(self, *a):
+        self._conv("lowdin_it_ao_push_blocks", a)
+        nblk, S = a[2], a[3]
+        raw = np.ctypeslib.as_array(C.cast(a[1], C.POINTER(C.c_uint8)), (nblk * 24 * S,)).reshape(nblk, 24 * S)
+        idx = [raw[:, 4 * S * k:4 * S * (k + 1)].view(np.int32).ravel() for k in range(4)]
+        v = raw[:, 16 * S:].view(np.float64).ravel()
+        m = int(np.argmax(idx[0] == -1))
+        assert idx[0][m] == -1
+        for dst, src in zip(self.list, idx + [v]):
             dst.append(np.array(src[:m]))
         return 0
 
@@ -166,6 +178,22 @@ def test_stored_ao_e2e_leg_with_stand_in_context(O, monkeypatch):
     assert cpu["transformer_e_port_s"] > 0 and cpu["transformer_c_port_s"] > 0
     import json
     json.dumps(out), json.dumps(cpu)          # everything that reaches the bench line is JSON-serialisable
+
+
+def test_stored_ao_e2e_leg_raw_blocks_mode(O):
+    """The same leg pushing the list as the raw bytes of a .ints stream (one lowdin_it_ao_push_blocks call per step)."""
+    real = capi.load()
+    fake = _FakeLib(O, real)
+
+    class FakeTransformer(capi.Transformer):
+        def __init__(self, device=0):
+            self.L, self.h, self.n = fake, C.c_void_p(1), {}
+
+    ol = types.SimpleNamespace(Transformer=FakeTransformer)
+    n, occ = 7, 2
+    out = bench.stored_ao_e2e(_FakeTorch, ol, capi, 0, n, occ, steps=1, mode="blocks", stack_size=37)
+    assert out["same_index_lists_as_generated"] is True and out["max_abs_diff_vs_generated"] == 0.0
+    assert fake.calls.count("lowdin_it_ao_push_blocks") == 2 and "lowdin_it_ao_push_stacks" not in fake.calls
 
 
 def test_transformer_d_leg_with_stand_in(O):

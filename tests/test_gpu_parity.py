@@ -343,3 +343,20 @@ def test_generator_kinds_and_fused_kernel_variants(O, T, kind, variant):
     T.set_species(1, O.random_orthonormal(na, 1)); T.set_species(2, O.random_orthonormal(nb, 2))
     T.set_generator(1, 2, seed, kind)
     assert np.array_equal(T.debug_expand(1, 2, 0, O.npairs(nb)), rect.reshape(O.npairs(nb), O.npairs(na))[:, O.pair_table(na)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("conv", [ol.CONV_C, ol.CONV_E])
+def test_empty_windows_on_a_fresh_handle(O, conv):
+    """No window pair at all (one-function species under MP2), and a first pair with slots but an empty second window:
+    a valid transform with zero integrals, downloadable on a handle that has never produced a result."""
+    for n, win in ((1, [2, 1, 1, 1, 2, 1, 1, 1]), (4, [3, 4, 1, 2, 5, 4, 1, 2])):
+        T = ol.Transformer(0)
+        try:
+            T.set_species(0, O.random_orthonormal(n, n) if n > 1 else np.ones((1, 1)))
+            T.set_generator(0, 0, 3)
+            out = T.transform(0, 0, win, conv)
+            assert all(len(x) == 0 for x in out)
+            assert np.all(T.transform_stream(0, 0, win, conv) == 0.0)
+        finally:
+            T.close()

@@ -228,6 +228,23 @@ def test_one_species_file_to_file(O, HT, tmp_path, method, mode):
 
 
 @pytest.mark.parametrize("method", ["C", "E"])
+def test_empty_window_writes_a_terminator_only_file(O, HT, tmp_path, method):
+    """A one-function species under MP2 has the virtual window 2..1: the reference writes a moint.dat holding only the terminator
+    stack (TransformIntegralsC.f90:450-456, TransformIntegralsE.f90:1263-1268); so must the drop-in, on a FRESH context."""
+    n, occ, S = 1, 1, 16
+    one = np.array([1], np.int32)
+    _split_to_files(tmp_path, "H_1", (one, one, one, one, np.array([0.75])), 1, S)
+    ctl = capi.host_control(method, "MP2", stack=S, nfiles=1, scratch_dir=str(tmp_path))
+    sp = capi.host_species("H_1", 1, n, occ, coeff=np.ones((1, 1)))
+    cnt = capi.host_transform_one_species(HT, ctl, sp)
+    assert cnt == 0
+    path = str(tmp_path / "H_1moint.dat")
+    got = read_moint_quads(path, S) if method == "C" else read_moint_pairs(path, S)
+    assert len(got[-1]) == 0
+    assert len(list(_records(open(path, "rb").read()))) == 1
+
+
+@pytest.mark.parametrize("method", ["C", "E"])
 def test_two_species_file_to_file_both_call_orders(O, HT, tmp_path, method):
     T = HT
     na, nb, oa, ob, S = 9, 7, 3, 1, 50
