@@ -454,7 +454,8 @@ def main():
     ap.add_argument("--gen", type=int, default=GEN_KIND, help="synthetic AO generator: 1 = kind H (splitmix64), 2 = kind F (mul-fold-mul)")
     ap.add_argument("--q1-variant", type=int, default=0, help="fused first-quarter kernel variant (0 = library default)")
     ap.add_argument("--gemm-variant", type=int, default=0, help="quarter-transform GEMM variant (0 = library default)")
-    ap.add_argument("--frag-perm", type=int, default=0, help="1 = conflict-free fragment-row permutation of the TMA kernels (experimental)")
+    ap.add_argument("--frag-perm", type=int, default=-1, help="fragment-row permutation of the TMA kernels: 0 / 1 (-1 = library default)")
+    ap.add_argument("--q3-red", type=int, default=-1, help="third-quarter accumulation by red.global.add.f64: 0 / 1 (-1 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -503,8 +504,10 @@ def main():
         T.set_option(T.OPT_Q1_VARIANT, args.q1_variant)
     if args.gemm_variant:
         T.set_option(T.OPT_GEMM_VARIANT, args.gemm_variant)
-    if args.frag_perm:
-        T.set_option(T.OPT_FRAG_PERM, 1)
+    if args.frag_perm >= 0:
+        T.set_option(T.OPT_FRAG_PERM, args.frag_perm)
+    if args.q3_red >= 0:
+        T.set_option(T.OPT_Q3_RED, args.q3_red)
     T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 

@@ -136,13 +136,17 @@ int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks);
 /* ---- tuning ----------------------------------------------------------------------- */
 #define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
 #define LOWDIN_IT_OPT_CHUNK_COLS 2      /* cap on AO-pair columns per chunk of the half-transformed block (0 = from free HBM) */
-#define LOWDIN_IT_OPT_Q1_VARIANT 3      /* fused generation + first quarter: 1 = shared-memory ring, 2 = L1 path without barriers, 3 = warp-specialised (8 generator + 8 DMMA warps, TMA), 4 = 4 vectorised generator warps + 8 DMMA warps with register double-buffering */
+#define LOWDIN_IT_OPT_Q1_VARIANT 3      /* fused generation + first quarter: 1 = shared-memory ring, 2 = L1 path without barriers, 3 = warp-specialised (8 generator + 8 DMMA warps, TMA), 4 = 4 vectorised generator warps + 8 DMMA warps with register double-buffering, 5 = 256-row tiles with 32-row DMMA warps and setmaxnreg register rebalancing */
 #define LOWDIN_IT_OPT_BENCH_GEN 4       /* generator kind used by lowdin_it_kernel_bench kind 2 */
 #define LOWDIN_IT_OPT_GEMM_VARIANT 5    /* quarter-transform GEMM: 1 = cp.async ring + block barrier, 2 = TMA + mbarrier, persistent */
 #define LOWDIN_IT_OPT_SPLIT_ROW_TAIL 6  /* TMA GEMM: 1 (default) = the <= 80-row tail of a few-rows x many-columns product runs as a second, operand-swapped launch instead of a padded 128-row tile */
-#define LOWDIN_IT_OPT_FRAG_PERM 7       /* TMA kernels: 1 = fragment rows permuted so that the 128-bit shared loads of a quarter-warp are conflict-free (default 0 until measured on a GPU) */
+#define LOWDIN_IT_OPT_FRAG_PERM 7       /* TMA kernels: 1 = fragment rows permuted so that the 128-bit shared loads of a quarter-warp are conflict-free (default 1; 0 = the unpermuted mapping, bit-identical results) */
 #define LOWDIN_IT_OPT_ASYNC_PUSH 8      /* 1 = the caller leaves pushed host buffers untouched until lowdin_it_ao_end: pushes return without waiting for their copies */
 #define LOWDIN_IT_OPT_STAGING_BYTES 9   /* size of each of the two device staging buffers of the AO upload (default 96 MiB) */
+#define LOWDIN_IT_OPT_AO_LIST 11        /* 1 = the uploads that follow keep the canonical AO list on the device as it comes (16 bytes per stored integral, no
+                                         * M(M+1)/2 dense tensor); the first quarter is then LIST-DRIVEN: every integral is scattered with its <= 4 images into the
+                                         * quarter-transformed slabs (the DIRECT first quarter of Libint2Iface.cpp:793-853 / TransformIntegralsC.f90:545-558) */
+#define LOWDIN_IT_OPT_Q3_RED 10         /* third-quarter accumulation into T3: 0 = read-modify-write epilogue staged through shared memory, 1 = one red.global.add.f64 per element */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 
 /* ---- instrumentation -------------------------------------------------------------- */
@@ -166,6 +170,8 @@ int lowdin_it_debug_gemm(lowdin_it_handle h, const double *A, const double *B, d
 int lowdin_it_debug_expand(lowdin_it_handle h, int slotA, int slotB, int64_t slab0, int nb, double *X);
 /* First half only (TransformIntegralsE.f90:1043-1132) of AO-pair slabs [slab0, slab0+nslabs): out[k][z] for the k-th window
  * pair in convention order (E: ijmap order) -- the oracle check of the first half at sizes no CPU transforms whole. */
+/* First quarter only: out[f][z][mu] = sum_nu AO(slab0+z; mu nu) C(nu, f_first+f), f < nf, z < nslabs (host, nf*nslabs*nao doubles). */
+int lowdin_it_debug_first_quarter(lowdin_it_handle h, int slotA, int slotB, int f_first, int nf, int64_t slab0, int nslabs, double *out);
 int lowdin_it_debug_first_half(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv, double drop_tol,
                                int64_t slab0, int nslabs, double *out, int64_t *npairs);
 

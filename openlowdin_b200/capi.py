@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_shard_plan", "lowdin_it_blocked_offset", "lowdin_it_timers", "lowdin_it_kernel_bench",
     "lowdin_it_set_profiling", "lowdin_it_set_option", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
     "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
-    "lowdin_it_debug_first_half",
+    "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter",
 ]
 
 
@@ -87,6 +87,7 @@ def load():
     L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
     L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
     L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_debug_first_quarter.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _f64p]
     L.lowdin_it_debug_first_half.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p,
                                              C.POINTER(C.c_int64)]
     _lib = L
@@ -157,6 +158,11 @@ class Transformer:
     def materialize(self, a, b):
         self._ck(self.L.lowdin_it_ao_materialize(self.h, a, b))
 
+    def debug_first_quarter(self, a, b, f_first, nf, slab0, nslabs):
+        out = np.zeros((nf, nslabs, self.n[a]))
+        self._ck(self.L.lowdin_it_debug_first_quarter(self.h, a, b, f_first, nf, slab0, nslabs, out))
+        return out
+
     def debug_first_half(self, a, b, win, conv, slab0, nslabs, tol=1e-10):
         w = np.ascontiguousarray(win, dtype=np.int32)
         npairs = C.c_int64()
@@ -209,8 +215,8 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
-    OPT_ASYNC_PUSH, OPT_STAGING_BYTES = 8, 9
-    DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT = 3, 2  # library defaults (it_api.cu); tests restore them after forcing a variant
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST = 8, 9, 10, 11
+    DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT, DEFAULT_FRAG_PERM = 3, 2, 1  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):
         self._ck(self.L.lowdin_it_set_option(self.h, option, int(value)))

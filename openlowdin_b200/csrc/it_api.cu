@@ -7,6 +7,7 @@
 // IntTransfD.cpp:125-181, :245-323 (full in-place transform behind the same style of C ABI).
 #include "it_kernels.cuh"
 #include "it_gemm_tma.cuh"
+#include "it_list.cuh"
 #include "../../include/lowdin_it.h"
 
 #include <dlfcn.h>
@@ -53,7 +54,13 @@ struct AoSet {
   AoSource src{};
   DevBuf data;
   DevBuf fa, fb;  // kind K: pair-vector factors [RANKK][M_a], [RANKK][M_b]
+  // list storage (LOWDIN_IT_OPT_AO_LIST): the canonical list as uploaded, one segment per staged piece
+  std::vector<DevBuf> segs;
+  DevBuf seg_counts;      // entries kept in each segment (device, unsigned long long)
+  int swapped = 0;
+  void release_list() { for (auto &b : segs) b.release(); segs.clear(); }
 };
+constexpr int kMaxListSegs = 4096;
 
 // NCCL, resolved lazily so that single-GPU use has no link-time dependency on it.
 struct Id128 { char b[128]; };  // ncclUniqueId is passed by value (128 bytes)
@@ -132,6 +139,8 @@ struct lowdin_it_ctx {
   int async_push = 0;                        // 1: pushed host buffers stay untouched until ao_end -> pushes do not wait for their copies
   size_t staging_bytes = (size_t)96 << 20;   // per staging buffer
   // workspaces
+  DevBuf T1list, Cw;                         // list-driven first quarter: T1[slab][nu][f] of the pass, window rows Cw[mu][f]
+  int ao_list = 0;                           // uploads keep the canonical list instead of the dense tensor (LOWDIN_IT_OPT_AO_LIST)
   DevBuf X, T1t, H, H2, OUT, T3, order, tab, sa, sb, ss, sf, blockcount, blockoff, sums, running, overflow, epsA, epsB, dtmp, agree;
   // results of the last lowdin_it_transform
   DevBuf r_i0, r_i1, r_i2, r_i3, r_v;
@@ -149,7 +158,8 @@ struct lowdin_it_ctx {
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
-  int frag_perm = 0;                         // TMA kernels: 1 = conflict-free fragment-row permutation (it_gemm_tma.cuh, frag_row); not yet validated on a GPU
+  int q3_red = 0;                            // third-quarter accumulation: 0 = staged read-modify-write epilogue, 1 = red.global.add.f64 (EpiAccRed)
+  int frag_perm = 1;                         // TMA kernels: 1 = conflict-free fragment-row permutation (it_gemm_tma.cuh, frag_row); validated on B200 in round 2 (bit-identical, +2.4 % per pass)
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
   int64_t chunk_cols_limit = 0;              // >0: cap on AO-pair columns per chunk (tests force many chunks with it)
   // per-kernel-category device timing (lowdin_it_set_profiling): CUDA event pairs around every launch
@@ -506,9 +516,35 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
   h->launches += 1;
   return cudaGetLastError();
 }
+// variant 5 (q1_gen_ws5_kernel): 256-row tiles, 32-row DMMA warps, setmaxnreg
+template <int TN, int KIND, int GEN>
+cudaError_t launch_q1_ws5_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
+                              int nfb, double *T1t, int64_t ldt) {
+  constexpr int ST = 5;
+  constexpr size_t smem = q1_ws5_smem_bytes<TN, ST>();
+  static_assert(smem <= 232448, "shared memory per CTA");
+  auto kern = q1_gen_ws5_kernel<TN, ST, KIND, GEN>;
+  static uint64_t configured = 0;
+  if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured); e != cudaSuccess) return e;
+  CUtensorMap mapB;
+  if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
+  const int64_t ntiles = ceil_div(nc, 256) * (int64_t)bc;
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
+  Q1WsArgs q{slab0, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
+  kern<<<grid, 512, smem, h->stream>>>(mapB, q);
+  h->launches += 1;
+  return cudaGetLastError();
+}
 template <int TN>
 cudaError_t launch_q1_ws(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb,
                          double *T1t, int64_t ldt) {
+  if (h->q1_variant == 5) {
+    if (src.kind == SRC_HASH_SYM)
+      return src.gen == 2 ? launch_q1_ws5_cfg<TN, SRC_HASH_SYM, 2>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt)
+                          : launch_q1_ws5_cfg<TN, SRC_HASH_SYM, 1>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+    return src.gen == 2 ? launch_q1_ws5_cfg<TN, SRC_HASH_RECT, 2>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt)
+                        : launch_q1_ws5_cfg<TN, SRC_HASH_RECT, 1>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
+  }
   if (src.kind == SRC_HASH_SYM)
     return src.gen == 2 ? launch_q1_ws_cfg<TN, SRC_HASH_SYM, 2>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt)
                         : launch_q1_ws_cfg<TN, SRC_HASH_SYM, 1>(h, src, slab0, bc, nc, Cf, ldc, nfb, T1t, ldt);
@@ -520,7 +556,7 @@ cudaError_t launch_q1_ws(lowdin_it_handle h, const AoSource &src, int64_t slab0,
 // Cf: coefficient window [nfb][ldc]; Cfs: the same window of the 2^-53-scaled copy (needed by the warp-specialised variant)
 int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, const double *Cfs, int64_t ldc,
                   int nfb, double *T1t, int64_t ldt) {
-  const bool ws = (h->q1_variant == 3 || h->q1_variant == 4) && Cfs && tensor_map_encoder() != nullptr && ((uintptr_t)Cfs % 16 == 0) && (ldc % 2 == 0);
+  const bool ws = (h->q1_variant >= 3 && h->q1_variant <= 5) && Cfs && tensor_map_encoder() != nullptr && ((uintptr_t)Cfs % 16 == 0) && (ldc % 2 == 0);
   // Column groups of at most 64 (8 DMMA n-tiles), balanced in units of 8 columns: 80 -> 40 + 40, 150 -> 56 + 48 + 46.
   // (A 64 + 16 split runs its narrow launch at 12 TF/s: measured 19.9 TF/s for 80 columns against 24.3 for 40 + 40.)
   const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
@@ -547,6 +583,73 @@ int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc
   return 0;
 }
 
+// List-driven first quarter of ONE PASS (it_list.cuh): T1list[slab][nu][f] for every slab, from the resident canonical list.
+int list_first_quarter(lowdin_it_handle h, const Plan &pl, const PassTables &pt) {
+  const Half &hf = pl.h1;
+  AoSet &S = h->ao[pl.a][pl.b];
+  const int nc = hf.nc, nfb = pt.nfb, nfbp = (nfb + 3) & ~3;
+  const int n_slab = h->sp[pl.b].n;
+  const size_t t1_bytes = (size_t)pl.nslabs1 * nc * nfbp * sizeof(double);
+  CK(h->Cw.ensure((size_t)nc * nfbp * sizeof(double)));
+  CK(h->T1list.ensure(t1_bytes));
+  ProfScope ps(h, 1, 2.0 * (double)pl.nslabs1 * nc * (double)nc * nfb);
+  list_window_kernel<<<(unsigned)ceil_div((int64_t)nc * nfbp, 256), 256, 0, h->stream>>>(hf.C, hf.ldc, nc, hf.lf - 1 + pt.f0, nfb, nfbp, h->Cw.as<double>());
+  CK(cudaMemsetAsync(h->T1list.p, 0, t1_bytes, h->stream));
+  for (size_t i = 0; i < S.segs.size(); ++i) {
+    list_first_quarter_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(S.segs[i].as<ListEntry>(), S.seg_counts.as<unsigned long long>() + i,
+                                                                   pl.intra ? 1 : 0, S.swapped, nc, n_slab, h->Cw.as<double>(), nfb, nfbp,
+                                                                   h->T1list.as<double>());
+    h->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// First quarter (E.f90:1047-1090) of the batch of bc slabs starting at `slab`: T1t[f][z][mu] = sum_nu AO(slab+z; mu nu) C(nu, lf+f0+f)
+int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t slab, int64_t bc, int64_t ldx, int64_t ldt) {
+  const Half &hf = pl.h1;
+  const int nc = hf.nc, nfb = pt.nfb;
+  const double *Cf = hf.C + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc;
+  const double *Cfs = hf.Cs ? hf.Cs + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc : nullptr;
+  if (pl.src.kind == SRC_LIST) {
+    // the quarter-transformed slabs of the pass exist already (list_first_quarter): bring the batch into the operand layout
+    const int nfbp = (nfb + 3) & ~3;
+    dim3 grid((unsigned)ceil_div(nc, 32), (unsigned)ceil_div(nfb, 32), (unsigned)bc);
+    ProfScope ps(h, 0, (double)bc * nc * nfb * 16.0);
+    list_transpose_kernel<<<grid, 256, 0, h->stream>>>(h->T1list.as<double>(), slab, (int)bc, nc, nfb, nfbp, h->T1t.as<double>(), ldt);
+    h->launches += 1;
+    CK(cudaGetLastError());
+  } else if (pl.src.kind == SRC_HASH_SYM || pl.src.kind == SRC_HASH_RECT) {
+    // slab generation + first quarter in one kernel: the dense slab never exists
+    ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
+    if (launch_q1_gen(h, pl.src, slab, (int)bc, nc, Cf, Cfs, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+  } else {
+    {  // unpack (E.f90:1047-1063)
+      ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
+      if (launch_expand(h, pl.src, slab, bc, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
+    }
+    // first quarter (E.f90:1081-1090): T1t[f][z][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
+    GemmArgs g{h->X.as<double>(), Cf, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
+    EpiQ1 epi{h->T1t.as<double>(), nc, (int)bc, ldt};
+    ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
+    CK(launch_gemm(h, g, epi));
+  }
+  return 0;
+}
+
+// slabs per batch of the first half: what the X / T1t workspaces hold, within the grid limits of the kernels
+int64_t first_half_batch(lowdin_it_handle h, const Plan &pl, int nfb, int64_t count) {
+  const int nc = pl.h1.nc;
+  const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
+  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK || pl.src.kind == SRC_RECT_BLOCKED);
+  const size_t per_slab = std::max(dense ? (size_t)nc * ldx : (size_t)0, (size_t)nfb * ldt) * sizeof(double);
+  int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
+  B = std::min<int64_t>(B, count);
+  B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / nc)));  // gridDim.y limit of the stacked GEMM
+  B = std::min<int64_t>(B, 65535);                                                 // gridDim limits of expansion / fused kernel
+  return B;
+}
+
 // First half (E.f90:1043-1132) of `count` AO-pair slabs starting at slab `slab0`:
 //   Hc[slot][col0 + (slab - slab0)] for every slot of the pass.
 int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t slab0, int64_t count, double *Hc, int64_t ldh,
@@ -554,33 +657,13 @@ int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t
   const Half &hf = pl.h1;
   const int nc = hf.nc, nfb = pt.nfb;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool generated = (pl.src.kind == SRC_HASH_SYM || pl.src.kind == SRC_HASH_RECT);
-  const size_t per_slab = std::max(generated ? (size_t)0 : (size_t)nc * ldx, (size_t)nfb * ldt) * sizeof(double);
-  int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
-  B = std::min<int64_t>(B, count);
-  B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / nc)));  // gridDim.y limit of the stacked GEMM
-  B = std::min<int64_t>(B, 65535);                                                 // gridDim limits of expansion / fused kernel
-  if (!generated) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK || pl.src.kind == SRC_RECT_BLOCKED);
+  const int64_t B = first_half_batch(h, pl, nfb, count);
+  if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
-  const double *Cf = hf.C + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc;
-  const double *Cfs = hf.Cs ? hf.Cs + (int64_t)(hf.lf - 1 + pt.f0) * hf.ldc : nullptr;
   for (int64_t s = 0; s < count; s += B) {
     const int64_t bc = std::min<int64_t>(B, count - s);
-    if (generated) {
-      // slab generation + first quarter in one kernel: the dense slab never exists
-      ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
-      if (launch_q1_gen(h, pl.src, slab0 + s, (int)bc, nc, Cf, Cfs, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
-    } else {
-      {  // unpack (E.f90:1047-1063)
-        ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
-        if (launch_expand(h, pl.src, slab0 + s, bc, nc, 0, nc, 0, nc, 0, (int)ldx, h->X.as<double>())) return 1;
-      }
-      // first quarter (E.f90:1081-1090): T1t[f][z][mu] = sum_nu X[z][mu][nu] C(nu, lf+f0+f)
-      GemmArgs g{h->X.as<double>(), Cf, (int)(bc * nc), nfb, nc, ldx, hf.ldc, 0, 0};
-      EpiQ1 epi{h->T1t.as<double>(), nc, (int)bc, ldt};
-      ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
-      CK(launch_gemm(h, g, epi));
-    }
+    if (first_quarter_batch(h, pl, pt, slab0 + s, bc, ldx, ldt)) return 1;
     {  // second quarter (E.f90:1099-1110): T2[s][(f,z)] = sum_mu C(mu, ls+s) T1t[f][z][mu]  ->  Hc[slot(s,f)][col0+s'+z]
       GemmArgs g{hf.C + (int64_t)(hf.ls - 1) * hf.ldc, h->T1t.as<double>(), hf.ns, (int)(bc * nfb), nc, hf.ldc, ldt, 0, 0};
       EpiScatterH epi{Hc, ldh, col0 + s, h->tab.as<int32_t>(), nfb, (int)bc, tol};
@@ -623,10 +706,12 @@ int second_half_partial(lowdin_it_handle h, const Plan &pl, const AoSource &hsrc
     {
       ProfScope ps(h, 4, 2.0 * bs * (double)nf2 * ((double)nrw * pc + (double)pc * ncv));
       GemmArgs g{h->X.as<double>(), C2f + ck.p0, (int)(bs * nrw), nf2, pc, ldw, h2.ldc, 0, 0};
-      CK(launch_gemm(h, g, EpiAccT{T3s, nrw, ck.p0, nf2, ldt2}));
+      if (h->q3_red) CK(launch_gemm(h, g, EpiAccRed{T3s, nrw, ck.p0, nf2, ldt2}));
+      else CK(launch_gemm(h, g, EpiAccT{T3s, nrw, ck.p0, nf2, ldt2}));
       if (ncv > 0) {
         GemmArgs g2{h->T1t.as<double>(), C2f + ck.p1, (int)(bs * pc), nf2, ncv, ldv, h2.ldc, 0, 0};
-        CK(launch_gemm(h, g2, EpiAccT{T3s, pc, ck.p0, nf2, ldt2}));
+        if (h->q3_red) CK(launch_gemm(h, g2, EpiAccRed{T3s, pc, ck.p0, nf2, ldt2}));
+        else CK(launch_gemm(h, g2, EpiAccT{T3s, pc, ck.p0, nf2, ldt2}));
       }
     }
   }
@@ -727,6 +812,11 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     const size_t t3_bytes = std::max<size_t>((size_t)std::max(nmine, 1) * nf2 * ldt2, 1) * sizeof(double);
     CK(h->T3.ensure(t3_bytes));
     CK(cudaMemsetAsync(h->T3.p, 0, t3_bytes, h->stream));
+    if (pl.src.kind == SRC_LIST) {
+      if (G > 1) return fail(h, "the list-driven first quarter runs on one GPU; upload the dense tensor for a communicator");
+      if (list_first_quarter(h, pl, pt)) return 1;
+      flops += 0.0;  // counted with the chunks below (the algorithmic count is the dense one)
+    }
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const bool download = (cons.mode == 0);
@@ -980,8 +1070,8 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
-  for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); }
-  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
+  for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); a.release_list(); a.seg_counts.release(); }
+  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
@@ -1034,9 +1124,19 @@ int lowdin_it_ao_begin(lowdin_it_handle h, int a, int b, int swapped) {
   AoSet &S = h->ao[a][b];
   const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
   const size_t count = (a == b) ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb);
-  CK(S.data.ensure(count * sizeof(double)));
-  CK(cudaMemsetAsync(S.data.p, 0, count * sizeof(double), h->stream));  // C.f90:669-685 zero-initialises
-  S.src = (a == b) ? AoSource{SRC_SYM_PACKED, S.data.as<double>(), Ma, 0, 0, 0} : AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
+  S.release_list();
+  S.swapped = swapped;
+  if (h->ao_list) {  // keep the list as it comes (16 bytes per integral); the first quarter is then list-driven (it_list.cuh)
+    if (h->sp[a].n > 65535 || h->sp[b].n > 65535) return fail(h, "ao_begin: the resident list stores 16-bit AO indices");
+    S.data.release();
+    CK(S.seg_counts.ensure(kMaxListSegs * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(S.seg_counts.p, 0, kMaxListSegs * sizeof(unsigned long long), h->stream));
+    S.src = AoSource{SRC_LIST, nullptr, Ma, 0, Mb, 0};
+  } else {
+    CK(S.data.ensure(count * sizeof(double)));
+    CK(cudaMemsetAsync(S.data.p, 0, count * sizeof(double), h->stream));  // C.f90:669-685 zero-initialises
+    S.src = (a == b) ? AoSource{SRC_SYM_PACKED, S.data.as<double>(), Ma, 0, 0, 0} : AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
+  }
   S.valid = false;
   h->up_a = a; h->up_b = b; h->up_swapped = swapped;
   h->up_pos = 0; h->up_piece = 0; h->st_busy[0] = h->st_busy[1] = false;
@@ -1077,11 +1177,20 @@ int push_piece(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int
   CK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
   const int na = h->sp[h->up_a].n, nb = h->sp[h->up_b].n;
-  ScatterDst d{h->ao[h->up_a][h->up_b].data.as<double>(), h->up_a == h->up_b, h->up_swapped, na, nb, 0, 0, 1, 0};
+  AoSet &AS = h->ao[h->up_a][h->up_b];
   unsigned long long *state = h->up_state.as<unsigned long long>();
   const unsigned grid = (unsigned)ceil_div(cnt, 256);
   find_terminator_kernel<<<grid, 256, 0, h->stream>>>(w, state);
-  scatter_stacks_kernel<<<grid, 256, 0, h->stream>>>(w, d, state);
+  if (AS.src.kind == SRC_LIST) {
+    if ((int)AS.segs.size() >= kMaxListSegs) return fail(h, "ao_push: too many list segments; push larger pieces");
+    AS.segs.emplace_back();
+    CK(AS.segs.back().ensure((size_t)cnt * sizeof(ListEntry)));
+    append_list_kernel<<<grid, 256, 0, h->stream>>>(w, h->up_a == h->up_b, h->up_swapped, na, nb, AS.segs.back().as<ListEntry>(),
+                                                    AS.seg_counts.as<unsigned long long>() + (AS.segs.size() - 1), state);
+  } else {
+    ScatterDst d{AS.data.as<double>(), h->up_a == h->up_b, h->up_swapped, na, nb, 0, 0, 1, 0};
+    scatter_stacks_kernel<<<grid, 256, 0, h->stream>>>(w, d, state);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev_scattered[slot], h->stream));
   h->st_busy[slot] = true;
@@ -1160,6 +1269,7 @@ int lowdin_it_ao_set_generator(lowdin_it_handle h, int a, int b, int kind, uint6
   if (kind != LOWDIN_IT_GEN_HASH && kind != LOWDIN_IT_GEN_FOLD) return fail(h, "unknown generator kind");
   AoSet &S = h->ao[a][b];
   S.data.release();
+  S.release_list();
   S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed, kind} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed, kind};
   S.valid = true;
   return 0;
@@ -1290,7 +1400,8 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
   const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
-  int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f)));
+  const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 : 0.0;  // T1list[slab][nu][f]
+  int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
   if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
   const int qmax = (int)qmax64;
   const int passes = (int)ceil_div(nf, qmax);
@@ -1347,7 +1458,7 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       if (value < 0) return fail(h, "negative chunk column limit");
       h->chunk_cols_limit = value; return 0;
     case LOWDIN_IT_OPT_Q1_VARIANT:
-      if (value < 1 || value > 4) return fail(h, "q1 variant must be 1..4");
+      if (value < 1 || value > 5) return fail(h, "q1 variant must be 1..5");
       h->q1_variant = (int)value; return 0;
     case LOWDIN_IT_OPT_GEMM_VARIANT:
       if (value != 1 && value != 2) return fail(h, "gemm variant must be 1 or 2");
@@ -1357,6 +1468,10 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->split_row_tail = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_FRAG_PERM:
       h->frag_perm = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_AO_LIST:
+      h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_Q3_RED:
+      h->q3_red = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_ASYNC_PUSH:
       h->async_push = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_STAGING_BYTES:
@@ -1487,6 +1602,39 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
   return 0;
 }
 
+// First QUARTER only: out[f][z][mu] = sum_nu AO(slab0+z; mu nu) C(nu, f_first+f) for nf MO indices starting at orbital f_first (1-based)
+// and nslabs AO-pair slabs, through whichever first-quarter kernel the AO set's storage selects (expansion + DMMA GEMM, fused
+// generator, list-driven scatter).  With C = identity this is the AO tensor itself: the bit-exact test of the index work.
+int lowdin_it_debug_first_quarter(lowdin_it_handle h, int a, int b, int f_first, int nf, int64_t slab0, int nslabs, double *out) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].n || !h->sp[b].n || !h->ao[a][b].valid) return fail(h, "debug_first_quarter: AO set not available");
+  const Species &A = h->sp[a];
+  if (f_first < 1 || nf < 1 || f_first + nf - 1 > A.ncols || !out) return fail(h, "debug_first_quarter: bad orbital range");
+  Plan pl;
+  pl.a = a; pl.b = b; pl.intra = (a == b); pl.src = h->ao[a][b].src; pl.nslabs1 = h->sp[b].M;
+  pl.h1.nc = A.n; pl.h1.C = A.C.as<double>(); pl.h1.Cs = A.Cs.as<double>(); pl.h1.ldc = A.ldc; pl.h1.lf = f_first; pl.h1.nf = nf;
+  if (slab0 < 0 || nslabs < 1 || slab0 + nslabs > pl.nslabs1) return fail(h, "debug_first_quarter: slab range out of bounds");
+  PassTables pt;
+  pt.f0 = 0; pt.nfb = nf;
+  const int nc = A.n;
+  const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
+  if (pl.src.kind == SRC_LIST && list_first_quarter(h, pl, pt)) return 1;
+  const int64_t B = first_half_batch(h, pl, nf, nslabs);
+  const bool dense = !(pl.src.kind == SRC_LIST || pl.src.kind == SRC_HASH_SYM || pl.src.kind == SRC_HASH_RECT);
+  if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  CK(h->T1t.ensure((size_t)B * nf * ldt * sizeof(double)));
+  for (int64_t s = 0; s < nslabs; s += B) {
+    const int64_t bc = std::min<int64_t>(B, nslabs - s);
+    if (first_quarter_batch(h, pl, pt, slab0 + s, bc, ldx, ldt)) return 1;
+    for (int f = 0; f < nf; ++f)  // T1t[f][z][mu] of the batch -> out[f][s+z][mu]
+      CK(cudaMemcpy2DAsync(out + ((size_t)f * nslabs + s) * nc, (size_t)nc * 8, h->T1t.as<double>() + (size_t)f * bc * ldt, (size_t)ldt * 8,
+                           (size_t)nc * 8, (size_t)bc, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
 int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks) {
   if (!handles || nranks < 1 || nranks > 16) return fail(nullptr, "comm_init_local: 1..16 handles required");
   for (int r = 0; r < nranks; ++r) if (!handles[r]) return fail(nullptr, "comm_init_local: null handle");
@@ -1597,6 +1745,28 @@ int lowdin_it_kernel_bench(lowdin_it_handle h, int kind, int64_t m, int64_t n, i
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (check) CK(cudaMemcpy(check, h->OUT.p, sizeof(double), cudaMemcpyDeviceToHost));
+  } else if (kind == 4 || kind == 5) {  // third-quarter shape: (m/1500 slots x 1500 rows) x n x k accumulated into T3[slot][n][1500]; 4 = staged RMW, 5 = red
+    const int nrows = 1500;
+    const int64_t lda = roundup2(k), slots = std::max<int64_t>(1, m / nrows), ldt = nrows;
+    m = slots * nrows;
+    CK(h->X.ensure((size_t)m * lda * sizeof(double)));
+    CK(h->T1t.ensure((size_t)n * lda * sizeof(double)));
+    CK(h->OUT.ensure((size_t)slots * n * ldt * sizeof(double)));
+    CK(cudaMemsetAsync(h->X.p, 0x3f, (size_t)m * lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->T1t.p, 0x3f, (size_t)n * lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->OUT.p, 0, (size_t)slots * n * ldt * sizeof(double), h->stream));
+    GemmArgs g{h->X.as<double>(), h->T1t.as<double>(), (int)m, (int)n, (int)k, lda, lda, 0, 0};
+    auto run = [&]() -> cudaError_t {
+      return kind == 5 ? launch_gemm(h, g, EpiAccRed{h->OUT.as<double>(), nrows, 0, (int)n, ldt})
+                       : launch_gemm(h, g, EpiAccT{h->OUT.as<double>(), nrows, 0, (int)n, ldt});
+    };
+    CK(run());
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < iters; ++i) CK(run());
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (check) CK(cudaMemcpy(check, h->OUT.p, sizeof(double), cudaMemcpyDeviceToHost));
   } else {  // DGEMM m x n x k on generated operands
     const int64_t lda = roundup2(k);
     CK(h->X.ensure((size_t)m * lda * sizeof(double)));
@@ -1640,6 +1810,7 @@ int lowdin_it_debug_gemm(lowdin_it_handle h, const double *A, const double *B, d
 int lowdin_it_debug_expand(lowdin_it_handle h, int a, int b, int64_t slab0, int nb, double *X) {
   if (!h) return 1;
   if (a < 0 || a > 7 || b < 0 || b > 7 || !h->ao[a][b].valid) return fail(h, "debug_expand: AO set not available");
+  if (h->ao[a][b].src.kind == SRC_LIST) return fail(h, "debug_expand: the AO set is a resident list (no dense slabs exist)");
   CK(cudaSetDevice(h->device));
   const int nc = h->sp[a].n; const int64_t ldx = roundup2(nc);
   CK(h->X.ensure((size_t)nb * nc * ldx * sizeof(double)));

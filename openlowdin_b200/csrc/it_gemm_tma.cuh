@@ -660,4 +660,161 @@ __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constan
   }
 }
 
+// =================================================================================================================
+// q1 variant 5: 256-row tiles, 32-row DMMA warps, register file re-divided between the two roles.
+// Measured on B200 (profiles/r02a_perm_probe.log): the fused first quarter scales with the number of DMMAs a warp runs per set of
+// fragment loads -- 28.1 / 27.4 / 25.9 / 25.2 TF/s at 64 / 56 / 48 / 40 window columns, i.e. a pipe utilisation of
+// TN / (TN + 2.6): every half k-tile costs a DMMA warp about 2.6 column-tiles' worth of tensor time in fragment loads and barrier
+// traffic that its partner warp does not cover.  With 16-row warps the DMMA phase is 2 x 2 TN instructions per 2 + TN loads; a
+// 32-row warp runs 4 x 2 TN per 4 + TN loads (0.196 loads per DMMA at TN = 7, the ratio at which the plain GEMM reaches cuBLAS
+// speed) -- but needs 8 TN + 44 accumulator/fragment registers, more than the 128 a 512-thread CTA gives each thread.  So the
+// roles trade registers (setmaxnreg, sm_90+): the 8 generator warps shrink to 88, the 8 DMMA warps grow to 168.
+//   tile = 256 rows x 8 TN columns of one slab;  ring stage = 32 KB (A, generated) + TN KB (B, TMA);  5 stages.
+// Fragment rows are permuted (frag_row<true>): conflict-free 128-bit shared accesses on both sides.
+// =================================================================================================================
+template <int TN, int STAGES>
+constexpr size_t q1_ws5_smem_bytes() {
+  return (size_t)STAGES * (256 + TN * 8) * 128 + 2 * STAGES * 8 + 1024;
+}
+
+template <int TN, int STAGES, int KIND, int GEN>
+__global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constant__ CUtensorMap mapB, Q1WsArgs q) {
+  constexpr int BK = 16, BM = 256, BN = TN * 8;
+  constexpr int NCW = 8, NGW = 8;  // DMMA warps (32 rows each) / generator warps (32 rows each)
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tig = lane & 3;
+  const int grp = frag_row<true>(lane >> 2);
+  const int KT = (q.nc + BK - 1) / BK;
+  const int row_blocks = (q.nc + BM - 1) / BM;
+  const int ntiles = row_blocks * q.bc;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, NGW + 1);         // one arrive per generator warp + the arrive.expect_tx of the TMA issuer
+      mbar_init(bars + 8 * (STAGES + s), NCW);  // one arrive per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&mapB);
+  }
+  __syncthreads();
+
+  const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk tig of a row with (row & 7) == grp; chunk 4+tig is off0 ^ 64
+
+  if (warp >= NCW) {
+    // ============================== generators (warpgroups 2 and 3) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int gw = warp - NCW;
+    const uint32_t n = (uint32_t)q.nc;
+    uint8_t *a_rows = ring + (gw * 32 + grp) * 128;  // rows 32 gw + 8 rg + grp, rg = 0..3
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / row_blocks, rb = tile - z * row_blocks;
+      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
+      uint32_t base_mu[4];
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) base_mu[rg] = pair_base(mu0 + 8u * rg, n);
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const uint32_t s = it % STAGES;
+        if (it >= (uint32_t)STAGES) mbar_wait(bars + 8 * (STAGES + s), ((it / STAGES) & 1u) ^ 1u);
+        if (gw == 0 && lane == 0) {
+          mbar_expect_tx(bars + 8 * s, B_BYTES);
+          tma_load_2d(ring_u + s * STAGE_BYTES + A_BYTES, &mapB, bars + 8 * s, kt * BK, 0);
+        }
+        uint8_t *dst = a_rows + s * STAGE_BYTES;
+        const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
+        const uint32_t nus[4] = {nu0, nu0 + 1u, nu0 + 8u, nu0 + 9u};  // chunks tig and 4 + tig
+        uint32_t base_nu[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base_nu[c] = pair_base(nus[c], n);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two row groups (8 values) at a time, all chains advanced together
+          uint64_t x[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int rg = 2 * hh + (v >> 2), c = v & 3;
+            const uint32_t mu = mu0 + 8u * rg;
+            const uint32_t pair = (nus[c] >= mu) ? base_mu[rg] + nus[c] : base_nu[c] + mu;
+            uint64_t key;
+            if (KIND == SRC_HASH_SYM) {
+              const uint32_t a = min(slab, pair), b = max(slab, pair);
+              key = (uint64_t)b * (uint64_t)q.m32 + a;
+            } else {
+              key = (uint64_t)pair * (uint64_t)q.m32 + slab;
+            }
+            x[v] = q.seed ^ key;
+          }
+          hash8<GEN>(x);
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            const int rg = 2 * hh + r2;
+            *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + off0) = make_double2(bits_to_unscaled(x[4 * r2 + 0]), bits_to_unscaled(x[4 * r2 + 1]));
+            *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (off0 ^ 64u)) = make_double2(bits_to_unscaled(x[4 * r2 + 2]), bits_to_unscaled(x[4 * r2 + 3]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * s);
+      }
+    }
+    return;
+  }
+
+  // ============================== DMMA warps (warpgroups 0 and 1) ==============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+  const uint8_t *a_base = ring + (warp * 32 + grp) * 128;
+  const uint8_t *b_base = ring + A_BYTES + grp * 128;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int z = tile / row_blocks, rb = tile - z * row_blocks;
+    double acc[4][TN][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const uint32_t s = it % STAGES;
+      mbar_wait(bars + 8 * s, (it / STAGES) & 1u);
+      const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = h ? (off0 ^ 64u) : off0;
+        double2 a[4], b[TN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2 *>(as + i * 8 * 128 + off);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const double2 *>(bs + j * 8 * 128 + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = rb * BM + warp * 32 + i * 8 + grp;
+      if (m >= q.nc) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int f = j * 8 + tig;  // permuted fragment mapping: accumulator [0] is column tig, [1] column tig + 4
+        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+        if (f + 4 < q.nfb) q.T1t[((int64_t)(f + 4) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+      }
+    }
+  }
+}
+
 }  // namespace lowdin

@@ -30,6 +30,7 @@ enum SrcKind : int {
   SRC_HASH_RECT = 3,   // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
   SRC_RECT_BLOCKED = 4,// data[((pair/ld)*aux + slab)*ld + pair%ld]: the half-transformed chunk as it arrives from the
                        // all-to-all, one [slots][ld] block per sending rank (aux = slots per block)
+  SRC_LIST = 6,        // the canonical AO list kept as uploaded (it_list.cuh): no dense tensor, list-driven first quarter
   SRC_RANKK = 5        // generated, kind K: (slab | pair) = sum_{k<8} data2[k*aux + slab] * data[k*M + pair]
                        // (rank-8 separable tensor with closed-form MO integrals; intra: data2 == data, aux == M)
 };
@@ -357,6 +358,19 @@ struct EpiAccT {
     return T3 + ((int64_t)zz * nf2 * ldt + roff + r);
   }
   __device__ __forceinline__ int64_t col_stride() const { return ldt; }
+};
+// The same accumulation as ONE fire-and-forget reduction per element (red.global.add.f64, performed by the L2): no load comes
+// back to the SM, so the epilogue costs its issue time instead of an HBM round trip, and needs no shared-memory staging -- the 8
+// rows of a lane group are 64 consecutive bytes of T3, i.e. whole 32-byte sectors.  Every T3 element receives exactly one add
+// per launch (one tile owns it) and launches are stream-ordered, so the result does not depend on the execution order.
+struct EpiAccRed {
+  static constexpr bool kSplitRowTail = false;
+  static constexpr bool kRowCoalesced = false;
+  double *T3; int nrows; int roff; int nf2; int64_t ldt;
+  __device__ __forceinline__ void operator()(int, int m, int n, double v) const {
+    int zz = m / nrows, r = m - zz * nrows;
+    atomicAdd(T3 + (((int64_t)zz * nf2 + n) * ldt + roff + r), v);
+  }
 };
 // Fourth quarter: m = ks, n = (z, kf)  ->  OUT[z][ks][kf]
 struct EpiOut {

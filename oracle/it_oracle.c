@@ -603,3 +603,37 @@ int64_t orc_e_first_half_values(int gen_kind, uint64_t seed, int n, const double
   free(x1); free(x2); free(ijmap);
   return nij;
 }
+
+/* ------------------------------------------------------------------ */
+/* DIRECT first quarter (the list-driven, un-densified form)           */
+/* ------------------------------------------------------------------ */
+
+/* Libint2Iface.cpp:793-868 with the integrals taken from a canonical list instead of being recomputed: for the MO index
+ * whose AO coefficients are coef[mu] (the reference's C(p, bf)), every stored integral (bf1 bf2|bf3 bf4) -- 1-based in the
+ * list, bf1>=bf2, bf3>=bf4, (12)>=(34), Iterators.cpp:45-77 -- adds v*coef to up to four elements of GG[n][n][n]
+ * (:803-851), the last two indices ordered; then GG is symmetrised in its last two indices (:858-868).
+ * GG[nu][lam][sig] = sum_mu (mu nu|lam sig) coef[mu], i.e. auxtempA(lam, sig, nu) of TransformIntegralsC.f90:545-558. */
+void orc_direct_first_quarter(int n, const double *coef, const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s,
+                              const double *v, int64_t count, double *GG) {
+#define GG3(a, b, c) GG[((int64_t)(a) * n + (b)) * n + (c)]
+  for (int64_t e = 0; e < (int64_t)n * n * n; ++e) GG[e] = 0.0;
+  for (int64_t e = 0; e < count; ++e) {
+    if (p[e] == -1) break;
+    const int bf1 = p[e] - 1, bf2 = q[e] - 1, bf3 = r[e] - 1, bf4 = s[e] - 1;
+    const double val = v[e];
+    if (bf3 < bf4) GG3(bf2, bf3, bf4) += val * coef[bf1]; else GG3(bf2, bf4, bf3) += val * coef[bf1];
+    if (bf1 != bf2) {
+      if (bf3 < bf4) GG3(bf1, bf3, bf4) += val * coef[bf2]; else GG3(bf1, bf4, bf3) += val * coef[bf2];
+    }
+    if (bf1 != bf3 || bf2 != bf4) {
+      if (bf1 < bf2) GG3(bf4, bf1, bf2) += val * coef[bf3]; else GG3(bf4, bf2, bf1) += val * coef[bf3];
+      if (bf3 != bf4) {
+        if (bf1 < bf2) GG3(bf3, bf1, bf2) += val * coef[bf4]; else GG3(bf3, bf2, bf1) += val * coef[bf4];
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      for (int k = j; k < n; ++k) GG3(i, k, j) = GG3(i, j, k);
+#undef GG3
+}

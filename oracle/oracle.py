@@ -94,6 +94,8 @@ def lib():
         L.orc_gen_value.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
         L.orc_e_first_half_sample.restype = C.c_double
         L.orc_e_first_half_sample.argtypes = [C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int]
+        L.orc_direct_first_quarter.restype = None
+        L.orc_direct_first_quarter.argtypes = [C.c_int, _f64p, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int64, _f64p]
         L.orc_e_first_half_values.restype = C.c_int64
         L.orc_e_first_half_values.argtypes = [C.c_int, C.c_uint64, C.c_int, _f64pf, C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         L.orc_reader_pairs_intra.restype = None
@@ -620,6 +622,16 @@ def e_first_half_values(seed, Cm, win, pq0, npq, nthreads=1, gen_kind=1):
     out = np.zeros((nij, npq))
     lib().orc_e_first_half_values(gen_kind, seed, n, Cf, n, _win(win), pq0, npq, nthreads, out.ctypes.data)
     return out
+
+
+def direct_first_quarter(coef, p, q, r, s, v):
+    """The DIRECT first quarter of the reference (Libint2Iface.cpp:793-868) fed from a canonical list:
+    GG[nu, lam, sig] = sum_mu (mu nu|lam sig) coef[mu]."""
+    n = len(coef)
+    GG = np.zeros((n, n, n))
+    lib().orc_direct_first_quarter(n, np.ascontiguousarray(coef, dtype=np.float64), *[np.ascontiguousarray(x, dtype=np.int32) for x in (p, q, r, s)],
+                                   np.ascontiguousarray(v, dtype=np.float64), len(v), GG)
+    return GG
 
 
 def rankk_factors(seed, n, K=8):

@@ -316,7 +316,7 @@ def test_chunked_stream_mp2_energy_intra(O, T, chunked):
         assert abs(sums[3] - e_orc) <= 1e-9
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("kind", [1, 2])
 def test_generator_kinds_and_fused_kernel_variants(O, T, kind, variant):
     """Both synthetic generators (H: splitmix64, F: mul-fold-mul) are bit-identical on host and device, through the

@@ -108,7 +108,7 @@ def test_tma_generated_chunked_stream_energy(O, tma, cols):
 
 
 # ---- warp-specialised fused generation + first-quarter kernel (q1 variant 3, q1_gen_ws_kernel) --------------------------------
-@pytest.fixture(params=[1, 3, 4], ids=["single_role", "warp_specialised_8g", "warp_specialised_4g_pipelined"])
+@pytest.fixture(params=[1, 3, 4, 5], ids=["single_role", "warp_specialised_8g", "warp_specialised_4g_pipelined", "warp_specialised_256row"])
 def ws(T, request):
     T.set_option(T.OPT_Q1_VARIANT, request.param)
     yield T
@@ -118,7 +118,7 @@ def ws(T, request):
 @pytest.mark.parametrize("kind", [1, 2])
 @pytest.mark.parametrize("n,win", [(19, [6, 19, 1, 5, 6, 19, 1, 5]), (23, [1, 23, 1, 23, 1, 23, 1, 23]), (37, [12, 37, 1, 11, 12, 37, 1, 11]),
                                    (70, [1, 70, 1, 1, 1, 70, 1, 70]), (70, [66, 70, 1, 65, 1, 3, 1, 2]), (133, [11, 133, 1, 10, 11, 133, 1, 10]),
-                                   (100, [1, 100, 1, 70, 1, 2, 1, 2])])
+                                   (100, [1, 100, 1, 70, 1, 2, 1, 2]), (300, [271, 275, 1, 56, 271, 272, 1, 2]), (257, [250, 252, 3, 42, 1, 2, 1, 2])])
 def test_ws_generated_source_intra(O, ws, n, win, kind):
     """several 128-row blocks, row and K tails, windows wider than 64 columns (two launches), both generators"""
     seed = 4242 + n
@@ -173,7 +173,7 @@ def test_all_new_variants_n500_properties(T):
         T.set_option(T.OPT_Q1_VARIANT, 1)
         ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
         got = []
-        for q1v, split in ((3, 1), (4, 1), (4, 0)):
+        for q1v, split in ((3, 1), (4, 1), (4, 0), (5, 1)):
             T.set_option(T.OPT_GEMM_VARIANT, 2)
             T.set_option(T.OPT_Q1_VARIANT, q1v)
             T.set_option(T.OPT_SPLIT_ROW_TAIL, split)
@@ -190,19 +190,16 @@ def test_all_new_variants_n500_properties(T):
 
 
 # ---- fragment-row permutation (LOWDIN_IT_OPT_FRAG_PERM, it_gemm_tma.cuh frag_row) ----------------------------------------------
-# Written after the last GPU session of round 1: not yet run on a GPU, so these tests are opt-in (LOWDIN_IT_EXPERIMENTAL=1)
-# until the variant has passed once; the default path does not use it.
-import os  # noqa: E402
-
-experimental = pytest.mark.skipif(os.environ.get("LOWDIN_IT_EXPERIMENTAL", "") != "1",
-                                  reason="variant not yet validated on a GPU; set LOWDIN_IT_EXPERIMENTAL=1")
+# Validated on B200 in round 2 (profiles/r02a_pytest_perm.log: 29 passed; bit-identical results, +2.4 % on the N_bf = 1500 pass):
+# the permutation is the library default now; these tests compare it with the unpermuted mapping (LOWDIN_IT_OPT_FRAG_PERM = 0).
+experimental = pytest.mark.gpu
 
 
 @pytest.fixture
 def perm(T):
     T.set_option(T.OPT_FRAG_PERM, 1)
     yield T
-    T.set_option(T.OPT_FRAG_PERM, 0)
+    T.set_option(T.OPT_FRAG_PERM, T.DEFAULT_FRAG_PERM)
 
 
 @experimental
@@ -252,11 +249,12 @@ def test_perm_n500_stream_sums_identical(T):
     T.set_generator(0, 0, 77)
     T.set_option(T.OPT_CHUNK_COLS, 30000)
     try:
+        T.set_option(T.OPT_FRAG_PERM, 0)
         ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
         T.set_option(T.OPT_FRAG_PERM, 1)
         got = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=8, first_pass=1, n_passes=1, epsA=eps)
     finally:
-        T.set_option(T.OPT_FRAG_PERM, 0)
+        T.set_option(T.OPT_FRAG_PERM, T.DEFAULT_FRAG_PERM)
         T.set_option(T.OPT_CHUNK_COLS, 0)
     assert got[0] == ref[0]
     for a, b in zip(got[1:], ref[1:]):
