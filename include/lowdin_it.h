@@ -88,7 +88,14 @@ int lowdin_it_ao_materialize(lowdin_it_handle h, int slotA, int slotB);
  * drop_tol is the reference's 1e-10 (C.f90:418, E.f90:1113, :1242). */
 int lowdin_it_transform(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv, int symmetric,
                         double drop_tol);
+/* On a communicator lowdin_it_transform is COLLECTIVE and every rank ends up with the integrals of ITS window pairs (first pairs
+ * (i,j) / (p,q) are divided among the ranks): lowdin_it_result_count and the downloads are then per rank, each list in the
+ * reference's loop order.  lowdin_it_result_segments tells how the lists interleave: this rank holds `npairs` window pairs, the
+ * one with convention-order index pair_index[t] (0-based, counted over all window pairs: ijmap order for E, the (p,q) loop for C)
+ * contributed the next kept[t] entries of its list.  Taking the pairs in increasing index from whichever rank holds them gives
+ * the single-GPU list, entry for entry (what the lowdin_it_group_* calls below do for a one-process host). */
 int lowdin_it_result_count(lowdin_it_handle h, int64_t *count);
+int lowdin_it_result_segments(lowdin_it_handle h, int64_t *npairs, int64_t *pair_index, int64_t *kept);
 /* E record content (TransformIntegralsE.f90:1244-1250): pair ids + value, reference loop order. */
 int lowdin_it_download_pairs(lowdin_it_handle h, int64_t *ij, int64_t *kl, double *v);
 /* C record content (TransformIntegralsC.f90:420-425): p,q,r,s + value, p,q,r,s loop order. */
@@ -103,6 +110,22 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
 int lowdin_it_transform_stream(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv,
                                double drop_tol, int occ_batch, int first_pass, int n_passes,
                                const double *epsA, const double *epsB, double lambda, double sums[4]);
+/* The same, and every dense block of results also goes to the HOST: the MO integrals of N_bf = 1500 (328 GB for the MP2 window)
+ * fit neither the device nor one download, so they leave block by block while the transform runs.  A block holds the integrals of
+ * `nslots` first pairs: values[slot][ks][kf] = (a_slot b_slot | r s) with r, s the orbitals orb_second0 + ks, orb_first0 + kf in the
+ * order (r, s) when second_is_conv_first != 0, else (s, r); slot_a/slot_b are the first pair's orbital numbers in convention order
+ * ((i,j) for E, (p,q) for C).  No threshold is applied: the consumer drops |x| <= 1e-10 as it writes its records
+ * (TransformIntegralsE.f90:1242).  `values` is pinned memory owned by the library, valid during the callback, which runs on the
+ * calling thread while the next block is being computed and copied; a non-zero return aborts the transform. */
+typedef struct lowdin_it_block {
+  int conv, nslots, n_second, n_first, orb_second0, orb_first0, second_is_conv_first;
+  const int32_t *slot_a, *slot_b;
+  const double *values;
+} lowdin_it_block;
+typedef int (*lowdin_it_sink_fn)(void *user, const lowdin_it_block *block);
+int lowdin_it_transform_stream_sink(lowdin_it_handle h, int slotA, int slotB, const int win[8], int conv, double drop_tol,
+                                    int occ_batch, int first_pass, int n_passes, const double *epsA, const double *epsB,
+                                    double lambda, double sums[4], lowdin_it_sink_fn sink, void *user);
 /* On a communicator (lowdin_it_comm_init, nranks > 1) lowdin_it_transform_stream is COLLECTIVE: every rank makes the same
  * call with the same arguments.  With occ_batch == 0 so is lowdin_it_stream_num_passes (the ranks agree on the batch that fits
  * the rank with the least free memory). */
@@ -119,19 +142,35 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
 
 /* ---- multi-GPU (one process per GPU; first half sharded over AO pair slabs,
  *      NCCL all-to-all, second half sharded over MO pairs) ----------------------------- */
-/* The division of work the library uses (no device needed; the CPU multi-rank test drives it):
- * own[r]..own[r+1] = slots of rank r (fbeg[f] = first slot of first-contracted index f, nfb+1 entries);
- * columns [col_lo,col_hi) of a chunk of chunk_width AO-pair slabs belong to `rank`, wblk = columns per rank.
- * After the all-to-all rank r holds element (its local slot `row`, chunk column `col`) at lowdin_it_blocked_offset(). */
-int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_width, int nranks, int rank, int *own, int64_t *wblk,
-                         int64_t *col_lo, int64_t *col_hi);
-int64_t lowdin_it_blocked_offset(int64_t row, int64_t col, int64_t wblk, int64_t rows);
+/* The division of work the library uses (no device needed; the CPU multi-rank test drives it).
+ * First half: the AO-pair slabs are distributed BLOCK-CYCLICALLY, blocks of 2^log_block consecutive slabs, block b on rank
+ * b % nranks (LOWDIN_IT_OPT_SLAB_BLOCK_LOG, default 5); a rank numbers its own slabs consecutively ("local" slab number), which is
+ * also its row in a stored AO tensor uploaded on a communicator (each rank keeps only the full M-vectors of its own slabs).
+ * Second half: own[r]..own[r+1] = slots of rank r (fbeg[f] = first slot of first-contracted index f, nfb+1 entries).
+ * For the chunk of slabs [chunk_base, chunk_base+chunk_width): `rank` computes its local slabs [loc_lo, loc_lo+count);
+ * wblk = the largest count over the ranks = row stride of the exchanged blocks.  After the all-to-all the owner of a slot holds
+ * element (its local slot `row`, global slab `slab`) at lowdin_it_exchanged_offset(). */
+int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t chunk_width, int nranks, int rank, int log_block,
+                         int *own, int64_t *wblk, int64_t *loc_lo, int64_t *count);
+int lowdin_it_slab_owner(int64_t slab, int nranks, int log_block);
+int64_t lowdin_it_slab_local(int64_t slab, int nranks, int log_block);
+int64_t lowdin_it_slab_global(int64_t local_slab, int nranks, int rank, int log_block);
+int64_t lowdin_it_exchanged_offset(int64_t row, int64_t slab, int64_t chunk_base, int64_t wblk, int64_t rows, int nranks, int log_block);
 int lowdin_it_comm_unique_id(char id[128]);
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]);
 /* The same collective semantics for handles of ONE process (rank r = handles[r], each then driven by its own host thread):
  * the all-to-all is a set of direct peer copies ordered by CUDA events.  The handles may share a device, which is how the
  * multi-rank division of work is parity-tested on a one-GPU box. */
 int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks);
+/* What a ONE-PROCESS host (the reference's transformation program is one process) calls on such a group: the transform runs on
+ * all handles at once (one internal host thread per handle); the downloads return the merged list in the reference's order, as a
+ * single GPU would.  Inputs (lowdin_it_set_species, the lowdin_it_ao_* upload) go to every handle of the group; each keeps only
+ * the rows of the AO tensor it owns (2/nranks of the packed tensor per GPU). */
+int lowdin_it_group_transform(lowdin_it_handle *handles, int nranks, int slotA, int slotB, const int win[8], int conv, int symmetric,
+                              double drop_tol);
+int lowdin_it_group_result_count(lowdin_it_handle *handles, int nranks, int64_t *count);
+int lowdin_it_group_download_pairs(lowdin_it_handle *handles, int nranks, int64_t *ij, int64_t *kl, double *v);
+int lowdin_it_group_download_quads(lowdin_it_handle *handles, int nranks, int32_t *p, int32_t *q, int32_t *r, int32_t *s, double *v);
 
 /* ---- tuning ----------------------------------------------------------------------- */
 #define LOWDIN_IT_OPT_WORKSPACE_BYTES 1 /* size of each slab-batch workspace (default 1 GiB) */
@@ -146,6 +185,8 @@ int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks);
 #define LOWDIN_IT_OPT_AO_LIST 11        /* 1 = the uploads that follow keep the canonical AO list on the device as it comes (16 bytes per stored integral, no
                                          * M(M+1)/2 dense tensor); the first quarter is then LIST-DRIVEN: every integral is scattered with its <= 4 images into the
                                          * quarter-transformed slabs (the DIRECT first quarter of Libint2Iface.cpp:793-853 / TransformIntegralsC.f90:545-558) */
+#define LOWDIN_IT_OPT_SLAB_BLOCK_LOG 12 /* log2 of the block of consecutive AO-pair slabs one rank owns in the block-cyclic first half (default 5); set before uploading */
+#define LOWDIN_IT_OPT_Q1_DEBUG 13       /* probe switches of the warp-specialised first quarter (timing experiments only; results are wrong when set) */
 #define LOWDIN_IT_OPT_Q3_RED 10         /* third-quarter accumulation into T3: 0 = read-modify-write epilogue staged through shared memory, 1 = one red.global.add.f64 per element */
 int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value);
 

@@ -21,15 +21,27 @@ ABI_SYMBOLS = [
     "lowdin_it_ao_push_stacks", "lowdin_it_ao_end", "lowdin_it_ao_set_generator", "lowdin_it_transform",
     "lowdin_it_result_count", "lowdin_it_download_pairs", "lowdin_it_download_quads", "lowdin_it_transform_stream",
     "lowdin_it_stream_num_passes", "lowdin_it_transform_all", "lowdin_it_transform_inter_all",
-    "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_shard_plan", "lowdin_it_blocked_offset", "lowdin_it_timers", "lowdin_it_kernel_bench",
+    "lowdin_it_comm_unique_id", "lowdin_it_comm_init", "lowdin_it_shard_plan", "lowdin_it_exchanged_offset", "lowdin_it_slab_owner", "lowdin_it_slab_local", "lowdin_it_slab_global", "lowdin_it_timers", "lowdin_it_kernel_bench",
     "lowdin_it_set_profiling", "lowdin_it_set_option", "lowdin_it_kernel_stats", "lowdin_it_debug_gemm", "lowdin_it_debug_expand",
     "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
-    "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter",
+    "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter", "lowdin_it_result_segments", "lowdin_it_group_transform",
+    "lowdin_it_group_result_count", "lowdin_it_group_download_pairs", "lowdin_it_group_download_quads",
+    "lowdin_it_transform_stream_sink",
 ]
 
 
 class LowdinITError(RuntimeError):
     pass
+
+
+class Block(C.Structure):
+    """lowdin_it_block: one dense block of MO integrals handed to a host sink."""
+    _fields_ = [("conv", C.c_int), ("nslots", C.c_int), ("n_second", C.c_int), ("n_first", C.c_int), ("orb_second0", C.c_int),
+                ("orb_first0", C.c_int), ("second_is_conv_first", C.c_int), ("slot_a", C.POINTER(C.c_int32)),
+                ("slot_b", C.POINTER(C.c_int32)), ("values", C.POINTER(C.c_double))]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Block))
 
 
 def lib_path() -> str:
@@ -65,16 +77,23 @@ def load():
     L.lowdin_it_download_quads.argtypes = [H, _i32p, _i32p, _i32p, _i32p, _f64p]
     L.lowdin_it_transform_stream.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_double, _f64p]
+    L.lowdin_it_transform_stream_sink.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_double, _f64p, SINK_FN, C.c_void_p]
     L.lowdin_it_stream_num_passes.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.POINTER(C.c_int),
                                               C.POINTER(C.c_int)]
     L.lowdin_it_transform_all.argtypes = [_f64pf, _f64p, C.c_int]
     L.lowdin_it_transform_inter_all.argtypes = [_f64pf, _f64pf, _f64p, C.c_int, C.c_int]
     L.lowdin_it_comm_unique_id.argtypes = [C.c_char_p]
     L.lowdin_it_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
-    L.lowdin_it_shard_plan.argtypes = [C.c_int, _i32p, C.c_int64, C.c_int, C.c_int, _i32p, C.POINTER(C.c_int64),
+    L.lowdin_it_shard_plan.argtypes = [C.c_int, _i32p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-    L.lowdin_it_blocked_offset.argtypes = [C.c_int64] * 4
-    L.lowdin_it_blocked_offset.restype = C.c_int64
+    L.lowdin_it_exchanged_offset.argtypes = [C.c_int64] * 5 + [C.c_int, C.c_int]
+    L.lowdin_it_exchanged_offset.restype = C.c_int64
+    L.lowdin_it_slab_owner.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.lowdin_it_slab_local.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.lowdin_it_slab_local.restype = C.c_int64
+    L.lowdin_it_slab_global.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
+    L.lowdin_it_slab_global.restype = C.c_int64
     L.lowdin_it_timers.argtypes = [H, _f64p]
     L.lowdin_it_kernel_bench.argtypes = [H, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double),
                                          C.POINTER(C.c_double)]
@@ -87,6 +106,11 @@ def load():
     L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
     L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
     L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_result_segments.argtypes = [H, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+    L.lowdin_it_group_transform.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_double]
+    L.lowdin_it_group_result_count.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_int64)]
+    L.lowdin_it_group_download_pairs.argtypes = [C.POINTER(H), C.c_int, _i64p, _i64p, _f64p]
+    L.lowdin_it_group_download_quads.argtypes = [C.POINTER(H), C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p]
     L.lowdin_it_debug_first_quarter.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _f64p]
     L.lowdin_it_debug_first_half.argtypes = [H, C.c_int, C.c_int, _i32p, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_void_p,
                                              C.POINTER(C.c_int64)]
@@ -186,6 +210,14 @@ class Transformer:
         self._ck(self.L.lowdin_it_download_quads(self.h, *o, v))
         return (*o, v)
 
+    def result_segments(self):
+        """(pair_index, kept): the window pairs (convention-order index) behind this rank's list and the entries each contributed."""
+        n = C.c_int64()
+        self._ck(self.L.lowdin_it_result_segments(self.h, C.byref(n), None, None))
+        idx, kept = np.zeros(n.value, np.int64), np.zeros(n.value, np.int64)
+        self._ck(self.L.lowdin_it_result_segments(self.h, C.byref(n), idx.ctypes.data, kept.ctypes.data))
+        return idx, kept
+
     def num_passes(self, a, b, win, conv, occ_batch=0):
         w = np.ascontiguousarray(win, dtype=np.int32)
         npass, used = C.c_int(), C.c_int()
@@ -203,6 +235,34 @@ class Transformer:
             ea.ctypes.data if ea is not None else None, eb.ctypes.data if eb is not None else None, lam, sums))
         return sums
 
+    def transform_stream_sink(self, a, b, win, conv, sink, tol=1e-10, occ_batch=0, first_pass=0, n_passes=0, epsA=None, epsB=None, lam=2.0):
+        """transform_stream with every dense result block also delivered to sink(slot_a, slot_b, values[nslots, n_second, n_first],
+        block) on the host (numpy views valid during the call)."""
+        w = np.ascontiguousarray(win, dtype=np.int32)
+        sums = np.zeros(4)
+        ea = np.ascontiguousarray(epsA, dtype=np.float64) if epsA is not None else None
+        eb = np.ascontiguousarray(epsB, dtype=np.float64) if epsB is not None else None
+        err = []
+
+        def cb(_user, bp):
+            try:
+                b_ = bp.contents
+                n = b_.nslots
+                vals = np.ctypeslib.as_array(b_.values, (n, b_.n_second, b_.n_first))
+                sink(np.ctypeslib.as_array(b_.slot_a, (n,)), np.ctypeslib.as_array(b_.slot_b, (n,)), vals, b_)
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
+                return 1
+        fn = SINK_FN(cb)
+        rc = self.L.lowdin_it_transform_stream_sink(
+            self.h, a, b, w, conv, tol, occ_batch, first_pass, n_passes,
+            ea.ctypes.data if ea is not None else None, eb.ctypes.data if eb is not None else None, lam, sums, fn, None)
+        if err:
+            raise err[0]
+        self._ck(rc)
+        return sums
+
     def comm_init(self, rank, nranks, uid: bytes):
         self._ck(self.L.lowdin_it_comm_init(self.h, rank, nranks, uid))
 
@@ -215,7 +275,7 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
-    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST = 8, 9, 10, 11
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG = 8, 9, 10, 11, 12, 13
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT, DEFAULT_FRAG_PERM = 3, 2, 1  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):
@@ -255,6 +315,28 @@ def local_group(transformers):
         raise LowdinITError(load().lowdin_it_last_error(None).decode())
 
 
+def group_transform(transformers, a, b, win, conv, symmetric=False, tol=1e-10):
+    """lowdin_it_group_transform + the merged download: what a one-process host gets from a group of GPUs."""
+    L = load()
+    arr = (C.c_void_p * len(transformers))(*[t.h for t in transformers])
+    w = np.ascontiguousarray(win, dtype=np.int32)
+    if L.lowdin_it_group_transform(arr, len(transformers), a, b, w, conv, int(symmetric), tol):
+        raise LowdinITError(L.lowdin_it_last_error(transformers[0].h).decode())
+    cnt = C.c_int64()
+    L.lowdin_it_group_result_count(arr, len(transformers), C.byref(cnt))
+    n = cnt.value
+    v = np.zeros(n)
+    if conv == CONV_E:
+        ij, kl = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        if L.lowdin_it_group_download_pairs(arr, len(transformers), ij, kl, v):
+            raise LowdinITError(L.lowdin_it_last_error(transformers[0].h).decode())
+        return ij, kl, v
+    o = [np.zeros(n, np.int32) for _ in range(4)]
+    if L.lowdin_it_group_download_quads(arr, len(transformers), *o, v):
+        raise LowdinITError(L.lowdin_it_last_error(transformers[0].h).decode())
+    return (*o, v)
+
+
 def run_ranks(transformers, fn):
     """Run fn(rank, transformer) on one thread per rank (collective calls of an in-process group); returns the results."""
     import threading
@@ -276,18 +358,31 @@ def run_ranks(transformers, fn):
     return out
 
 
-def shard_plan(fbeg, chunk_width, nranks, rank):
-    """(own[nranks+1], wblk, col_lo, col_hi): the library's division of slots and chunk columns among ranks."""
+def shard_plan(fbeg, chunk_base, chunk_width, nranks, rank, log_block=5):
+    """(own[nranks+1], wblk, loc_lo, count): the library's division of slots and of the chunk's slabs among ranks."""
     fbeg = np.ascontiguousarray(fbeg, np.int32)
     own = np.zeros(nranks + 1, np.int32)
-    w, lo, hi = C.c_int64(), C.c_int64(), C.c_int64()
-    if load().lowdin_it_shard_plan(len(fbeg) - 1, fbeg, chunk_width, nranks, rank, own, C.byref(w), C.byref(lo), C.byref(hi)):
+    w, lo, cnt = C.c_int64(), C.c_int64(), C.c_int64()
+    if load().lowdin_it_shard_plan(len(fbeg) - 1, fbeg, chunk_base, chunk_width, nranks, rank, log_block, own, C.byref(w), C.byref(lo),
+                                   C.byref(cnt)):
         raise LowdinITError("bad shard_plan arguments")
-    return own, w.value, lo.value, hi.value
+    return own, w.value, lo.value, cnt.value
 
 
-def blocked_offset(row, col, wblk, rows):
-    return load().lowdin_it_blocked_offset(row, col, wblk, rows)
+def exchanged_offset(row, slab, chunk_base, wblk, rows, nranks, log_block=5):
+    return load().lowdin_it_exchanged_offset(row, slab, chunk_base, wblk, rows, nranks, log_block)
+
+
+def slab_owner(slab, nranks, log_block=5):
+    return load().lowdin_it_slab_owner(slab, nranks, log_block)
+
+
+def slab_local(slab, nranks, log_block=5):
+    return load().lowdin_it_slab_local(slab, nranks, log_block)
+
+
+def slab_global(local, nranks, rank, log_block=5):
+    return load().lowdin_it_slab_global(local, nranks, rank, log_block)
 
 
 def unique_id() -> bytes:

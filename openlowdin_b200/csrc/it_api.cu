@@ -20,6 +20,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace lowdin;
@@ -58,6 +59,7 @@ struct AoSet {
   std::vector<DevBuf> segs;
   DevBuf seg_counts;      // entries kept in each segment (device, unsigned long long)
   int swapped = 0;
+  bool sharded = false;   // data holds full M-vectors of the rank's own slabs only (uploaded on a communicator)
   void release_list() { for (auto &b : segs) b.release(); segs.clear(); }
 };
 constexpr int kMaxListSegs = 4096;
@@ -146,18 +148,28 @@ struct lowdin_it_ctx {
   DevBuf r_i0, r_i1, r_i2, r_i3, r_v;
   int64_t count = 0;
   int res_conv = -1;
+  std::vector<int64_t> res_pair;             // download mode: convention-order index (0-based, over ALL window pairs) of each of this rank's pairs
+  std::vector<int64_t> res_seg;              // ... and the number of entries it kept (the rank's list is the concatenation of these segments)
   double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double sink_bytes = 0;                     // bytes handed to the host sink by the last transform
   double launches = 0;
   cudaEvent_t ev[6] = {};
   // multi-GPU
   int rank = 0, nranks = 1;
   void *comm = nullptr;                      // NCCL communicator (one process per GPU)
   std::shared_ptr<LocalGroup> lgroup;        // or: in-process group of handles
+  int slab_logB = 5;                         // block-cyclic distribution of the first half's slabs: blocks of 2^slab_logB slabs (it_kernels.cuh, slab_owner)
+  void *sink_host[2] = {nullptr, nullptr};   // pinned host ring of the dense-block sink (lowdin_it_transform_stream_sink)
+  size_t sink_host_cap = 0;
+  cudaEvent_t ev_q4[2] = {}, ev_d2h[2] = {};
+  DevBuf coltab;                             // column table of the chunk after the exchange (SRC_RECT_TABLE)
+  DevBuf seg;                                // download mode: kept entries per window pair (convention order)
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
   int q1_variant = 3;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
+  int q1_dbg = 0;                            // probe switches of the warp-specialised first quarter (Q1WsArgs::dbg)
   int q3_red = 0;                            // third-quarter accumulation: 0 = staged read-modify-write epilogue, 1 = red.global.add.f64 (EpiAccRed)
   int frag_perm = 1;                         // TMA kernels: 1 = conflict-free fragment-row permutation (it_gemm_tma.cuh, frag_row); validated on B200 in round 2 (bit-identical, +2.4 % per pass)
   int bench_gen = 1;                         // generator kind used by lowdin_it_kernel_bench kind 2
@@ -370,6 +382,7 @@ struct Plan {
 struct PassTables {
   int f0 = 0, nfb = 0, nslots = 0;
   std::vector<int32_t> table, sa, sb, ss, sf, order;
+  std::vector<int64_t> order_conv;  // convention-order index (over all window pairs of the plan) of order[k]
   std::vector<int> fbeg;  // [nfb+1] first slot of each f
 };
 
@@ -401,6 +414,12 @@ int build_plan(lowdin_it_handle h, int a, int b, const int win[8], int conv, int
   setup(pl.h2, B, 2, 3);
   pl.nslabs1 = B.M;
   pl.src = h->ao[a][b].src;
+  if (h->nranks > 1) {
+    // the first half runs over the rank's own slabs (block-cyclic, fixed at upload): stored tensors must be the row-sharded ones
+    if ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !h->ao[a][b].sharded)
+      return fail(h, "the AO integrals of this species pair were uploaded before the communicator existed; upload them again");
+    pl.src.logB = h->slab_logB; pl.src.G = h->nranks; pl.src.rank = h->rank;
+  } else if (h->ao[a][b].sharded) return fail(h, "the AO integrals of this species pair are one rank's share of a communicator upload");
   // needed first pairs, convention order
   pl.pairs_s.clear(); pl.pairs_f.clear(); pl.pairs_a.clear(); pl.pairs_b.clear();
   std::vector<int> per_f(std::max(pl.h1.nf, 1), 0);
@@ -447,7 +466,8 @@ void build_pass(const Plan &pl, int f0, int nfb, PassTables &pt) {
   pt.fbeg[nfb] = slot;
   pt.nslots = slot;
   std::sort(byconv.begin(), byconv.end());
-  for (auto &e : byconv) pt.order.push_back(e.second);
+  pt.order_conv.clear();
+  for (auto &e : byconv) { pt.order.push_back(e.second); pt.order_conv.push_back(e.first); }
 }
 
 int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
@@ -466,7 +486,7 @@ int launch_expand(lowdin_it_handle h, const AoSource &src, int64_t slab0, int64_
   switch (src.kind) {
     case SRC_SYM_PACKED: expand_block_kernel<SRC_SYM_PACKED><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     case SRC_RECT: expand_block_kernel<SRC_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
-    case SRC_RECT_BLOCKED: expand_block_kernel<SRC_RECT_BLOCKED><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
+    case SRC_RECT_TABLE: expand_block_kernel<SRC_RECT_TABLE><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     case SRC_HASH_SYM: expand_block_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     case SRC_RANKK: expand_block_kernel<SRC_RANKK><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
     default: expand_block_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(src, slab0, n, r0, nrows, c0, ncols, colbase, ldx, X); break;
@@ -511,7 +531,7 @@ cudaError_t launch_q1_ws_cfg(lowdin_it_handle h, const AoSource &src, int64_t sl
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(nc, 128) * (int64_t)bc;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
-  Q1WsArgs q{slab0, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
+  Q1WsArgs q{slab0, src.logB, src.G, src.rank, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt, h->q1_dbg};
   kern<<<grid, v4 ? 384 : 512, smem, h->stream>>>(mapB, q);
   h->launches += 1;
   return cudaGetLastError();
@@ -530,7 +550,7 @@ cudaError_t launch_q1_ws5_cfg(lowdin_it_handle h, const AoSource &src, int64_t s
   if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(nc, 256) * (int64_t)bc;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
-  Q1WsArgs q{slab0, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt};
+  Q1WsArgs q{slab0, src.logB, src.G, src.rank, bc, nc, nfb, (uint32_t)(KIND == SRC_HASH_SYM ? src.M : src.aux), src.seed, T1t, ldt, h->q1_dbg};
   kern<<<grid, 512, smem, h->stream>>>(mapB, q);
   h->launches += 1;
   return cudaGetLastError();
@@ -589,7 +609,8 @@ int list_first_quarter(lowdin_it_handle h, const Plan &pl, const PassTables &pt)
   AoSet &S = h->ao[pl.a][pl.b];
   const int nc = hf.nc, nfb = pt.nfb, nfbp = (nfb + 3) & ~3;
   const int n_slab = h->sp[pl.b].n;
-  const size_t t1_bytes = (size_t)pl.nslabs1 * nc * nfbp * sizeof(double);
+  const int64_t nloc = slabs_owned_below(pl.nslabs1, h->slab_logB, h->nranks, h->rank);  // this rank's slabs (all of them on one GPU)
+  const size_t t1_bytes = std::max<size_t>((size_t)nloc * nc * nfbp, 1) * sizeof(double);
   CK(h->Cw.ensure((size_t)nc * nfbp * sizeof(double)));
   CK(h->T1list.ensure(t1_bytes));
   ProfScope ps(h, 1, 2.0 * (double)pl.nslabs1 * nc * (double)nc * nfb);
@@ -598,7 +619,7 @@ int list_first_quarter(lowdin_it_handle h, const Plan &pl, const PassTables &pt)
   for (size_t i = 0; i < S.segs.size(); ++i) {
     list_first_quarter_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(S.segs[i].as<ListEntry>(), S.seg_counts.as<unsigned long long>() + i,
                                                                    pl.intra ? 1 : 0, S.swapped, nc, n_slab, h->Cw.as<double>(), nfb, nfbp,
-                                                                   h->T1list.as<double>());
+                                                                   h->T1list.as<double>(), h->slab_logB, h->nranks, h->rank);
     h->launches += 1;
   }
   CK(cudaGetLastError());
@@ -641,7 +662,7 @@ int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt
 int64_t first_half_batch(lowdin_it_handle h, const Plan &pl, int nfb, int64_t count) {
   const int nc = pl.h1.nc;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK || pl.src.kind == SRC_RECT_BLOCKED);
+  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK);
   const size_t per_slab = std::max(dense ? (size_t)nc * ldx : (size_t)0, (size_t)nfb * ldt) * sizeof(double);
   int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
   B = std::min<int64_t>(B, count);
@@ -657,7 +678,7 @@ int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t
   const Half &hf = pl.h1;
   const int nc = hf.nc, nfb = pt.nfb;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK || pl.src.kind == SRC_RECT_BLOCKED);
+  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK);
   const int64_t B = first_half_batch(h, pl, nfb, count);
   if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
@@ -718,13 +739,20 @@ int second_half_partial(lowdin_it_handle h, const Plan &pl, const AoSource &hsrc
   return 0;
 }
 
-// How one chunk of `width` AO-pair slabs and the pass's slots are divided among G ranks:
-// slabs in G contiguous blocks of wblk columns; slots by contiguous blocks of first-contracted indices.
-void shard_plan(int nfb, const int *fbeg, int64_t width, int G, int rank, int *own, int64_t *wblk, int64_t *c_lo, int64_t *c_hi) {
+// How one chunk of AO-pair slabs [base, base + width) and the pass's slots are divided among G ranks:
+// slabs block-cyclically (blocks of 2^logB slabs, block b on rank b % G -- it_kernels.cuh, slab_owner): rank r computes its
+// own slabs of the chunk, which are the consecutive LOCAL slabs [loc_lo, loc_lo + cnt); wblk = the largest cnt over the ranks
+// (row stride of every rank's H and of the exchanged blocks).  Slots by contiguous blocks of first-contracted indices.
+void shard_plan(int nfb, const int *fbeg, int64_t base, int64_t width, int G, int rank, int logB, int *own, int64_t *wblk, int64_t *loc_lo,
+                int64_t *cnt) {
   for (int r = 0; r <= G; ++r) own[r] = fbeg[(int)((int64_t)nfb * r / G)];
-  *wblk = ceil_div(width, G);
-  *c_lo = std::min<int64_t>(width, *wblk * rank);
-  *c_hi = std::min<int64_t>(width, *c_lo + *wblk);
+  int64_t w = 0;
+  for (int r = 0; r < G; ++r) {
+    const int64_t lo = slabs_owned_below(base, logB, G, r), c = slabs_owned_below(base + width, logB, G, r) - lo;
+    w = std::max(w, c);
+    if (r == rank) { *loc_lo = lo; *cnt = c; }
+  }
+  *wblk = w;
 }
 
 // Ranks size their batches from their OWN free memory, which differs by a few MB from rank to rank; everything that
@@ -753,7 +781,9 @@ int agree_min(lowdin_it_handle h, int64_t *v) {
 }
 
 struct Consumer {
-  int mode = 0;  // 0: compaction (download), 1: streaming reduce
+  int mode = 0;  // 0: compaction (download), 1: streaming reduce (+ optional host sink of every dense result block)
+  lowdin_it_sink_fn sink = nullptr;
+  void *sink_user = nullptr;
   double tol = 1e-10;
   const double *epsA = nullptr, *epsB = nullptr;  // device
   double lambda = 2.0;
@@ -777,6 +807,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     CK(cudaMemsetAsync(h->sums.p, 0, 4 * sizeof(double), h->stream));
   }
   h->count = 0;
+  h->sink_bytes = 0;
   if (cons.mode == 0) {
     // An empty window (e.g. a one-function species under MP2: virtual window 2..1) is a valid transform with no
     // integrals: the reference writes a terminator-only moint.dat (C.f90:450-456, E.f90:1263-1268).
@@ -806,16 +837,14 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       return 1;
     // slot ownership: rank r owns the slots of a contiguous block of first-contracted indices
     std::vector<int> own(G + 1, 0);
-    { int64_t w_, a_, b_; shard_plan(nfb, pt.fbeg.data(), 0, G, h->rank, own.data(), &w_, &a_, &b_); }
+    { int64_t w_, a_, b_; shard_plan(nfb, pt.fbeg.data(), 0, 0, G, h->rank, h->slab_logB, own.data(), &w_, &a_, &b_); }
     const int s_lo = own[h->rank], s_hi = own[h->rank + 1], nmine = s_hi - s_lo;
     // ---- device memory of the pass: T3 accumulators (own slots) + one chunk of half-transformed rows ----
     const size_t t3_bytes = std::max<size_t>((size_t)std::max(nmine, 1) * nf2 * ldt2, 1) * sizeof(double);
     CK(h->T3.ensure(t3_bytes));
     CK(cudaMemsetAsync(h->T3.p, 0, t3_bytes, h->stream));
     if (pl.src.kind == SRC_LIST) {
-      if (G > 1) return fail(h, "the list-driven first quarter runs on one GPU; upload the dense tensor for a communicator");
-      if (list_first_quarter(h, pl, pt)) return 1;
-      flops += 0.0;  // counted with the chunks below (the algorithmic count is the dense one)
+      if (list_first_quarter(h, pl, pt)) return 1;  // flops are counted with the chunks below (the algorithmic count is the dense one)
     }
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -851,19 +880,27 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     float ms_first = 0, ms_exch = 0, ms_second = 0;
     for (const Chunk &ck : chunks) {
       // ---------------- first half (E.f90:1043-1132) over this rank's share of the chunk's slabs ----------------
-      int64_t wblk, c_lo, c_hi;
-      shard_plan(nfb, pt.fbeg.data(), ck.width, G, h->rank, own.data(), &wblk, &c_lo, &c_hi);
-      const int64_t ldh = (G > 1) ? wblk : ck.width;
+      int64_t wblk, loc_lo, cnt;  // this rank's slabs of the chunk: local slabs [loc_lo, loc_lo + cnt) (G == 1: the chunk itself)
+      shard_plan(nfb, pt.fbeg.data(), ck.base, ck.width, G, h->rank, h->slab_logB, own.data(), &wblk, &loc_lo, &cnt);
+      const int64_t ldh = (G > 1) ? std::max<int64_t>(wblk, 1) : ck.width;
       CK(h->H.ensure(std::max<size_t>((size_t)pt.nslots * ldh, 1) * sizeof(double)));
       CK(cudaEventRecord(h->ev[1], h->stream));
-      if (first_half(h, pl, pt, ck.base + c_lo, c_hi - c_lo, h->H.as<double>(), ldh, 0, half_tol)) return 1;
-      flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)(c_hi - c_lo);
+      if (cnt > 0 && first_half(h, pl, pt, loc_lo, cnt, h->H.as<double>(), ldh, 0, half_tol)) return 1;
+      flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)cnt;
       CK(cudaEventRecord(h->ev[2], h->stream));
       // ---------------- exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203) ----------------
       AoSource hsrc{SRC_RECT, h->H.as<double>(), ck.width, ldh, 0, 0};
       if (G > 1) {
-        ProfScope ps(h, 7, (double)pt.nslots * (double)(c_hi - c_lo) * 8.0);
-        if (exchange_chunk(h, own, wblk, &hsrc)) return 1;
+        ProfScope ps(h, 7, (double)pt.nslots * (double)cnt * 8.0);
+        if (exchange_chunk(h, own, ldh, &hsrc)) return 1;
+        // column table: chunk column -> (sending rank's block, its local column)
+        RankStarts st{};
+        for (int r = 0; r < G; ++r) st.lo[r] = slabs_owned_below(ck.base, h->slab_logB, G, r);
+        CK(h->coltab.ensure((size_t)ck.width * sizeof(int64_t)));
+        column_table_kernel<<<(unsigned)ceil_div(ck.width, 256), 256, 0, h->stream>>>(ck.base, ck.width, h->slab_logB, G, (int64_t)nmine, ldh, st,
+                                                                                     h->coltab.as<int64_t>());
+        CK(cudaGetLastError());
+        hsrc = AoSource{SRC_RECT_TABLE, h->H2.as<double>(), ck.width, ldh, (int64_t)nmine, 0, 0, reinterpret_cast<const double *>(h->coltab.p)};
       }
       CK(cudaEventRecord(h->ev[3], h->stream));
       // ---------------- third quarter of the chunk, accumulated into T3 (own slots) ----------------
@@ -889,8 +926,35 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     float ms_consume = 0;
     if (nmine > 0) {
       const int fr_lo = (int)((int64_t)nfb * h->rank / G), fr_hi = (int)((int64_t)nfb * (h->rank + 1) / G);
-      const int64_t out_slots_cap = download ? nmine : std::max<int64_t>(pl.max_slots_per_f, (int64_t)(out_need / (per_out * 8.0)));
-      CK(h->OUT.ensure(std::max<size_t>((size_t)out_slots_cap * per_out, 1) * sizeof(double)));
+      const bool sinking = (cons.mode == 1 && cons.sink != nullptr);
+      // with a host sink the groups are smaller (one workspace, 1 GiB: finer pipelining of Q4, device-to-host copy and the host's consumer) and
+      // OUT is double-buffered: the copy of group g overlaps the fourth quarter of group g + 1
+      const double group_bytes = sinking ? std::min(out_need, std::max((double)h->workspace_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
+      const int64_t out_slots_cap = download ? nmine : std::max<int64_t>(pl.max_slots_per_f, (int64_t)(group_bytes / (per_out * 8.0)));
+      const size_t out_elems = std::max<size_t>((size_t)out_slots_cap * per_out, 1);
+      CK(h->OUT.ensure(out_elems * (sinking ? 2 : 1) * sizeof(double)));
+      int gi = 0, pending = -1;            // sink: group counter, ring slot whose block the host has not consumed yet
+      lowdin_it_block blk_pending{};
+      if (sinking) {
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+          if (!h->ev_q4[i]) CK(cudaEventCreateWithFlags(&h->ev_q4[i], cudaEventDisableTiming));
+          if (!h->ev_d2h[i]) CK(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+        }
+        if (h->sink_host_cap < out_elems * sizeof(double)) {
+          for (int i = 0; i < 2; ++i) { if (h->sink_host[i]) cudaFreeHost(h->sink_host[i]); h->sink_host[i] = nullptr; }
+          h->sink_host_cap = 0;
+          for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&h->sink_host[i], out_elems * sizeof(double), cudaHostAllocDefault));
+          h->sink_host_cap = out_elems * sizeof(double);
+        }
+      }
+      auto flush_pending = [&]() -> int {   // hand the block whose copy was enqueued last to the host consumer
+        if (pending < 0) return 0;
+        CK(cudaEventSynchronize(h->ev_d2h[pending]));
+        pending = -1;
+        if (cons.sink(cons.sink_user, &blk_pending)) return fail(h, "the sink callback returned an error");
+        return 0;
+      };
       for (int fa = fr_lo; fa < fr_hi;) {
         int fb = fa + 1;
         while (fb < fr_hi && pt.fbeg[fb + 1] - pt.fbeg[fa] <= out_slots_cap) ++fb;
@@ -898,7 +962,9 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         fa = fb;
         if (gn <= 0) continue;
         const double *T3g = h->T3.as<double>() + (int64_t)(g_lo - s_lo) * nf2 * ldt2;
-        double *OUT = h->OUT.as<double>();
+        const int ring = sinking ? (gi & 1) : 0;
+        double *OUT = h->OUT.as<double>() + (size_t)ring * out_elems;
+        if (sinking && gi >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[ring], 0));  // the copy of group gi - 2 has left this buffer
         // batches bounded by the GEMM grid (N dimension = slots * nf2)
         const int64_t Bq = std::max<int64_t>(1, std::min<int64_t>(gn, (int64_t)2000000000 / std::max(nf2, 1) / 64));
         for (int64_t s = 0; s < gn; s += Bq) {
@@ -923,17 +989,37 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
           h->launches += 1;
           CK(cudaGetLastError());
         }
+        if (sinking) {
+          // the previous block goes to the host consumer while this group's fourth quarter runs; it also frees its ring slot
+          if (flush_pending()) return 1;
+          CK(cudaEventRecord(h->ev_q4[ring], h->stream));
+          CK(cudaStreamWaitEvent(h->copy_stream, h->ev_q4[ring], 0));
+          CK(cudaMemcpyAsync(h->sink_host[ring], OUT, (size_t)gn * per_out * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+          CK(cudaEventRecord(h->ev_d2h[ring], h->copy_stream));
+          blk_pending = lowdin_it_block{pl.conv, gn, ns2, nf2, h2.ls, h2.lf, h2.first_is_conv_second ? 1 : 0, pt.sa.data() + g_lo, pt.sb.data() + g_lo,
+                                        static_cast<const double *>(h->sink_host[ring])};
+          pending = ring;
+          h->sink_bytes += (double)gn * per_out * sizeof(double);
+          ++gi;
+        }
       }
+      if (sinking && flush_pending()) return 1;
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
+    if (download) { h->res_pair.clear(); h->res_seg.clear(); }
     if (nmine > 0 && download) {
+      // this rank's window pairs in the reference's loop order, as slots relative to its first one (one GPU: all of them)
+      std::vector<int32_t> own_order;
+      for (size_t k = 0; k < pt.order.size(); ++k)
+        if (pt.order[k] >= s_lo && pt.order[k] < s_hi) { own_order.push_back(pt.order[k] - s_lo); h->res_pair.push_back(pt.order_conv[k]); }
+      if (upload_i32(h, h->order, own_order)) return 1;
       SelectArgs sa{};
       sa.OUT = h->OUT.as<double>(); sa.order = h->order.as<int32_t>(); sa.nslots_batch = nmine; sa.ns2 = ns2; sa.nf2 = nf2;
       sa.swap2 = h2.first_is_conv_second ? 0 : 1;
       sa.n_outer = std::max(0, pl.win[5] - pl.win[4] + 1); sa.n_inner = std::max(0, pl.win[7] - pl.win[6] + 1);
       sa.lo_outer = pl.win[4]; sa.lo_inner = pl.win[6];
       sa.conv = pl.conv; sa.symmetric = pl.symmetric; sa.intra = pl.intra ? 1 : 0;
-      sa.slot_a = h->sa.as<int32_t>(); sa.slot_b = h->sb.as<int32_t>();
+      sa.slot_a = h->sa.as<int32_t>() + s_lo; sa.slot_b = h->sb.as<int32_t>() + s_lo;
       sa.nA = h->sp[pl.a].n; sa.nB = h->sp[pl.b].n; sa.tol = cons.tol;
       const int64_t ncand = (int64_t)nmine * sa.n_outer * sa.n_inner;
       const int64_t nblk = ceil_div(ncand, SEL_CHUNK);
@@ -966,7 +1052,16 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         select_emit_kernel<<<(unsigned)nblk, SEL_THREADS, 0, h->stream>>>(sa, ncand, h->blockoff.as<int64_t>(), ea);
         h->launches += 1;
         CK(cudaGetLastError());
-      }
+        // entries kept per window pair: the segments a host merges the ranks' lists by (lowdin_it_result_segments)
+        CK(h->seg.ensure((size_t)nmine * sizeof(unsigned long long)));
+        select_segments_kernel<<<(unsigned)nmine, SEL_THREADS, 0, h->stream>>>(sa, h->seg.as<unsigned long long>());
+        h->launches += 1;
+        CK(cudaGetLastError());
+        std::vector<unsigned long long> seg(nmine);
+        CK(cudaMemcpyAsync(seg.data(), h->seg.p, (size_t)nmine * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->res_seg.assign(seg.begin(), seg.end());
+      } else h->res_seg.assign(h->res_pair.size(), 0);
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -989,7 +1084,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
 
 // All-to-all of one chunk of the half-transformed block between the halves.  Every rank holds
 // H[slot][its own wblk columns of the chunk] for ALL slots; afterwards it holds, for ITS slots, all columns as G
-// blocks [g][slot_local][wblk], which the chunk expansion reads in place (SRC_RECT_BLOCKED).
+// blocks [g][slot_local][wblk], which the chunk expansion reads in place through the chunk's column table (SRC_RECT_TABLE).
 int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out) {
   const int G = h->nranks;
   if (!h->comm && !h->lgroup) return fail(h, "multi-GPU transform without a communicator");
@@ -1012,7 +1107,6 @@ int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk
     if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the exchange");
     for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->stream, L.done[g], 0));  // my H is rewritten only after every peer has pulled
     h->launches += 1;
-    *src_out = AoSource{SRC_RECT_BLOCKED, h->H2.as<double>(), src_out->M, wblk, (int64_t)mine, 0};
     return 0;
   }
   int rc = g_nccl.GroupStart();
@@ -1025,7 +1119,7 @@ int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk
   if (rc == 0) rc = g_nccl.GroupEnd();
   if (rc != 0) return fail(h, std::string("NCCL all-to-all failed: ") + g_nccl.GetErrorString(rc));
   h->launches += 1;
-  *src_out = AoSource{SRC_RECT_BLOCKED, h->H2.as<double>(), src_out->M, wblk, (int64_t)mine, 0};
+  (void)src_out;
   return 0;
 }
 
@@ -1071,13 +1165,14 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
   for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); a.release_list(); a.seg_counts.release(); }
-  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
+  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->coltab, &h->seg, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : h->prof_pool) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
+  for (int i = 0; i < 2; ++i) { if (h->sink_host[i]) cudaFreeHost(h->sink_host[i]); if (h->ev_q4[i]) cudaEventDestroy(h->ev_q4[i]); if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -1132,10 +1227,21 @@ int lowdin_it_ao_begin(lowdin_it_handle h, int a, int b, int swapped) {
     CK(S.seg_counts.ensure(kMaxListSegs * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(S.seg_counts.p, 0, kMaxListSegs * sizeof(unsigned long long), h->stream));
     S.src = AoSource{SRC_LIST, nullptr, Ma, 0, Mb, 0};
+    S.sharded = false;
+  } else if (h->nranks > 1) {
+    // On a communicator a rank stores only the slabs it computes in the first half (block-cyclic, it_kernels.cuh slab_owner): the
+    // full M_a-vector of each, i.e. 2/G of the packed tensor per rank.  Every rank is pushed the whole list and keeps its rows.
+    const int64_t nloc = slabs_owned_below(Mb, h->slab_logB, h->nranks, h->rank);
+    const size_t cnt = std::max<size_t>((size_t)nloc * Ma, 1);
+    CK(S.data.ensure(cnt * sizeof(double)));
+    CK(cudaMemsetAsync(S.data.p, 0, cnt * sizeof(double), h->stream));
+    S.src = AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, nloc, 0};
+    S.sharded = true;
   } else {
     CK(S.data.ensure(count * sizeof(double)));
     CK(cudaMemsetAsync(S.data.p, 0, count * sizeof(double), h->stream));  // C.f90:669-685 zero-initialises
     S.src = (a == b) ? AoSource{SRC_SYM_PACKED, S.data.as<double>(), Ma, 0, 0, 0} : AoSource{SRC_RECT, S.data.as<double>(), Ma, Ma, Mb, 0};
+    S.sharded = false;
   }
   S.valid = false;
   h->up_a = a; h->up_b = b; h->up_swapped = swapped;
@@ -1188,7 +1294,7 @@ int push_piece(lowdin_it_handle h, const int32_t *p, const int32_t *q, const int
     append_list_kernel<<<grid, 256, 0, h->stream>>>(w, h->up_a == h->up_b, h->up_swapped, na, nb, AS.segs.back().as<ListEntry>(),
                                                     AS.seg_counts.as<unsigned long long>() + (AS.segs.size() - 1), state);
   } else {
-    ScatterDst d{AS.data.as<double>(), h->up_a == h->up_b, h->up_swapped, na, nb, 0, 0, 1, 0};
+    ScatterDst d{AS.data.as<double>(), h->up_a == h->up_b, h->up_swapped, na, nb, AS.sharded ? 1 : 0, h->slab_logB, h->nranks, h->rank};
     scatter_stacks_kernel<<<grid, 256, 0, h->stream>>>(w, d, state);
   }
   CK(cudaGetLastError());
@@ -1270,6 +1376,7 @@ int lowdin_it_ao_set_generator(lowdin_it_handle h, int a, int b, int kind, uint6
   AoSet &S = h->ao[a][b];
   S.data.release();
   S.release_list();
+  S.sharded = false;
   S.src = (a == b) ? AoSource{SRC_HASH_SYM, nullptr, h->sp[a].M, 0, 0, seed, kind} : AoSource{SRC_HASH_RECT, nullptr, h->sp[a].M, 0, h->sp[b].M, seed, kind};
   S.valid = true;
   return 0;
@@ -1282,6 +1389,8 @@ int lowdin_it_ao_set_rankk(lowdin_it_handle h, int a, int b, int K, const double
   CK(cudaSetDevice(h->device));
   AoSet &S = h->ao[a][b];
   S.data.release();
+  S.release_list();
+  S.sharded = false;
   const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
   CK(S.fa.ensure((size_t)RANKK * Ma * sizeof(double)));
   CK(cudaMemsetAsync(S.fa.p, 0, (size_t)RANKK * Ma * sizeof(double), h->stream));
@@ -1308,18 +1417,26 @@ int lowdin_it_ao_materialize(lowdin_it_handle h, int a, int b) {
   if (src.kind != SRC_HASH_SYM && src.kind != SRC_HASH_RECT && src.kind != SRC_RANKK) return fail(h, "ao_materialize: the AO set is not a generated one");
   const bool intra = (a == b);
   const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
-  const size_t count = intra ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb);
-  CK(S.data.ensure(count * sizeof(double)));
-  const unsigned grid = (unsigned)std::min<int64_t>(Mb, (int64_t)h->num_sms * 16);
-  double *dst = S.data.as<double>();
+  const bool shard = h->nranks > 1;  // on a communicator: the rank's own rows only, as an upload would leave them
+  const int64_t nrows = shard ? slabs_owned_below(Mb, h->slab_logB, h->nranks, h->rank) : Mb;
+  const size_t count = shard ? std::max<size_t>((size_t)nrows * Ma, 1) : (intra ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb));
+  DevBuf fresh;  // the generator's factor arrays (kind K) stay alive until the fill is done
+  CK(fresh.ensure(count * sizeof(double)));
+  AoSource gsrc = src;
+  if (shard) { gsrc.logB = h->slab_logB; gsrc.G = h->nranks; gsrc.rank = h->rank; }
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nrows, (int64_t)h->num_sms * 16));
+  double *dst = fresh.as<double>();
   switch (src.kind) {
-    case SRC_HASH_SYM: materialize_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(src, 1, Ma, Ma, dst); break;
-    case SRC_HASH_RECT: materialize_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(src, 0, Ma, Mb, dst); break;
-    default: materialize_kernel<SRC_RANKK><<<grid, 256, 0, h->stream>>>(src, intra ? 1 : 0, Ma, intra ? Ma : Mb, dst); break;
+    case SRC_HASH_SYM: materialize_kernel<SRC_HASH_SYM><<<grid, 256, 0, h->stream>>>(gsrc, 1, Ma, nrows, dst); break;
+    case SRC_HASH_RECT: materialize_kernel<SRC_HASH_RECT><<<grid, 256, 0, h->stream>>>(gsrc, 0, Ma, nrows, dst); break;
+    default: materialize_kernel<SRC_RANKK><<<grid, 256, 0, h->stream>>>(gsrc, intra ? 1 : 0, Ma, nrows, dst); break;
   }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  S.src = intra ? AoSource{SRC_SYM_PACKED, dst, Ma, 0, 0, 0} : AoSource{SRC_RECT, dst, Ma, Ma, Mb, 0};
+  S.data.release();
+  S.data = fresh;
+  S.sharded = shard;
+  S.src = shard ? AoSource{SRC_RECT, dst, Ma, Ma, nrows, 0} : (intra ? AoSource{SRC_SYM_PACKED, dst, Ma, 0, 0, 0} : AoSource{SRC_RECT, dst, Ma, Ma, Mb, 0});
   return 0;
 }
 
@@ -1329,11 +1446,11 @@ int lowdin_it_transform(lowdin_it_handle h, int a, int b, const int win[8], int 
   Plan pl;
   if (build_plan(h, a, b, win, conv, symmetric, pl)) return 1;
   Consumer cons; cons.mode = 0; cons.tol = drop_tol;
-  if (h->nranks > 1) return fail(h, "lowdin_it_transform is single-GPU; use lowdin_it_transform_stream on a communicator");
-  // download mode keeps the dense result block of every window pair and the third-quarter accumulators: check that they fit
+  // download mode keeps the dense result block of every window pair (of this rank's share of them, on a communicator) and the
+  // third-quarter accumulators: check that they fit
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const double need = (double)pl.pairs_s.size() * ((double)pl.h2.ns * pl.h2.nf + (double)pl.h2.nf * roundup2(pl.h2.nc)) * 8.0;
+  const double need = (double)pl.pairs_s.size() / h->nranks * ((double)pl.h2.ns * pl.h2.nf + (double)pl.h2.nf * roundup2(pl.h2.nc)) * 8.0;
   if (need > 0.8 * ((double)free_b + (double)h->T3.cap + (double)h->OUT.cap + (double)h->H.cap))
     return fail(h, "result block does not fit in device memory; use lowdin_it_transform_stream");
   return run_passes(h, pl, 0, 0, 0, cons, nullptr);
@@ -1342,6 +1459,14 @@ int lowdin_it_transform(lowdin_it_handle h, int a, int b, const int win[8], int 
 int lowdin_it_result_count(lowdin_it_handle h, int64_t *count) {
   if (!h || !count) return 1;
   *count = h->count;
+  return 0;
+}
+
+int lowdin_it_result_segments(lowdin_it_handle h, int64_t *npairs, int64_t *pair_index, int64_t *kept) {
+  if (!h || !npairs) return 1;
+  *npairs = (int64_t)h->res_pair.size();
+  if (pair_index) memcpy(pair_index, h->res_pair.data(), h->res_pair.size() * sizeof(int64_t));
+  if (kept) memcpy(kept, h->res_seg.data(), h->res_seg.size() * sizeof(int64_t));
   return 0;
 }
 
@@ -1400,7 +1525,7 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
   const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
-  const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 : 0.0;  // T1list[slab][nu][f]
+  const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 / G : 0.0;  // T1list[own slab][nu][f]
   int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
   if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
   const int qmax = (int)qmax64;
@@ -1426,13 +1551,19 @@ int lowdin_it_stream_num_passes(lowdin_it_handle h, int a, int b, const int win[
 
 int lowdin_it_transform_stream(lowdin_it_handle h, int a, int b, const int win[8], int conv, double drop_tol, int occ_batch,
                                int first_pass, int n_passes, const double *epsA, const double *epsB, double lambda, double sums[4]) {
+  return lowdin_it_transform_stream_sink(h, a, b, win, conv, drop_tol, occ_batch, first_pass, n_passes, epsA, epsB, lambda, sums, nullptr, nullptr);
+}
+
+int lowdin_it_transform_stream_sink(lowdin_it_handle h, int a, int b, const int win[8], int conv, double drop_tol, int occ_batch,
+                                    int first_pass, int n_passes, const double *epsA, const double *epsB, double lambda, double sums[4],
+                                    lowdin_it_sink_fn sink, void *user) {
   if (!h) return 1;
   CK(cudaSetDevice(h->device));
   Plan pl;
   if (build_plan(h, a, b, win, conv, 0, pl)) return 1;
   int used = 0;
   if (pick_occ_batch(h, pl, occ_batch, &used)) return 1;
-  Consumer cons; cons.mode = 1; cons.tol = drop_tol; cons.lambda = lambda;
+  Consumer cons; cons.mode = 1; cons.tol = drop_tol; cons.lambda = lambda; cons.sink = sink; cons.sink_user = user;
   if (epsA) {
     const int na = h->sp[a].ncols, nb = h->sp[b].ncols;
     CK(h->epsA.ensure(na * sizeof(double)));
@@ -1468,8 +1599,14 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->split_row_tail = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_FRAG_PERM:
       h->frag_perm = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_SLAB_BLOCK_LOG:
+      if (value < 0 || value > 20) return fail(h, "slab block size must be 2^0 .. 2^20");
+      for (auto &row : h->ao) for (auto &a : row) if (a.sharded) return fail(h, "the slab block size cannot change while row-sharded AO integrals are resident");
+      h->slab_logB = (int)value; return 0;
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_Q1_DEBUG:
+      h->q1_dbg = (int)value; return 0;
     case LOWDIN_IT_OPT_Q3_RED:
       h->q3_red = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_ASYNC_PUSH:
@@ -1571,14 +1708,22 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------
-int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_width, int nranks, int rank, int *own, int64_t *wblk,
-                         int64_t *col_lo, int64_t *col_hi) {
-  if (nfb < 1 || !fbeg || nranks < 1 || rank < 0 || rank >= nranks || !own || !wblk || !col_lo || !col_hi) return 1;
-  shard_plan(nfb, fbeg, chunk_width, nranks, rank, own, wblk, col_lo, col_hi);
+int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t chunk_width, int nranks, int rank, int log_block, int *own,
+                         int64_t *wblk, int64_t *loc_lo, int64_t *count) {
+  if (nfb < 1 || !fbeg || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks || log_block < 0 || log_block > 20 || chunk_base < 0 ||
+      chunk_width < 0 || !own || !wblk || !loc_lo || !count)
+    return 1;
+  shard_plan(nfb, fbeg, chunk_base, chunk_width, nranks, rank, log_block, own, wblk, loc_lo, count);
   return 0;
 }
-
-int64_t lowdin_it_blocked_offset(int64_t row, int64_t col, int64_t wblk, int64_t rows) { return blocked_offset(row, col, wblk, rows); }
+int lowdin_it_slab_owner(int64_t slab, int nranks, int log_block) { return nranks > 1 ? slab_owner(slab, log_block, nranks) : 0; }
+int64_t lowdin_it_slab_local(int64_t slab, int nranks, int log_block) { return nranks > 1 ? slab_local(slab, log_block, nranks) : slab; }
+int64_t lowdin_it_slab_global(int64_t local, int nranks, int rank, int log_block) { return slab_global(local, log_block, nranks, rank); }
+int64_t lowdin_it_exchanged_offset(int64_t row, int64_t slab, int64_t chunk_base, int64_t wblk, int64_t rows, int nranks, int log_block) {
+  if (nranks <= 1) return row * wblk + (slab - chunk_base);
+  const int r = slab_owner(slab, log_block, nranks);
+  return ((int64_t)r * rows + row) * wblk + (slab_local(slab, log_block, nranks) - slabs_owned_below(chunk_base, log_block, nranks, r));
+}
 
 int lowdin_it_comm_unique_id(char id[128]) {
   std::string err;
@@ -1590,7 +1735,7 @@ int lowdin_it_comm_unique_id(char id[128]) {
 
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]) {
   if (!h) return 1;
-  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, "bad rank / nranks");
+  if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return fail(h, "bad rank / nranks (1..16 ranks)");
   CK(cudaSetDevice(h->device));
   if (nranks == 1) { h->rank = 0; h->nranks = 1; return 0; }
   std::string err;
@@ -1661,6 +1806,83 @@ int lowdin_it_comm_init_local(lowdin_it_handle *handles, int nranks) {
   }
   for (int r = 0; r < nranks; ++r) { handles[r]->rank = r; handles[r]->nranks = nranks; handles[r]->lgroup = L; }
   return 0;
+}
+
+// ---- single-process multi-GPU: the calls a one-process host (the reference's is one) makes for a whole group ----------------
+}  // extern "C"
+namespace {
+// Merge the ranks' lists into the reference's loop order: window pair k (convention order) is one segment of its owner's list.
+template <class Copy>
+int merge_group_lists(lowdin_it_handle *hs, int n, Copy copy_segment) {
+  std::vector<size_t> next(n, 0), off(n, 0);
+  int64_t out = 0;
+  for (;;) {
+    int best = -1;
+    int64_t kbest = 0;
+    for (int r = 0; r < n; ++r)
+      if (next[r] < hs[r]->res_pair.size() && (best < 0 || hs[r]->res_pair[next[r]] < kbest)) { best = r; kbest = hs[r]->res_pair[next[r]]; }
+    if (best < 0) break;
+    const int64_t len = hs[best]->res_seg[next[best]];
+    copy_segment(best, (int64_t)off[best], out, len);
+    off[best] += len; out += len; ++next[best];
+  }
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int lowdin_it_group_transform(lowdin_it_handle *hs, int n, int a, int b, const int win[8], int conv, int symmetric, double drop_tol) {
+  if (!hs || n < 1) return 1;
+  if (n == 1) return lowdin_it_transform(hs[0], a, b, win, conv, symmetric, drop_tol);
+  std::vector<int> rc(n, 0);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n; ++r) th.emplace_back([&, r] { rc[r] = lowdin_it_transform(hs[r], a, b, win, conv, symmetric, drop_tol); });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < n; ++r) if (rc[r]) { if (r) hs[0]->err = hs[r]->err; return 1; }
+  return 0;
+}
+
+int lowdin_it_group_result_count(lowdin_it_handle *hs, int n, int64_t *count) {
+  if (!hs || n < 1 || !count) return 1;
+  *count = 0;
+  for (int r = 0; r < n; ++r) *count += hs[r]->count;
+  return 0;
+}
+
+int lowdin_it_group_download_pairs(lowdin_it_handle *hs, int n, int64_t *ij, int64_t *kl, double *v) {
+  if (!hs || n < 1) return 1;
+  if (n == 1) return lowdin_it_download_pairs(hs[0], ij, kl, v);
+  std::vector<std::vector<int64_t>> tij(n), tkl(n);
+  std::vector<std::vector<double>> tv(n);
+  for (int r = 0; r < n; ++r) {
+    const size_t c = std::max<size_t>((size_t)hs[r]->count, 1);
+    tij[r].resize(c); tkl[r].resize(c); tv[r].resize(c);
+    if (lowdin_it_download_pairs(hs[r], tij[r].data(), tkl[r].data(), tv[r].data())) { if (r) hs[0]->err = hs[r]->err; return 1; }
+  }
+  return merge_group_lists(hs, n, [&](int r, int64_t src, int64_t dst, int64_t len) {
+    memcpy(ij + dst, tij[r].data() + src, len * sizeof(int64_t));
+    memcpy(kl + dst, tkl[r].data() + src, len * sizeof(int64_t));
+    memcpy(v + dst, tv[r].data() + src, len * sizeof(double));
+  });
+}
+
+int lowdin_it_group_download_quads(lowdin_it_handle *hs, int n, int32_t *p, int32_t *q, int32_t *r_, int32_t *s_, double *v) {
+  if (!hs || n < 1) return 1;
+  if (n == 1) return lowdin_it_download_quads(hs[0], p, q, r_, s_, v);
+  std::vector<std::vector<int32_t>> t0(n), t1(n), t2(n), t3(n);
+  std::vector<std::vector<double>> tv(n);
+  for (int r = 0; r < n; ++r) {
+    const size_t c = std::max<size_t>((size_t)hs[r]->count, 1);
+    t0[r].resize(c); t1[r].resize(c); t2[r].resize(c); t3[r].resize(c); tv[r].resize(c);
+    if (lowdin_it_download_quads(hs[r], t0[r].data(), t1[r].data(), t2[r].data(), t3[r].data(), tv[r].data())) { if (r) hs[0]->err = hs[r]->err; return 1; }
+  }
+  return merge_group_lists(hs, n, [&](int r, int64_t src, int64_t dst, int64_t len) {
+    memcpy(p + dst, t0[r].data() + src, len * sizeof(int32_t));
+    memcpy(q + dst, t1[r].data() + src, len * sizeof(int32_t));
+    memcpy(r_ + dst, t2[r].data() + src, len * sizeof(int32_t));
+    memcpy(s_ + dst, t3[r].data() + src, len * sizeof(int32_t));
+    memcpy(v + dst, tv[r].data() + src, len * sizeof(double));
+  });
 }
 
 // ---- stand-alone kernel timing / debug --------------------------------------------------------

@@ -322,12 +322,15 @@ __device__ __forceinline__ double gen_unscaled(uint32_t slab, uint32_t mu, uint3
 }
 
 struct Q1WsArgs {
-  int64_t slab0;
+  int64_t slab0;  // first slab of the batch, in the rank's local numbering (slab_global() gives the id the generator hashes)
+  int logB, G, rank;
   int bc, nc, nfb;
   uint32_t m32;   // SRC_HASH_SYM: pairs per slab vector (M); SRC_HASH_RECT: number of slabs (M_b)
   uint64_t seed;
   double *T1t;
   int64_t ldt;
+  int dbg;  // probe switches (LOWDIN_IT_OPT_Q1_DEBUG; results are wrong when set): 1 = generator warps store zeros instead of hashing,
+            // 2 = DMMA warps skip loads and DMMAs, 4 = variant 3 only: roles by scheduler (warps with bit 1 set generate)
 };
 
 template <int TN, int STAGES>
@@ -366,15 +369,19 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
 
   const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk tig of a row with (row & 7) == grp; chunk 4+tig is off0 ^ 64
 
-  if (warp >= NCW) {
+  // roles: warps 8-15 generate (two of each kind per scheduler); probe switch 4: the warps of schedulers 2 and 3 generate
+  const bool split = (q.dbg & 4) != 0;
+  const bool is_gen = split ? ((warp & 2) != 0) : (warp >= NCW);
+  const int role_idx = split ? (((warp >> 2) << 1) | (warp & 1)) : (warp & 7);  // 0..7 within the role
+  if (is_gen) {
     // ============================== generators ==============================
-    const int gw = warp - NCW;
+    const int gw = role_idx;
     const uint32_t n = (uint32_t)q.nc;
     uint8_t *a_rows = ring + (gw * 16 + grp) * 128;  // rows 16 gw + grp and + 8
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / row_blocks, rb = tile - z * row_blocks;
-      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t slab = (uint32_t)slab_global(q.slab0 + z, q.logB, q.G, q.rank);
       const uint32_t mu0 = (uint32_t)(rb * BM + gw * 16 + grp);
       const uint32_t base_mu[2] = {pair_base(mu0, n), pair_base(mu0 + 8u, n)};
       for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -397,8 +404,11 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
           for (int cg = 0; cg < 2; ++cg) {
             const uint32_t mu = mu0 + 8 * rg;
             double2 v;
-            v.x = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg], base_mu[rg], base_nu[2 * cg], q.m32, q.seed);
-            v.y = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg + 1], base_mu[rg], base_nu[2 * cg + 1], q.m32, q.seed);
+            if (q.dbg & 1) { v.x = 0.0; v.y = 0.0; }
+            else {
+              v.x = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg], base_mu[rg], base_nu[2 * cg], q.m32, q.seed);
+              v.y = gen_unscaled<KIND, GEN>(slab, mu, nus[2 * cg + 1], base_mu[rg], base_nu[2 * cg + 1], q.m32, q.seed);
+            }
             *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (cg ? (off0 ^ 64u) : off0)) = v;
           }
         }
@@ -410,7 +420,8 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
   }
 
   // ============================== consumers ==============================
-  const uint8_t *a_base = ring + (warp * 16 + grp) * 128;
+  const int cw = role_idx;
+  const uint8_t *a_base = ring + (cw * 16 + grp) * 128;
   const uint8_t *b_base = ring + A_BYTES + grp * 128;
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -424,6 +435,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
       const uint32_t s = it % STAGES;
       mbar_wait(bars + 8 * s, (it / STAGES) & 1u);
       const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+      if (!(q.dbg & 2))
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t off = h ? (off0 ^ 64u) : off0;
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int m = rb * BM + warp * 16 + i * 8 + grp;
+      const int m = rb * BM + cw * 16 + i * 8 + grp;
       if (m >= q.nc) continue;
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
@@ -536,7 +548,7 @@ __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constan
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / row_blocks, rb = tile - z * row_blocks;
-      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t slab = (uint32_t)slab_global(q.slab0 + z, q.logB, q.G, q.rank);
       const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
       uint32_t base_mu[4];
 #pragma unroll
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int z = tile / row_blocks, rb = tile - z * row_blocks;
-      const uint32_t slab = (uint32_t)(q.slab0 + z);
+      const uint32_t slab = (uint32_t)slab_global(q.slab0 + z, q.logB, q.G, q.rank);
       const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
       uint32_t base_mu[4];
 #pragma unroll
@@ -752,7 +764,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
             }
             x[v] = q.seed ^ key;
           }
-          hash8<GEN>(x);
+          if (!(q.dbg & 1)) hash8<GEN>(x);
 #pragma unroll
           for (int r2 = 0; r2 < 2; ++r2) {
             const int rg = 2 * hh + r2;
@@ -783,6 +795,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
       const uint32_t s = it % STAGES;
       mbar_wait(bars + 8 * s, (it / STAGES) & 1u);
       const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+      if (!(q.dbg & 2))
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t off = h ? (off0 ^ 64u) : off0;

@@ -28,9 +28,10 @@ enum SrcKind : int {
   SRC_RECT = 1,        // data[slab*ld + pair]   (inter AO storage (rs-1)*M_a+pq, C.f90:882; and the half-transformed H)
   SRC_HASH_SYM = 2,    // generated, key = hi*M + lo
   SRC_HASH_RECT = 3,   // generated, key = pair*aux + slab   (inter: PQ*M_b + RS)
-  SRC_RECT_BLOCKED = 4,// data[((pair/ld)*aux + slab)*ld + pair%ld]: the half-transformed chunk as it arrives from the
-                       // all-to-all, one [slots][ld] block per sending rank (aux = slots per block)
+  // 4: retired (the divide-per-element blocked layout of round 1; replaced by SRC_RECT_TABLE)
   SRC_LIST = 6,        // the canonical AO list kept as uploaded (it_list.cuh): no dense tensor, list-driven first quarter
+  SRC_RECT_TABLE = 7,  // data[tab[pair] + slab*ld], tab = (const int64_t *)data2: the half-transformed chunk as it arrives from the
+                       // all-to-all (one [slots][ld] block per sending rank), addressed through a per-chunk column table
   SRC_RANKK = 5        // generated, kind K: (slab | pair) = sum_{k<8} data2[k*aux + slab] * data[k*M + pair]
                        // (rank-8 separable tensor with closed-form MO integrals; intra: data2 == data, aux == M)
 };
@@ -44,8 +45,29 @@ struct AoSource {
   int64_t aux;  // SRC_HASH_RECT: number of slabs (M_b)
   uint64_t seed;
   int gen;      // generated sources: 1 = splitmix64 (kind H), 2 = mul-fold-mul (kind F), 3 = rank-K separable (kind K)
-  const double *data2;  // SRC_RANKK: pair-vector factors of the SLAB species [RANKK][aux]
+  const double *data2;  // SRC_RANKK: pair-vector factors of the SLAB species [RANKK][aux]; SRC_RECT_TABLE: the int64 column table
+  // Multi-GPU first half: the slab argument of the kernels is the rank's LOCAL slab number; sources addressed by the global
+  // slab id (generated ones) translate it with slab_global().  G == 0 or 1: identity.
+  int logB, G, rank;
 };
+
+// Block-cyclic distribution of the AO-pair slabs over the ranks of the first half: blocks of 2^logB consecutive slabs, block b on
+// rank b % G; a rank numbers its own slabs consecutively (its LOCAL slab number = its row in row-sharded stored tensors).
+// Fixed at upload time and independent of the chunking, which is what lets a stored tensor be sharded by rows.
+__host__ __device__ __forceinline__ int slab_owner(int64_t slab, int logB, int G) { return (int)((slab >> logB) % G); }
+__host__ __device__ __forceinline__ int64_t slab_local(int64_t slab, int logB, int G) {
+  return (((slab >> logB) / G) << logB) + (slab & ((1ll << logB) - 1));
+}
+__host__ __device__ __forceinline__ int64_t slab_global(int64_t local, int logB, int G, int rank) {
+  if (G <= 1) return local;
+  return ((((local >> logB) * G) + rank) << logB) + (local & ((1ll << logB) - 1));
+}
+// number of slabs below x that rank r owns (= the local number of the first owned slab >= x)
+__host__ __device__ __forceinline__ int64_t slabs_owned_below(int64_t x, int logB, int G, int r) {
+  if (G <= 1) return x;
+  const int64_t nb = x >> logB, rem = x & ((1ll << logB) - 1);
+  return (((nb + G - 1 - r) / G) << logB) + ((nb % G) == r ? rem : 0);
+}
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -78,13 +100,6 @@ __host__ __device__ __forceinline__ double hash_value(int gen, uint64_t seed, ui
   return bits_to_value(gen == 2 ? mulfold64(seed ^ key) : splitmix64(seed ^ key));
 }
 
-// Offset of (row `slab`, column `pair`) in the chunk as it arrives from the all-to-all: one [rows][ld] block per
-// sending rank, ld = columns per rank.  Host-callable so that the CPU multi-rank test checks the same function.
-__host__ __device__ __forceinline__ int64_t blocked_offset(int64_t slab, int64_t pair, int64_t ld, int64_t rows) {
-  const int64_t blk = pair / ld;
-  return (blk * rows + slab) * ld + (pair - blk * ld);
-}
-
 // 0-based row-wise upper-triangular pair id (== xy(p,q)-1, C.f90:214-221)
 __host__ __device__ __forceinline__ int64_t pair0(int64_t i, int64_t j, int64_t n) {
   if (i > j) { int64_t t = i; i = j; j = t; }
@@ -114,12 +129,16 @@ struct SlabReader {
   uint64_t seed;
   int gen;
   double coef[KIND == SRC_RANKK ? RANKK : 1];  // SRC_RANKK: the slab's factor of every separable term
-  __device__ __forceinline__ SlabReader(const AoSource &src, int64_t slab_) : slab(slab_), M(src.M), ld((uint32_t)src.ld), rows((uint32_t)src.aux), seed(src.seed), gen(src.gen) {
-    base = (KIND == SRC_RECT) ? src.data + slab_ * src.ld : src.data;
+  const int64_t *tab;
+  __device__ __forceinline__ SlabReader(const AoSource &src, int64_t slab_) : M(src.M), ld((uint32_t)src.ld), rows((uint32_t)src.aux), seed(src.seed), gen(src.gen) {
+    // stored sources are addressed by the rank's local slab number, generated ones by the global slab id
+    slab = (KIND == SRC_HASH_SYM || KIND == SRC_HASH_RECT || KIND == SRC_RANKK) ? slab_global(slab_, src.logB, src.G, src.rank) : slab_;
+    base = (KIND == SRC_RECT || KIND == SRC_RECT_TABLE) ? src.data + slab_ * src.ld : src.data;
+    tab = (KIND == SRC_RECT_TABLE) ? reinterpret_cast<const int64_t *>(src.data2) : nullptr;
     if (KIND == SRC_HASH_RECT) M = src.aux;
     if (KIND == SRC_RANKK) {
 #pragma unroll
-      for (int k = 0; k < RANKK; ++k) coef[k] = __ldg(src.data2 + (int64_t)k * src.aux + slab_);
+      for (int k = 0; k < RANKK; ++k) coef[k] = __ldg(src.data2 + (int64_t)k * src.aux + slab);
     }
   }
   __device__ __forceinline__ double operator()(int64_t pair) const {
@@ -130,10 +149,7 @@ struct SlabReader {
       return v;
     }
     if (KIND == SRC_RECT) return __ldg(base + pair);
-    if (KIND == SRC_RECT_BLOCKED) {
-      const uint32_t p = (uint32_t)pair, blk = p / ld;
-      return __ldg(base + ((int64_t)blk * rows + slab) * (int64_t)ld + (p - blk * ld));
-    }
+    if (KIND == SRC_RECT_TABLE) return __ldg(base + __ldg(tab + pair));
     if (KIND == SRC_SYM_PACKED) {
       const int64_t lo = slab < pair ? slab : pair, hi = slab < pair ? pair : slab;
       return __ldg(base + (lo * M - (lo * (lo + 1)) / 2 + hi));
@@ -227,15 +243,6 @@ __global__ void __launch_bounds__(256) find_terminator_kernel(StackView w, unsig
   const int64_t t = k / w.S, e = k - t * w.S;
   if (__ldg(w.p + t * w.stride_i + e) == -1) atomicMin(state, (unsigned long long)(w.pos0 + k));
 }
-// Owner of a slab under the block-cyclic distribution of the multi-GPU first half (blocks of 2^logB consecutive slabs,
-// block b on rank b % G), and its row in the owner's local storage.
-__host__ __device__ __forceinline__ int slab_owner(int64_t slab, int logB, int G) { return (int)((slab >> logB) % G); }
-__host__ __device__ __forceinline__ int64_t slab_local(int64_t slab, int logB, int G) {
-  return (((slab >> logB) / G) << logB) + (slab & ((1ll << logB) - 1));
-}
-__host__ __device__ __forceinline__ int64_t slab_global(int64_t local, int logB, int G, int rank) {
-  return ((((local >> logB) * G) + rank) << logB) + (local & ((1ll << logB) - 1));
-}
 // pass 2: scatter the entries before the terminator
 __global__ void __launch_bounds__(256) scatter_stacks_kernel(StackView w, ScatterDst d, unsigned long long *__restrict__ state) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,13 +275,28 @@ __global__ void __launch_bounds__(256) scatter_stacks_kernel(StackView w, Scatte
   }
 }
 
+// Column table of one chunk after the all-to-all: chunk column c is the global slab base + c, computed by rank r = owner(slab) as
+// its local slab number loc; rank r's block [rows][ld] starts at r * rows * ld and holds its local slabs from loc_lo[r] on:
+//   tab[c] = r * rows * ld + (loc - loc_lo[r])      (offset of row 0; row s adds s * ld)
+struct RankStarts { int64_t lo[16]; };
+__global__ void column_table_kernel(int64_t base, int64_t width, int logB, int G, int64_t rows, int64_t ld, RankStarts st, int64_t *__restrict__ tab) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  const int64_t slab = base + c;
+  const int r = slab_owner(slab, logB, G);
+  tab[c] = (int64_t)r * rows * ld + (slab_local(slab, logB, G) - st.lo[r]);
+}
+
 // Generated AO set -> stored layout on the device (tests and the stored-AO bench leg at sizes whose list cannot come from a host):
 // intra: packed row `slab` holds pairs slab..M-1; inter: rectangular [slab][pair].  grid.x strides over slabs.
 template <int KIND>
 __global__ void __launch_bounds__(256) materialize_kernel(AoSource src, int intra, int64_t Ma, int64_t nslabs, double *__restrict__ dst) {
   for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
     const SlabReader<KIND> rd(src, slab);
-    if (intra) {
+    if (src.G > 1) {  // row-sharded: `slab` is the rank's local slab number, the row holds the whole M-vector
+      double *row = dst + slab * Ma;
+      for (int64_t pair = threadIdx.x; pair < Ma; pair += blockDim.x) row[pair] = rd(pair);
+    } else if (intra) {
       double *row = dst + (slab * Ma - (slab * (slab + 1)) / 2);
       for (int64_t pair = slab + threadIdx.x; pair < Ma; pair += blockDim.x) row[pair] = rd(pair);
     } else {
@@ -511,7 +533,7 @@ __global__ void __launch_bounds__(256) q1_gen_smem_kernel(AoSource src, int64_t 
   constexpr int BN = TN * 8, BK = 16, LDS = BK + 4, NT = 256, TM = 2;
   extern __shared__ __align__(16) double smem[];  // [STAGES][BN][LDS]
   const int z = blockIdx.y;
-  const uint32_t slab = (uint32_t)(slab0 + z);
+  const uint32_t slab = (uint32_t)slab_global(slab0 + z, src.logB, src.G, src.rank);
   const int m0 = blockIdx.x * 128;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = lane >> 2, tig = lane & 3;
@@ -606,7 +628,7 @@ __global__ void __launch_bounds__(256, 2) q1_gen_kernel(AoSource src, int64_t sl
                                                         int64_t ldc, int nfb, double *__restrict__ T1t, int64_t ldt) {
   constexpr int TM = 2;
   const int z = blockIdx.y;
-  const uint32_t slab = (uint32_t)(slab0 + z);
+  const uint32_t slab = (uint32_t)slab_global(slab0 + z, src.logB, src.G, src.rank);
   const int m0 = blockIdx.x * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 2, tig = lane & 3;
@@ -758,6 +780,26 @@ __global__ void __launch_bounds__(1024) select_scan_kernel(const unsigned *__res
     __syncthreads();
   }
   if (threadIdx.x == 0) *running = carry;
+}
+
+// Entries kept per window pair: block kk counts the kept candidates of the kk-th pair of `order` (the rank's list is the
+// concatenation of these segments, which is how the lists of several ranks are merged into the reference's order).
+__global__ void __launch_bounds__(SEL_THREADS) select_segments_kernel(SelectArgs a, unsigned long long *__restrict__ seg) {
+  __shared__ unsigned wsum[SEL_THREADS / 32];
+  const int64_t per = (int64_t)a.n_outer * a.n_inner, base = (int64_t)blockIdx.x * per;
+  unsigned cnt = 0;
+  for (int64_t t = threadIdx.x; t < per; t += SEL_THREADS) {
+    double v; int s, o, in;
+    if (select_candidate(a, base + t, v, s, o, in)) ++cnt;
+  }
+  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) t += wsum[w];
+    seg[blockIdx.x] = t;
+  }
 }
 
 struct EmitArgs {

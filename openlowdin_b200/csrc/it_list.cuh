@@ -59,9 +59,11 @@ __global__ void list_window_kernel(const double *__restrict__ C, int64_t ldc, in
 //                                         (ij)!=(kl): slab (ij): nu=l += v C(k,f);  k!=l: nu=k += v C(l,f)      (Libint2Iface.cpp:803-851)
 // inter (first pair on the contracted species A, second on the slab species B; `swapped`: the stacks hold (BB|AA)):
 //                                         slab (kl): nu=j += v C(i,f);  i!=j: nu=i += v C(j,f)
+// On a communicator every rank holds the whole list and keeps only the images that land in ITS slabs (block-cyclic owner,
+// it_kernels.cuh); T1 is then indexed by the rank's local slab number.
 __global__ void __launch_bounds__(256) list_first_quarter_kernel(const ListEntry *__restrict__ list, const unsigned long long *__restrict__ count,
                                                                  int intra, int swapped, int nc, int n_slab, const double *__restrict__ Cw,
-                                                                 int nfb, int nfbp, double *__restrict__ T1) {
+                                                                 int nfb, int nfbp, double *__restrict__ T1, int logB, int G, int rank) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = (int64_t)*count;
@@ -70,20 +72,24 @@ __global__ void __launch_bounds__(256) list_first_quarter_kernel(const ListEntry
     int i = en.p, j = en.q, k = en.r, l = en.s;
     if (!intra && swapped) { int t = i; i = k; k = t; t = j; j = l; l = t; }  // (BB|AA): the contracted pair is the second one
     const double v = en.v;
-    const int64_t slab_kl = pair0(k, l, n_slab);
+    const int64_t g_kl = pair0(k, l, n_slab), g_ij = intra ? pair0(i, j, nc) : -1;
+    const bool mine_kl = (G <= 1) || slab_owner(g_kl, logB, G) == rank;
+    const bool both = intra && (g_ij != g_kl) && ((G <= 1) || slab_owner(g_ij, logB, G) == rank);
+    const int64_t slab_kl = (G <= 1) ? g_kl : slab_local(g_kl, logB, G);
     double *row_j = T1 + (slab_kl * nc + j) * (int64_t)nfbp, *row_i = T1 + (slab_kl * nc + i) * (int64_t)nfbp;
     const double *ci = Cw + (int64_t)i * nfbp, *cj = Cw + (int64_t)j * nfbp;
-    const bool both = intra && (pair0(i, j, nc) != slab_kl);
     double *row_l = nullptr, *row_k = nullptr;
     const double *ck = nullptr, *cl = nullptr;
     if (both) {
-      const int64_t slab_ij = pair0(i, j, nc);
+      const int64_t slab_ij = (G <= 1) ? g_ij : slab_local(g_ij, logB, G);
       row_l = T1 + (slab_ij * nc + l) * (int64_t)nfbp; row_k = T1 + (slab_ij * nc + k) * (int64_t)nfbp;
       ck = Cw + (int64_t)k * nfbp; cl = Cw + (int64_t)l * nfbp;
     }
     for (int f = lane; f < nfb; f += 32) {
-      atomicAdd(row_j + f, v * __ldg(ci + f));
-      if (i != j) atomicAdd(row_i + f, v * __ldg(cj + f));
+      if (mine_kl) {
+        atomicAdd(row_j + f, v * __ldg(ci + f));
+        if (i != j) atomicAdd(row_i + f, v * __ldg(cj + f));
+      }
       if (both) {
         atomicAdd(row_l + f, v * __ldg(ck + f));
         if (k != l) atomicAdd(row_k + f, v * __ldg(cl + f));

@@ -74,6 +74,52 @@ def species_pairs_across_ranks(rank, world, local, dev):
     return good
 
 
+def collective_download(T, rank, world, local):
+    """lowdin_it_transform on the communicator with a STORED tensor (every rank is pushed the whole list and keeps the rows it
+    owns), per-rank downloads, merged by window-pair segments on rank 0 into ONE moint.dat: byte-identical to the file a single
+    GPU writes (TransformIntegralsE.f90:1242-1268 record order)."""
+    import tempfile
+    n, occ, S = 17, 5, 64
+    packed = O.hash_packed_intra(808, n)
+    Cm = O.random_orthonormal(n, n)
+    lst = O.canonical_list_intra(packed, n)
+    win = O.windows_e_intra("MP2", n, occ)
+    T.set_option(T.OPT_CHUNK_COLS, 45)
+    T.set_species(0, Cm)
+    T.upload_ao(0, 0, *lst, stack=S)
+    ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+    idx, kept = T.result_segments()
+    T.set_option(T.OPT_CHUNK_COLS, 0)
+    parts = [None] * world
+    dist.all_gather_object(parts, (idx, kept, ij, kl, v))
+    good = True
+    if rank == 0:
+        segs = []
+        for (pi, pk, a, b, c) in parts:
+            off = np.concatenate([[0], np.cumsum(pk)])
+            segs += [(int(pi[t]), a[off[t]:off[t + 1]], b[off[t]:off[t + 1]], c[off[t]:off[t + 1]]) for t in range(len(pi))]
+        segs.sort(key=lambda e: e[0])
+        mij, mkl, mv = (np.concatenate([e[k] for e in segs]) for k in (1, 2, 3))
+        d = tempfile.mkdtemp(prefix="lowdin_it_mgpu_dl_")
+        capi.host_write_moint_pairs(os.path.join(d, "merged.dat"), S, mij, mkl, mv)
+        T1 = ol.Transformer(local)
+        T1.set_species(0, Cm)
+        T1.upload_ao(0, 0, *lst, stack=S)
+        one = T1.transform(0, 0, win, ol.CONV_E)
+        T1.close()
+        capi.host_write_moint_pairs(os.path.join(d, "one.dat"), S, *one)
+        same_keys = np.array_equal(mij, one[0]) and np.array_equal(mkl, one[1])
+        diff = float(np.abs(mv - one[2]).max()) if same_keys else float("inf")
+        identical = open(os.path.join(d, "merged.dat"), "rb").read() == open(os.path.join(d, "one.dat"), "rb").read()
+        ref = O.transform_e_intra(Cm, packed, win)
+        M = O.npairs(n)
+        vs_oracle = float(np.abs(O.pairs_to_dense(mij, mkl, mv, M, M) - O.pairs_to_dense(*ref, M, M)).max())
+        good = same_keys and diff <= 1e-12 and vs_oracle <= 1e-10
+        print(f"collective download on {world} ranks: {len(mv)} integrals, same order as 1 GPU: {same_keys}, max|delta| vs 1 GPU {diff:.1e}, "
+              f"vs oracle {vs_oracle:.1e}, moint.dat byte-identical: {identical} -> {'ok' if good else 'MISMATCH'}", flush=True)
+    return good
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -119,6 +165,9 @@ def main():
             if rank == 0:
                 print(f"{kind} n={n} chunk_cols={cols} occ_batch={qb}: got {got} want {want} -> {'ok' if good else 'MISMATCH'}", flush=True)
     T.set_option(T.OPT_CHUNK_COLS, 0)
+    flag = torch.tensor([1.0 if collective_download(T, rank, world, local) else 0.0], dtype=torch.float64, device=dev)
+    dist.broadcast(flag, 0)
+    ok = ok and bool(flag.item() == 1.0)
     T.close()
     ok = species_pairs_across_ranks(rank, world, local, dev) and ok
     dist.destroy_process_group()

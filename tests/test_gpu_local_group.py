@@ -21,8 +21,8 @@ def _close(Ts):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("G", [2, 3, 4])
-def test_local_group_intra_mp2_matches_oracle(O, G):
+@pytest.mark.parametrize("G,logB", [(2, 5), (3, 0), (4, 1), (2, 2)])
+def test_local_group_intra_mp2_matches_oracle(O, G, logB):
     n, occ, seed = 24, 6, 31337
     packed = O.hash_packed_intra(seed, n)
     Cm = O.random_orthonormal(n, n)
@@ -34,6 +34,7 @@ def test_local_group_intra_mp2_matches_oracle(O, G):
     try:
         for cols, qb in ((0, 0), (60, 4), (1, 2), (200, 3)):
             def work(r, T):
+                T.set_option(T.OPT_SLAB_BLOCK_LOG, logB)
                 T.set_species(0, Cm)
                 T.set_generator(0, 0, seed)
                 T.set_option(T.OPT_CHUNK_COLS, cols)
@@ -101,5 +102,90 @@ def test_two_handles_one_process_are_independent(O):
             T.set_generator(0, 0, 7)
             ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
             assert np.abs(O.pairs_to_dense(ij, kl, v, M, M) - O.pairs_to_dense(*ref, M, M)).max() <= 1e-10
+    finally:
+        _close(Ts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,logB", [(2, 0), (3, 2), (4, 5)])
+def test_group_download_is_the_single_gpu_list(O, T, G, logB):
+    """lowdin_it_transform on a group (collective; stored tensor sharded by rows at upload) + the merged download: the same
+    entries in the same order as one GPU produces, for both record conventions."""
+    n, occ = 15, 4
+    packed = O.hash_packed_intra(44, n)
+    Cm = O.random_orthonormal(n, n)
+    lst = O.canonical_list_intra(packed, n)
+    T.set_species(0, Cm)
+    T.upload_ao(0, 0, *lst, stack=256)
+    Ts = _group(G)
+    try:
+        for t in Ts:
+            t.set_option(t.OPT_SLAB_BLOCK_LOG, logB)
+            t.set_option(t.OPT_CHUNK_COLS, 37)
+            t.set_species(0, Cm)
+            t.upload_ao(0, 0, *lst, stack=256)          # every rank is pushed the whole list and keeps its own rows
+        for conv, mode in ((ol.CONV_E, "MP2"), (ol.CONV_E, "ALL"), (ol.CONV_C, "MP2"), (ol.CONV_C, "PT2")):
+            if conv == ol.CONV_E:
+                win, sym = (O.windows_e_intra(mode, n, occ) if mode != "ALL" else [1, n] * 4), False
+            else:
+                win, sym = O.windows_c_intra(mode, n, occ)
+            one = T.transform(0, 0, win, conv, symmetric=sym)
+            got = capi.group_transform(Ts, 0, 0, win, conv, symmetric=sym)
+            assert len(got[-1]) == len(one[-1]) > 0
+            for a, b in zip(got[:-1], one[:-1]):
+                assert np.array_equal(a, b)               # same index lists, same order
+            assert np.abs(got[-1] - one[-1]).max() <= 1e-12
+            # the per-rank segments partition the window pairs
+            idx = np.concatenate([t.result_segments()[0] for t in Ts])
+            assert len(set(idx)) == len(idx)
+    finally:
+        _close(Ts)
+
+
+@pytest.mark.gpu
+def test_group_list_mode_and_materialized_sources(O):
+    """The list-driven first quarter and a device-materialised tensor on a group of 3 ranks."""
+    n, occ = 14, 4
+    packed = O.hash_packed_intra(12, n)
+    Cm = O.random_orthonormal(n, n)
+    lst = O.canonical_list_intra(packed, n)
+    eps = O.synthetic_eps(occ, n)
+    win = O.windows_e_intra("MP2", n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+    want = np.array([len(rv), rv.sum(), (rv * rv).sum(), O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps)])
+    Ts = _group(3)
+    try:
+        def work(r, T):
+            T.set_option(T.OPT_SLAB_BLOCK_LOG, 1)
+            T.set_option(T.OPT_CHUNK_COLS, 30)
+            T.set_species(0, Cm)
+            T.set_option(T.OPT_AO_LIST, 1)
+            T.upload_ao(0, 0, *lst, stack=128)
+            T.set_option(T.OPT_AO_LIST, 0)
+            a = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=2, epsA=eps)
+            T.set_generator(0, 0, 12)
+            T.materialize(0, 0)
+            b = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=3, epsA=eps)
+            return np.concatenate([a, b])
+        got = np.sum(capi.run_ranks(Ts, work), axis=0)
+        for g in (got[:4], got[4:]):
+            assert g[0] == want[0] and np.abs(g[1:] - want[1:]).max() <= 1e-9, (g, want)
+    finally:
+        _close(Ts)
+
+
+@pytest.mark.gpu
+def test_upload_before_group_is_rejected(O):
+    n = 6
+    Cm = O.random_orthonormal(n, n)
+    lst = O.canonical_list_intra(O.hash_packed_intra(1, n), n)
+    Ts = [ol.Transformer(0) for _ in range(2)]
+    try:
+        for t in Ts:
+            t.set_species(0, Cm)
+            t.upload_ao(0, 0, *lst)
+        capi.local_group(Ts)
+        with pytest.raises(ol.LowdinITError, match="before the communicator"):
+            capi.group_transform(Ts, 0, 0, [1, n] * 4, ol.CONV_E)
     finally:
         _close(Ts)

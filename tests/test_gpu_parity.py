@@ -360,3 +360,41 @@ def test_empty_windows_on_a_fresh_handle(O, conv):
             assert np.all(T.transform_stream(0, 0, win, conv) == 0.0)
         finally:
             T.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qb", [0, 2])
+def test_stream_sink_delivers_every_mo_integral(O, T, qb):
+    """lowdin_it_transform_stream_sink: the dense blocks handed to the host (pinned ring, copy overlapped with the next group's
+    fourth quarter) hold exactly the integrals lowdin_it_transform + download give, for intra and inter MP2 windows."""
+    n, occ = 19, 5
+    packed, Cm = _intra_setup(O, T, n, 77)
+    M = O.npairs(n)
+    pid = lambda x, y, nn: min(x, y) * nn - min(x, y) * (min(x, y) - 1) // 2 + abs(x - y)  # noqa: E731  0-based pair id of 0-based (x, y)
+    cases = [((0, 0), O.windows_e_intra("MP2", n, occ), n, n, M, M)]
+    na, nb = 11, 8
+    _inter_setup(O, T, na, nb, 5, 1, 2)
+    cases.append(((1, 2), O.windows_e_inter("MP2", na, nb, 3, 2), na, nb, O.npairs(na), O.npairs(nb)))
+    for (a, b), win, n1, n2, M1, M2 in cases:
+        ij, kl, v = T.transform(a, b, win, ol.CONV_E)
+        ref = dense_pairs(ij, kl, v, M1, M2)
+        got = np.zeros((M1, M2))
+        nblocks = [0]
+
+        def sink(sa, sb, vals, blk):
+            nblocks[0] += 1
+            for t in range(len(sa)):
+                row = pid(sa[t] - 1, sb[t] - 1, n1)
+                for ks in range(blk.n_second):
+                    for kf in range(blk.n_first):
+                        r, s = (blk.orb_second0 + ks, blk.orb_first0 + kf) if blk.second_is_conv_first else (blk.orb_first0 + kf, blk.orb_second0 + ks)
+                        x = vals[t, ks, kf]
+                        if abs(x) > 1e-10:
+                            got[row, pid(r - 1, s - 1, n2)] = x
+        T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 16)
+        try:
+            sums = T.transform_stream_sink(a, b, win, ol.CONV_E, sink, occ_batch=qb)
+        finally:
+            T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 30)
+        assert nblocks[0] >= 3 and sums[0] == len(v)
+        assert np.abs(got - ref).max() <= 1e-12

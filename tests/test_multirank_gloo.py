@@ -1,5 +1,6 @@
-"""N>1 path on CPU (gloo, world_size 2): the library's division of work (lowdin_it_shard_plan) and the layout the
-all-to-all leaves behind (lowdin_it_blocked_offset) drive a numpy emulation of the two-half transform; the ranks'
+"""N>1 path on CPU (gloo, world_size 2): the library's division of work (lowdin_it_shard_plan: block-cyclic slabs, slots by
+blocks of first-contracted indices) and the layout the all-to-all leaves behind (lowdin_it_exchanged_offset) drive a numpy
+emulation of the two-half transform; the ranks'
 combined result must equal the oracle's.  The arithmetic here is numpy (test scaffolding); what is under test is the
 host-side sharding logic that the CUDA path uses unchanged."""
 import os
@@ -29,20 +30,24 @@ def _worker(rank, world, port, n, occ, rows_per_chunk, q):
         V = n - occ
         # MP2 window, transformer-E roles: slots (a virt, i occ), numbered f-major (f = i)
         fbeg = np.arange(occ + 1, dtype=np.int32) * V
-        own, _, _, _ = capi.shard_plan(fbeg, 0, world, rank)
+        LOGB = 1                                                 # blocks of two slabs: several blocks per chunk at these sizes
+        own, _, _, _ = capi.shard_plan(fbeg, 0, 0, world, rank, LOGB)
         mine = own[rank + 1] - own[rank]
         Hmine = np.zeros((mine, M))
         Cv, Co = Cm[:, occ:], Cm[:, :occ]
         for p0 in range(0, n, rows_per_chunk):
             p1 = min(n, p0 + rows_per_chunk)
             base, width = xy[p0, p0], sum(n - p for p in range(p0, p1))
-            own, wblk, lo, hi = capi.shard_plan(fbeg, width, world, rank)
-            # first half of my columns of the chunk, for ALL slots
+            own, wblk, loc_lo, cnt = capi.shard_plan(fbeg, base, width, world, rank, LOGB)
+            wblk = max(wblk, 1)
+            # first half of my slabs of the chunk (consecutive LOCAL slabs), for ALL slots
             Hc = np.zeros((occ * V, wblk))
-            for c in range(lo, hi):
-                X = sq[base + c][xy]                             # dense slab (mu,nu)
+            for c in range(cnt):
+                z = capi.slab_global(loc_lo + c, world, rank, LOGB)
+                assert base <= z < base + width and capi.slab_owner(z, world, LOGB) == rank and capi.slab_local(z, world, LOGB) == loc_lo + c
+                X = sq[z][xy]                                    # dense slab (mu,nu)
                 T2 = Cv.T @ X @ Co                               # [a][i]
-                Hc[:, c - lo] = T2.T.reshape(-1)                 # slot = i*V + a
+                Hc[:, c] = T2.T.reshape(-1)                      # slot = i*V + a
             # exchange: rows own[g]:own[g+1] go to rank g (grouped send/recv like ncclSend/ncclRecv)
             recv = [torch.zeros(mine * wblk, dtype=torch.float64) for _ in range(world)]
             reqs = []
@@ -57,8 +62,8 @@ def _worker(rank, world, port, n, occ, rows_per_chunk, q):
                 r.wait()
             flat = torch.cat(recv).numpy()                       # [g][slot_local][wblk]
             for s in range(mine):
-                for c in range(width):
-                    Hmine[s, base + c] = flat[capi.blocked_offset(s, c, wblk, mine)]
+                for z in range(base, base + width):
+                    Hmine[s, z] = flat[capi.exchanged_offset(s, z, base, wblk, mine, world, LOGB)]
         # second half on my slots
         out = {}
         for s in range(mine):
@@ -106,16 +111,28 @@ def test_two_rank_sharding_reproduces_the_oracle(O, n, occ, rows):
 def test_shard_plan_properties():
     from openlowdin_b200 import capi
     fbeg = np.array([0, 3, 7, 7, 12, 20], np.int32)
+    base, width = 37, 101
     for G in (1, 2, 3, 5, 8):
-        cover = []
-        for r in range(G):
-            own, wblk, lo, hi = capi.shard_plan(fbeg, 101, G, r)
-            assert own[0] == 0 and own[G] == 20 and all(own[k] <= own[k + 1] for k in range(G))
-            assert all(o in fbeg for o in own)               # whole f-blocks only: exchange partners stay together
-            assert wblk * G >= 101 and 0 <= lo <= hi <= 101 and hi - lo <= wblk
-            cover += list(range(lo, hi))
-        assert cover == list(range(101))
-    assert capi.blocked_offset(2, 7, 5, 4) == (1 * 4 + 2) * 5 + 2
+        for logB in (0, 2, 5):
+            cover, offs, wmax = [], set(), 0
+            for r in range(G):
+                own, wblk, lo, cnt = capi.shard_plan(fbeg, base, width, G, r, logB)
+                assert own[0] == 0 and own[G] == 20 and all(own[k] <= own[k + 1] for k in range(G))
+                assert all(o in fbeg for o in own)               # whole f-blocks only: exchange partners stay together
+                assert 0 <= cnt <= wblk
+                wmax = max(wmax, cnt)
+                mine = [capi.slab_global(lo + c, G, r, logB) for c in range(cnt)]
+                assert all(capi.slab_owner(z, G, logB) == r and capi.slab_local(z, G, logB) == lo + c for c, z in enumerate(mine))
+                cover += mine
+            assert wblk == wmax
+            assert sorted(cover) == list(range(base, base + width))      # the ranks' slabs tile the chunk exactly
+            rows = 4
+            for z in range(base, base + width):                           # the exchanged layout has one place per (row, slab)
+                for row in range(rows):
+                    o = capi.exchanged_offset(row, z, base, max(wblk, 1), rows, G, logB)
+                    assert 0 <= o < G * rows * max(wblk, 1) and o not in offs
+                    offs.add(o)
+    assert capi.exchanged_offset(2, 7, 5, 5, 4, 1, 0) == 2 * 5 + 2
 
 
 def _plan_worker(rank, world, port, q):
