@@ -232,10 +232,16 @@ def stored_resident_leg(ol, dev_index, n, all_mode=False, hbm_gbs=6549.4, fp64_p
                                   "frac": kern["q1"]["TFLOP/s"] / fp64_peak}
         return res, sm
 
-    out["mp2"], s_st = run(win, "mp2")
+    out["mp2"], s_st = run(win, "mp2")          # default: unpack fused into the first quarter (q1_load_ws5_kernel), no dense slab in HBM
     scale = np.array([1.0, np.sqrt(s_gen[0] * s_gen[2]), s_gen[2], max(abs(s_gen[3]), 1e-300)])
     out["mp2"]["sums"] = list(map(float, s_st))
     out["mp2"]["vs_generated_source"] = {"count_equal": bool(s_st[0] == s_gen[0]), "max_rel_diff": float((np.abs(s_st - s_gen) / scale)[1:].max())}
+    out["mp2"]["first_quarter"] = "fused: packed rows -> shared memory -> DMMA (8 M bytes of HBM reads per slab)"
+    T.set_option(T.OPT_STORED_FUSED, 0)        # the two-kernel form: expansion kernel (dense slab to HBM) + DMMA GEMM
+    out["mp2_unfused"], s_un = run(win, "mp2")
+    T.set_option(T.OPT_STORED_FUSED, 1)
+    out["mp2_unfused"]["first_quarter"] = "expansion kernel writes the dense slab (8 M + 8 N^2 bytes per slab), TMA GEMM reads it back"
+    out["mp2_unfused"]["vs_fused"] = {"count_equal": bool(s_un[0] == s_st[0]), "max_rel_diff": float((np.abs(s_un - s_st) / scale)[1:].max())}
     if all_mode:
         out["all"], _ = run([1, n] * 4, "all")
     T.close()
@@ -600,10 +606,18 @@ def main():
     barrier()
     t1 = time.perf_counter()
     e2e_flops = 0.0
+    sunk = [0, 0.0]                      # bytes of MO integrals that reached the host, a checksum over a sample of them
+
+    def host_sink(sa, sb, vals, blk):
+        sunk[0] += vals.nbytes
+        sunk[1] += float(vals.reshape(-1)[::65521].sum())
+
     for i in range(e2e_steps):
         T.set_species(0, Cpin)           # H2D: coefficients
         T.set_generator(0, 0, SEED, args.gen)
-        s = one_pass(args.warmup + i)    # H2D: orbital energies; D2H: sums
+        # H2D: orbital energies; D2H: EVERY MO integral of the pass, block by block into pinned host memory, + the reduced sums
+        T.transform_stream_sink(0, 0, win, ol.CONV_E, host_sink, occ_batch=qb, first_pass=(args.warmup + i) % npass, n_passes=1, epsA=eps)
+        last_beat[0] = time.monotonic()
         e2e_flops += T.timers()["flops"]
     barrier()
     e2e_s = max(time.perf_counter() - t1, 1e-9)
@@ -612,9 +626,9 @@ def main():
         t = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, wall_s, e2e_s = t.tolist()
-        f = torch.tensor([flops, e2e_flops, float(launches)], dtype=torch.float64, device=dev)
+        f = torch.tensor([flops, e2e_flops, float(launches), float(sunk[0])], dtype=torch.float64, device=dev)
         dist.all_reduce(f, op=dist.ReduceOp.SUM)
-        flops, e2e_flops, launches = f.tolist()
+        flops, e2e_flops, launches, sunk[0] = f.tolist()
 
     # results of the passes that ran (every pass of the transform when warmup + steps >= npass), summed over ranks
     covered = sorted(pass_sums)
@@ -685,9 +699,11 @@ def main():
                            "fp64_pct_of_nominal_37tf_per_gpu": 100.0 * value / 37000.0 / world, "cublas_dgemm_tflops_measured": fp64_peak, "wall_ms_per_step": wall_s / args.steps * 1e3},
                 "roofline": roof, "kernels": kernels,
                 "e2e": {"value": (e2e_flops / e2e_s / 1e9) if e2e_steps else None, "unit": "GFLOP/s", "steps": e2e_steps,
-                        "h2d_bytes_per_step": int(n * n * 8 + n * 8), "d2h_bytes_per_step": 32,
-                        "note": "C-ABI calls with host buffers: coefficients (pinned) + orbital energies up, reduced sums down; "
-                                "AO values generated on the device from the canonical index (a 5 TB host tensor cannot exist)"},
+                        "h2d_bytes_per_step": int(n * n * 8 + n * 8) * world, "d2h_bytes_per_step": int(sunk[0] / max(e2e_steps, 1)) + 32 * world,
+                        "note": "C-ABI calls with host buffers (lowdin_it_set_species, lowdin_it_transform_stream_sink): coefficients (pinned) + orbital "
+                                "energies up; EVERY MO integral of the pass comes down as dense blocks into pinned host memory while the transform "
+                                "runs, + the reduced sums.  AO values are generated on the device from the canonical index (a 5 TB host tensor "
+                                "cannot exist); the stored-AO flow is measured by e2e_stored_ao / stored_ao_resident"},
                 "gpu_launches": int(launches), "clocks": clocks, "parity": parity}
         last_beat[0] = time.monotonic() + 3600.0   # the CPU legs below are bounded by their own sampling, not by the watchdog
         if world == 1 and not args.no_cpu_baseline:

@@ -165,10 +165,11 @@ struct lowdin_it_ctx {
   DevBuf coltab;                             // column table of the chunk after the exchange (SRC_RECT_TABLE)
   DevBuf seg;                                // download mode: kept entries per window pair (convention order)
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
-  int q1_variant = 3;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
+  int q1_variant = 5;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
+  int stored_fused = 1;                      // stored AO tensors: 1 = fused unpack + first quarter (q1_load_ws5_kernel), 0 = expansion kernel + DMMA GEMM
   int q1_dbg = 0;                            // probe switches of the warp-specialised first quarter (Q1WsArgs::dbg)
   int q3_red = 0;                            // third-quarter accumulation: 0 = staged read-modify-write epilogue, 1 = red.global.add.f64 (EpiAccRed)
   int frag_perm = 1;                         // TMA kernels: 1 = conflict-free fragment-row permutation (it_gemm_tma.cuh, frag_row); validated on B200 in round 2 (bit-identical, +2.4 % per pass)
@@ -603,6 +604,56 @@ int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc
   return 0;
 }
 
+// Fused first quarter of STORED tensors (q1_load_ws5_kernel): the packed rows feed the DMMA warps directly, no dense slab.
+template <int TN, int KIND>
+cudaError_t launch_q1_load_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
+                               int nfb, double *T1t, int64_t ldt) {
+  constexpr int ST = 5;
+  constexpr size_t smem = q1_ws5_smem_bytes<TN, ST>();
+  auto kern = q1_load_ws5_kernel<TN, ST, KIND>;
+  static uint64_t configured = 0;
+  if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured); e != cudaSuccess) return e;
+  CUtensorMap mapB;
+  if (!make_operand_map(&mapB, Cf, nfb, nc, ldc, TN * 8)) return cudaErrorInvalidValue;
+  const int64_t ntiles = ceil_div(nc, 256) * (int64_t)bc;
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
+  Q1LoadArgs q{src.data, src.M, src.ld, slab0, bc, nc, nfb, T1t, ldt};
+  kern<<<grid, 512, smem, h->stream>>>(mapB, q);
+  h->launches += 1;
+  return cudaGetLastError();
+}
+bool q1_load_eligible(lowdin_it_handle h, const AoSource &src, const double *Cf, int64_t ldc) {
+  return h->stored_fused && (src.kind == SRC_SYM_PACKED || src.kind == SRC_RECT) && tensor_map_encoder() != nullptr &&
+         ((uintptr_t)Cf % 16 == 0) && (ldc % 2 == 0);
+}
+int launch_q1_load(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb, double *T1t,
+                   int64_t ldt) {
+  // window columns in balanced groups of at most 64, as for the generated sources (launch_q1_gen)
+  const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
+  for (int gi = 0, f = 0, w = 0; gi < groups && f < nfb; ++gi, f += w) {
+    w = std::min(8 * (units / groups + (gi < units % groups ? 1 : 0)), nfb - f);
+    const int tn = (int)ceil_div(w, 8);
+    const double *cf = Cf + (int64_t)f * ldc;
+    double *out = T1t + (int64_t)f * bc * ldt;
+    cudaError_t e = cudaSuccess;
+#define LOWDIN_Q1L(TN) (src.kind == SRC_RECT ? launch_q1_load_cfg<TN, SRC_RECT>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt) \
+                                             : launch_q1_load_cfg<TN, SRC_SYM_PACKED>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt))
+    switch (tn) {
+      case 1: e = LOWDIN_Q1L(1); break;
+      case 2: e = LOWDIN_Q1L(2); break;
+      case 3: e = LOWDIN_Q1L(3); break;
+      case 4: e = LOWDIN_Q1L(4); break;
+      case 5: e = LOWDIN_Q1L(5); break;
+      case 6: e = LOWDIN_Q1L(6); break;
+      case 7: e = LOWDIN_Q1L(7); break;
+      default: e = LOWDIN_Q1L(8); break;
+    }
+#undef LOWDIN_Q1L
+    CK(e);
+  }
+  return 0;
+}
+
 // List-driven first quarter of ONE PASS (it_list.cuh): T1list[slab][nu][f] for every slab, from the resident canonical list.
 int list_first_quarter(lowdin_it_handle h, const Plan &pl, const PassTables &pt) {
   const Half &hf = pl.h1;
@@ -644,6 +695,10 @@ int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt
     // slab generation + first quarter in one kernel: the dense slab never exists
     ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
     if (launch_q1_gen(h, pl.src, slab, (int)bc, nc, Cf, Cfs, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+  } else if (q1_load_eligible(h, pl.src, Cf, hf.ldc)) {
+    // stored tensor, fused: unpack (E.f90:1047-1063) on the way into shared memory + first quarter, no dense slab in HBM
+    ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
+    if (launch_q1_load(h, pl.src, slab, (int)bc, nc, Cf, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
   } else {
     {  // unpack (E.f90:1047-1063)
       ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
@@ -662,7 +717,7 @@ int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt
 int64_t first_half_batch(lowdin_it_handle h, const Plan &pl, int nfb, int64_t count) {
   const int nc = pl.h1.nc;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK);
+  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, pl.h1.C, pl.h1.ldc));
   const size_t per_slab = std::max(dense ? (size_t)nc * ldx : (size_t)0, (size_t)nfb * ldt) * sizeof(double);
   int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
   B = std::min<int64_t>(B, count);
@@ -678,7 +733,7 @@ int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t
   const Half &hf = pl.h1;
   const int nc = hf.nc, nfb = pt.nfb;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT || pl.src.kind == SRC_RANKK);
+  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, hf.C, hf.ldc));
   const int64_t B = first_half_batch(h, pl, nfb, count);
   if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
@@ -1583,7 +1638,7 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
   if (!h) return 1;
   switch (option) {
     case LOWDIN_IT_OPT_WORKSPACE_BYTES:
-      if (value < (1 << 16)) return fail(h, "workspace too small");
+      if (value < (1 << 12)) return fail(h, "workspace too small");
       h->workspace_bytes = (size_t)value; return 0;
     case LOWDIN_IT_OPT_CHUNK_COLS:
       if (value < 0) return fail(h, "negative chunk column limit");
@@ -1605,6 +1660,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->slab_logB = (int)value; return 0;
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_STORED_FUSED:
+      h->stored_fused = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_Q1_DEBUG:
       h->q1_dbg = (int)value; return 0;
     case LOWDIN_IT_OPT_Q3_RED:
@@ -1766,7 +1823,7 @@ int lowdin_it_debug_first_quarter(lowdin_it_handle h, int a, int b, int f_first,
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
   if (pl.src.kind == SRC_LIST && list_first_quarter(h, pl, pt)) return 1;
   const int64_t B = first_half_batch(h, pl, nf, nslabs);
-  const bool dense = !(pl.src.kind == SRC_LIST || pl.src.kind == SRC_HASH_SYM || pl.src.kind == SRC_HASH_RECT);
+  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, pl.h1.C, pl.h1.ldc));
   if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nf * ldt * sizeof(double)));
   for (int64_t s = 0; s < nslabs; s += B) {

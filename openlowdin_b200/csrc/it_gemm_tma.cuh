@@ -830,4 +830,174 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
   }
 }
 
+// =================================================================================================================
+// Fused first quarter for STORED AO tensors: the packed row is the A operand, no dense slab in HBM.
+//   T1t[f][z][mu] = sum_nu AO(slab0+z ; pair(mu,nu)) * C(nu, f)            (E.f90:1047-1090 in one kernel)
+// The unpack of E.f90:1047-1063 happens on the way into shared memory: the kernel is q1 variant 5 with the hashing warps
+// replaced by LOADER warps.  A loader lane owns rows mu = mu0 + 8 rg and, per k-tile, the four k values of its two 16-byte
+// chunks; the element (mu,nu) of the slab is read from where the symmetric packing keeps it:
+//     nu >= mu: pair = base(mu) + nu  -- the 4 lanes of a lane group read 2 x 64 contiguous bytes of packed row mu;
+//     nu <  mu: pair = base(nu) + mu  -- the 8 lane groups read 64 contiguous bytes of packed row nu (8 consecutive mu);
+// so both triangles arrive in whole 32-byte sectors, each packed element being read twice (once per triangle; the second read is
+// an L2 hit), and nothing is written back: per slab 8 M bytes of HBM reads instead of 8 M + 16 N^2 (dense slab written, then read
+// by the GEMM).  SRC_RECT reads row `slab` of a rectangular [slab][pair] tensor (inter-species AO storage, and the row-sharded
+// intra tensors of a communicator); SRC_SYM_PACKED adds the second level of the packing: (slab | pair) lives at
+// [min][max] (C.f90:264-272).  The loads of k-tile t + 1 are in flight while k-tile t is stored (two register sets).
+// =================================================================================================================
+struct Q1LoadArgs {
+  const double *data;  // SRC_RECT: [slab][ld]; SRC_SYM_PACKED: packed tensor
+  int64_t M, ld;       // pairs per slab vector; row stride (SRC_RECT)
+  int64_t slab0;
+  int bc, nc, nfb;
+  double *T1t;
+  int64_t ldt;
+};
+
+template <int TN, int STAGES, int KIND>
+__global__ void __launch_bounds__(512, 1) q1_load_ws5_kernel(const __grid_constant__ CUtensorMap mapB, Q1LoadArgs q) {
+  constexpr int BK = 16, BM = 256, BN = TN * 8;
+  constexpr int NCW = 8, NGW = 8;  // DMMA warps (32 rows each) / loader warps (32 rows each)
+  constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bars = ring_u + STAGES * STAGE_BYTES;  // full[s] at bars + 8 s, empty[s] at bars + 8 (STAGES + s)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tig = lane & 3;
+  const int grp = frag_row<true>(lane >> 2);
+  const int KT = (q.nc + BK - 1) / BK;
+  const int row_blocks = (q.nc + BM - 1) / BM;
+  const int ntiles = row_blocks * q.bc;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)KT;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, NGW + 1);         // one arrive per loader warp + the arrive.expect_tx of the TMA issuer
+      mbar_init(bars + 8 * (STAGES + s), NCW);  // one arrive per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&mapB);
+  }
+  __syncthreads();
+
+  const uint32_t off0 = (uint32_t)((tig ^ grp) << 4);  // swizzled chunk tig of a row with (row & 7) == grp; chunk 4+tig is off0 ^ 64
+
+  if (warp >= NCW) {
+    // ============================== loaders (warpgroups 2 and 3) ==============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (total_it == 0) return;
+    const int gw = warp - NCW;
+    const uint32_t n = (uint32_t)q.nc;
+    uint8_t *a_rows = ring + (gw * 32 + grp) * 128;  // rows 32 gw + 8 rg + grp, rg = 0..3
+    // the 16 values of iteration (tile, kt): v = 4 rg + c, c = 0..3 <-> k = kt*16 + {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9}
+    auto fetch = [&](int tile, int kt, double (&x)[16]) {
+      const int z = tile / row_blocks, rb = tile - z * row_blocks;
+      const int64_t slab = q.slab0 + z;
+      const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
+      const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
+      const uint32_t nus[4] = {nu0, nu0 + 1u, nu0 + 8u, nu0 + 9u};
+      const double *row = (KIND == SRC_RECT) ? q.data + slab * q.ld : q.data;
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        const uint32_t mu = mu0 + 8u * rg;
+        const uint32_t base_mu = pair_base(mu, n);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t nu = nus[c];
+          double v = 0.0;
+          if (mu < n && nu < n) {
+            const uint32_t pair = (nu >= mu) ? base_mu + nu : pair_base(nu, n) + mu;
+            if (KIND == SRC_RECT) v = __ldg(row + pair);
+            else {
+              const int64_t lo = slab < (int64_t)pair ? slab : (int64_t)pair, hi = slab < (int64_t)pair ? (int64_t)pair : slab;
+              v = __ldg(row + (lo * q.M - (lo * (lo + 1)) / 2 + hi));
+            }
+          }
+          x[4 * rg + c] = v;
+        }
+      }
+    };
+    double cur[16], nxt[16];
+    int tile = blockIdx.x, kt = 0;
+    fetch(tile, kt, cur);
+    for (uint32_t it = 0; it < total_it; ++it) {
+      // coordinates of the next iteration; its loads go out before this one's values are stored
+      int ntile = tile, nkt = kt + 1;
+      if (nkt == KT) { nkt = 0; ntile += gridDim.x; }
+      if (it + 1u < total_it) fetch(ntile, nkt, nxt);
+      const uint32_t s = it % STAGES;
+      if (it >= (uint32_t)STAGES) mbar_wait(bars + 8 * (STAGES + s), ((it / STAGES) & 1u) ^ 1u);
+      if (gw == 0 && lane == 0) {
+        mbar_expect_tx(bars + 8 * s, B_BYTES);
+        tma_load_2d(ring_u + s * STAGE_BYTES + A_BYTES, &mapB, bars + 8 * s, kt * BK, 0);
+      }
+      uint8_t *dst = a_rows + s * STAGE_BYTES;
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + off0) = make_double2(cur[4 * rg + 0], cur[4 * rg + 1]);
+        *reinterpret_cast<double2 *>(dst + rg * 8 * 128 + (off0 ^ 64u)) = make_double2(cur[4 * rg + 2], cur[4 * rg + 3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * s);
+#pragma unroll
+      for (int v = 0; v < 16; ++v) cur[v] = nxt[v];
+      tile = ntile; kt = nkt;
+    }
+    return;
+  }
+
+  // ============================== DMMA warps (warpgroups 0 and 1) ==============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+  const uint8_t *a_base = ring + (warp * 32 + grp) * 128;
+  const uint8_t *b_base = ring + A_BYTES + grp * 128;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int z = tile / row_blocks, rb = tile - z * row_blocks;
+    double acc[4][TN][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const uint32_t s = it % STAGES;
+      mbar_wait(bars + 8 * s, (it / STAGES) & 1u);
+      const uint8_t *as = a_base + s * STAGE_BYTES, *bs = b_base + s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t off = h ? (off0 ^ 64u) : off0;
+        double2 a[4], b[TN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2 *>(as + i * 8 * 128 + off);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const double2 *>(bs + j * 8 * 128 + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = rb * BM + warp * 32 + i * 8 + grp;
+      if (m >= q.nc) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int f = j * 8 + tig;  // permuted fragment mapping: accumulator [0] is column tig, [1] column tig + 4
+        if (f < q.nfb) q.T1t[((int64_t)f * q.bc + z) * q.ldt + m] = acc[i][j][0];
+        if (f + 4 < q.nfb) q.T1t[((int64_t)(f + 4) * q.bc + z) * q.ldt + m] = acc[i][j][1];
+      }
+    }
+  }
+}
+
 }  // namespace lowdin

@@ -159,6 +159,30 @@ def test_first_quarter_variants_are_bit_identical(T, n, f_first, nf):
     assert np.abs(out[5][1][:, 0, :] - ref).max() <= 1e-12
 
 
+@pytest.mark.parametrize("n,f_first,nf", [(300, 3, 56), (257, 1, 42), (19, 1, 5), (133, 100, 33), (520, 2, 70)])
+def test_stored_first_quarter_fused_equals_two_kernel_form(T, n, f_first, nf):
+    """Stored tensors: the fused unpack + first quarter (packed rows -> shared memory -> DMMA, q1_load_ws5_kernel) against the
+    expansion kernel + TMA GEMM, packed (intra) and rectangular (row-sharded / inter layout) storage, and against numpy."""
+    q, _ = np.linalg.qr(np.random.default_rng(n).standard_normal((n, n)))
+    T.set_species(0, np.asfortranarray(q))
+    T.set_generator(0, 0, 7 + n)
+    T.materialize(0, 0)                                  # packed M(M+1)/2 tensor in HBM
+    M = n * (n + 1) // 2
+    starts = (0, M // 2, M - 5)
+    try:
+        T.set_option(T.OPT_STORED_FUSED, 0)
+        two = [T.debug_first_quarter(0, 0, f_first, nf, s0, 5) for s0 in starts]
+        T.set_option(T.OPT_STORED_FUSED, 1)
+        fused = [T.debug_first_quarter(0, 0, f_first, nf, s0, 5) for s0 in starts]
+    finally:
+        T.set_option(T.OPT_STORED_FUSED, 1)
+    for a, b in zip(fused, two):
+        assert np.abs(a - b).max() <= 1e-12
+    X = T.debug_expand(0, 0, M // 2, 1)[0]
+    assert np.abs(fused[1][:, 0, :] - (X @ q[:, f_first - 1:f_first - 1 + nf]).T).max() <= 1e-12
+    T.set_generator(0, 0, 1)
+
+
 @pytest.mark.parametrize("gemm_variant", [1, 2])
 def test_ws_generated_source_inter_stream(O, ws, gemm_variant):
     na, nb, oa, ob = 21, 16, 5, 2
