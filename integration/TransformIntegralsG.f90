@@ -13,8 +13,8 @@
 !!    * window table and `symmetric` flag from TransformIntegralsC_checkMOIntegralType / checkInterMOIntegralType
 !!      (TransformIntegralsC.f90:1436-1963): the transformer object of method C is reused for that.  Both routines are
 !!      private in TransformIntegralsC_ today: add their two names to its `public ::` list (TransformIntegralsC.f90:81-86);
-!!    * AO integrals are read from the per-thread stream files exactly as TransformIntegralsC.f90:231-298 / :852-972 does
-!!      and handed to the library one stack at a time, untouched (int32 p,q,r,s; real64 v; terminator p = -1);
+!!    * AO integrals are read from the per-thread stream files of TransformIntegralsC.f90:231-298 / :852-972 and handed to
+!!      the library as raw bytes, 64 MiB at a time (blocks of int32 p,q,r,s; real64 v; terminator p = -1 decoded on the device);
 !!    * <prefix>moint.dat is written in method C's layout (TransformIntegralsC.f90:419-456), so
 !!      ReadTransformedIntegrals needs only `case ("C","G")`.
 module TransformIntegralsG_
@@ -65,6 +65,12 @@ module TransformIntegralsG_
        type(c_ptr), value :: handle, p, q, r, s, v
        integer(c_int64_t), value :: n
      end function lowdin_it_ao_push_stacks
+     integer(c_int) function lowdin_it_ao_push_blocks(handle, blocks, nblocks, stackSize) bind(C, name="lowdin_it_ao_push_blocks")
+       import :: c_int, c_int64_t, c_ptr
+       type(c_ptr), value :: handle, blocks
+       integer(c_int64_t), value :: nblocks
+       integer(c_int), value :: stackSize
+     end function lowdin_it_ao_push_blocks
      integer(c_int) function lowdin_it_ao_end(handle) bind(C, name="lowdin_it_ao_end")
        import :: c_int, c_ptr
        type(c_ptr), value :: handle
@@ -206,21 +212,23 @@ contains
     call TransformIntegralsG_writeMOIntegrals(this, trim(this%tables%prefixOfFile)//"moint.dat")
   end subroutine TransformIntegralsG_atomicToMolecularOfTwoSpecies
 
-  !> Reads <tid><stem>.ints of every producer thread and passes each stack straight to the library
-  !! (the reader loops of TransformIntegralsC.f90:247-296; the library stops at the p = -1 terminator itself).
+  !> Reads <tid><stem>.ints of every producer thread in pieces of up to 64 MiB and passes the RAW BYTES to the library
+  !! (lowdin_it_ao_push_blocks): the blocks `pp, qq, rr, ss, shellIntegrals` that the reader loops of
+  !! TransformIntegralsC.f90:247-296 consume one by one are decoded on the device -- terminator (p = -1, :279-280), index range
+  !! check and the scatter to ioff(min)+max (:264-272) -- so the host only moves bytes (55 GB/s from pinned memory on B200).
   subroutine TransformIntegralsG_pushStreams(this, stem)
     implicit none
     type(TransformIntegralsG) :: this
     character(*) :: stem
-    integer(c_int), allocatable, target :: pp(:), qq(:), rr(:), ss(:)
-    real(c_double), allocatable, target :: shellIntegrals(:)
+    integer(c_int8_t), allocatable, target :: raw(:)
     character(50) :: fileid
     integer :: nfiles, tid, unitid, status, stackSize
-    integer(8) :: filesize, istack
+    integer(8) :: filesize, nstacks, istack, perRead, n
     logical :: existFile
 
     stackSize = CONTROL_instance%INTEGRAL_STACK_SIZE
-    allocate(pp(stackSize), qq(stackSize), rr(stackSize), ss(stackSize), shellIntegrals(stackSize))
+    perRead = max(1_8, (64_8 * 1024_8 * 1024_8) / (24_8 * stackSize))     !! stacks per read
+    allocate(raw(perRead * 24_8 * stackSize))
     nfiles = omp_get_max_threads()          !! lowdin-ints.x wrote one stream per OpenMP thread (Libint2Iface.cpp:282-286)
     unitid = 40
     do tid = 0, nfiles - 1
@@ -230,16 +238,20 @@ contains
        if (.not. existFile) cycle
        open(unit=unitid, file=trim(fileid)//trim(stem)//".ints", status='old', access='stream', form='unformatted')
        inquire(unit=unitid, size=filesize)
-       filesize = filesize/24/stackSize       !! 24 bytes per integral (TransformIntegralsC.f90:251-253)
-       do istack = 1, filesize
-          read(unit=unitid, iostat=status) pp, qq, rr, ss, shellIntegrals
+       nstacks = filesize/24/stackSize        !! 24 bytes per integral (TransformIntegralsC.f90:251-253)
+       istack = 0
+       do while (istack < nstacks)
+          n = min(perRead, nstacks - istack)
+          read(unit=unitid, iostat=status) raw(1:n * 24_8 * stackSize)
           if (status /= 0) exit
-          if (lowdin_it_ao_push_stacks(this%handle, c_loc(pp), c_loc(qq), c_loc(rr), c_loc(ss), c_loc(shellIntegrals), &
-               int(stackSize, c_int64_t)) /= 0) call TransformIntegralsG_fail(this%handle)
+          !! one call per file piece; the terminator of the file's last stack ends the call's stream on the device
+          if (lowdin_it_ao_push_blocks(this%handle, c_loc(raw), int(n, c_int64_t), int(stackSize, c_int)) /= 0) &
+               call TransformIntegralsG_fail(this%handle)
+          istack = istack + n
        end do
        close(unitid)
     end do
-    deallocate(pp, qq, rr, ss, shellIntegrals)
+    deallocate(raw)
   end subroutine TransformIntegralsG_pushStreams
 
   !> Downloads the kept integrals (|x| > 1E-10, p,q,r,s loop order) and writes them in method C's record layout:

@@ -162,6 +162,11 @@ struct lowdin_it_ctx {
   void *sink_host[2] = {nullptr, nullptr};   // pinned host ring of the dense-block sink (lowdin_it_transform_stream_sink)
   size_t sink_host_cap = 0;
   cudaEvent_t ev_q4[2] = {}, ev_d2h[2] = {};
+  DevBuf Hx, H2x, coltabx;                   // second set of chunk buffers: the exchange of chunk c overlaps the first half of chunk c + 1
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fh[2] = {}, ev_ex[2] = {}, ev_sh[2] = {};
+  std::vector<cudaEvent_t> chunk_ev;         // four timing events per chunk (first half begin/end, second half begin/end)
+  int overlap_exchange = 1;                  // N > 1 ranks: 1 = double-buffered chunks, exchange on its own stream under the next chunk's first half
   DevBuf coltab;                             // column table of the chunk after the exchange (SRC_RECT_TABLE)
   DevBuf seg;                                // download mode: kept entries per window pair (convention order)
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
@@ -223,6 +228,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 void prof_drain(lowdin_it_handle h) {
   if (h->prof_recs.empty()) return;
   cudaStreamSynchronize(h->stream);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   for (auto &r : h->prof_recs) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->prof_pool[r.e0], h->prof_pool[r.e1]) == cudaSuccess) { h->prof_ms[r.cat] += ms; h->prof_cnt[r.cat] += 1; }
@@ -231,8 +237,8 @@ void prof_drain(lowdin_it_handle h) {
   h->prof_used = 0;
 }
 struct ProfScope {
-  lowdin_it_handle h; int idx = -1;
-  ProfScope(lowdin_it_handle h_, int cat, double work) : h(h_) {
+  lowdin_it_handle h; int idx = -1; cudaStream_t st;
+  ProfScope(lowdin_it_handle h_, int cat, double work, cudaStream_t st_ = nullptr) : h(h_), st(st_ ? st_ : h_->stream) {
     if (!h->prof_on) return;
     if (h->prof_used + 2 > 8192) prof_drain(h);
     while ((int)h->prof_pool.size() < h->prof_used + 2) { cudaEvent_t e; cudaEventCreate(&e); h->prof_pool.push_back(e); }
@@ -240,9 +246,9 @@ struct ProfScope {
     h->prof_recs.push_back({cat, h->prof_used, h->prof_used + 1});
     h->prof_used += 2;
     h->prof_work[cat] += work;
-    cudaEventRecord(h->prof_pool[h->prof_recs[idx].e0], h->stream);
+    cudaEventRecord(h->prof_pool[h->prof_recs[idx].e0], st);
   }
-  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_pool[h->prof_recs[idx].e1], h->stream); }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_pool[h->prof_recs[idx].e1], st); }
 };
 
 // ---- GEMM dispatch ----------------------------------------------------------------------------
@@ -605,12 +611,12 @@ int launch_q1_gen(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc
 }
 
 // Fused first quarter of STORED tensors (q1_load_ws5_kernel): the packed rows feed the DMMA warps directly, no dense slab.
-template <int TN, int KIND>
+template <int TN>
 cudaError_t launch_q1_load_cfg(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc,
                                int nfb, double *T1t, int64_t ldt) {
   constexpr int ST = 5;
   constexpr size_t smem = q1_ws5_smem_bytes<TN, ST>();
-  auto kern = q1_load_ws5_kernel<TN, ST, KIND>;
+  auto kern = q1_load_ws5_kernel<TN, ST>;
   static uint64_t configured = 0;
   if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured); e != cudaSuccess) return e;
   CUtensorMap mapB;
@@ -628,6 +634,7 @@ bool q1_load_eligible(lowdin_it_handle h, const AoSource &src, const double *Cf,
 }
 int launch_q1_load(lowdin_it_handle h, const AoSource &src, int64_t slab0, int bc, int nc, const double *Cf, int64_t ldc, int nfb, double *T1t,
                    int64_t ldt) {
+  if (src.kind != SRC_RECT) return fail(h, "internal: the fused stored first quarter reads rectangular rows");
   // window columns in balanced groups of at most 64, as for the generated sources (launch_q1_gen)
   const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
   for (int gi = 0, f = 0, w = 0; gi < groups && f < nfb; ++gi, f += w) {
@@ -636,8 +643,7 @@ int launch_q1_load(lowdin_it_handle h, const AoSource &src, int64_t slab0, int b
     const double *cf = Cf + (int64_t)f * ldc;
     double *out = T1t + (int64_t)f * bc * ldt;
     cudaError_t e = cudaSuccess;
-#define LOWDIN_Q1L(TN) (src.kind == SRC_RECT ? launch_q1_load_cfg<TN, SRC_RECT>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt) \
-                                             : launch_q1_load_cfg<TN, SRC_SYM_PACKED>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt))
+#define LOWDIN_Q1L(TN) launch_q1_load_cfg<TN>(h, src, slab0, bc, nc, cf, ldc, w, out, ldt)
     switch (tn) {
       case 1: e = LOWDIN_Q1L(1); break;
       case 2: e = LOWDIN_Q1L(2); break;
@@ -696,9 +702,23 @@ int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt
     ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
     if (launch_q1_gen(h, pl.src, slab, (int)bc, nc, Cf, Cfs, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
   } else if (q1_load_eligible(h, pl.src, Cf, hf.ldc)) {
-    // stored tensor, fused: unpack (E.f90:1047-1063) on the way into shared memory + first quarter, no dense slab in HBM
+    // stored tensor, fused: the M-vector of a slab feeds the DMMA warps directly, the symmetric N x N slab of E.f90:1047-1063 is
+    // formed on the way into shared memory (q1_load_ws5_kernel) and never exists in HBM
+    AoSource rows = pl.src;
+    int64_t first = slab;
+    if (pl.src.kind == SRC_SYM_PACKED) {
+      // packed tensor: first the full M-vectors of the batch (both halves of the packed symmetry in whole sectors)
+      const int64_t M = pl.src.M, ldr = roundup2(M);
+      ProfScope ps(h, 0, (double)bc * 16.0 * (double)M);
+      dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(bc, 32));
+      complete_rows_kernel<<<grid, 256, 0, h->stream>>>(pl.src.data, M, slab, (int)bc, ldr, h->X.as<double>());
+      h->launches += 1;
+      CK(cudaGetLastError());
+      rows = AoSource{SRC_RECT, h->X.as<double>(), M, ldr, bc, 0};
+      first = 0;
+    }
     ProfScope ps(h, 1, 2.0 * bc * nc * (double)nc * nfb);
-    if (launch_q1_load(h, pl.src, slab, (int)bc, nc, Cf, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
+    if (launch_q1_load(h, rows, first, (int)bc, nc, Cf, hf.ldc, nfb, h->T1t.as<double>(), ldt)) return 1;
   } else {
     {  // unpack (E.f90:1047-1063)
       ProfScope ps(h, 0, (double)bc * 8.0 * ((double)pl.src.M + (double)nc * nc));
@@ -713,12 +733,20 @@ int first_quarter_batch(lowdin_it_handle h, const Plan &pl, const PassTables &pt
   return 0;
 }
 
+// doubles of the X workspace one slab of the first half needs: the dense slab (expansion kernel + GEMM), the completed M-vector
+// (packed tensor, fused first quarter), nothing (generated / list / rectangular rows read in place)
+size_t x_per_slab(lowdin_it_handle h, const Plan &pl) {
+  const int nc = pl.h1.nc;
+  const bool stored = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT);
+  if (stored && q1_load_eligible(h, pl.src, pl.h1.C, pl.h1.ldc)) return pl.src.kind == SRC_SYM_PACKED ? (size_t)roundup2(pl.src.M) : 0;
+  if (stored || pl.src.kind == SRC_RANKK) return (size_t)nc * roundup2(nc);
+  return 0;
+}
 // slabs per batch of the first half: what the X / T1t workspaces hold, within the grid limits of the kernels
 int64_t first_half_batch(lowdin_it_handle h, const Plan &pl, int nfb, int64_t count) {
   const int nc = pl.h1.nc;
-  const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, pl.h1.C, pl.h1.ldc));
-  const size_t per_slab = std::max(dense ? (size_t)nc * ldx : (size_t)0, (size_t)nfb * ldt) * sizeof(double);
+  const int64_t ldt = roundup2(nc);
+  const size_t per_slab = std::max(x_per_slab(h, pl), (size_t)nfb * ldt) * sizeof(double);
   int64_t B = std::max<int64_t>(1, (int64_t)(h->workspace_bytes / per_slab));
   B = std::min<int64_t>(B, count);
   B = std::min<int64_t>(B, std::max<int64_t>(1, (int64_t)(60000LL * 128 / nc)));  // gridDim.y limit of the stacked GEMM
@@ -733,9 +761,8 @@ int first_half(lowdin_it_handle h, const Plan &pl, const PassTables &pt, int64_t
   const Half &hf = pl.h1;
   const int nc = hf.nc, nfb = pt.nfb;
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
-  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, hf.C, hf.ldc));
   const int64_t B = first_half_batch(h, pl, nfb, count);
-  if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  if (x_per_slab(h, pl)) CK(h->X.ensure((size_t)B * x_per_slab(h, pl) * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nfb * ldt * sizeof(double)));
   for (int64_t s = 0; s < count; s += B) {
     const int64_t bc = std::min<int64_t>(B, count - s);
@@ -844,7 +871,7 @@ struct Consumer {
   double lambda = 2.0;
 };
 
-int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out);
+int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, DevBuf &Hsrc, DevBuf &H2dst, cudaStream_t st);
 
 int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass, int n_passes, const Consumer &cons,
                double sums_out[4]) {
@@ -907,11 +934,15 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     double out_need = download ? (double)std::max(nmine, 1) * per_out * 8.0
                                : std::min(4.0e9, (double)std::max(nmine, 1) * per_out * 8.0);
     out_need = std::max(out_need, (double)pl.max_slots_per_f * per_out * 8.0);
-    double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->OUT.cap + (double)h->X.cap + (double)h->T1t.cap) -
+    double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->OUT.cap +
+                           (double)h->X.cap + (double)h->T1t.cap) -
                    out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
     // bytes per chunk column: one rank holds H[all slots][its 1/G of the columns] and, after the exchange, H2[its slots][all
     // columns] (counted twice: headroom for NCCL's own buffers) -- the same 3/G of a full column pick_occ_batch assumes
-    const double per_col = (G > 1) ? (double)pt.nslots * 8.0 / G + 2.0 * (double)nmine * 8.0 : (double)pt.nslots * 8.0;
+    // (with the exchange overlapped: two sets of both buffers)
+    const double per_col = (G > 1) ? (h->overlap_exchange ? 2.0 * ((double)pt.nslots * 8.0 / G + (double)nmine * 8.0) + 8.0
+                                                          : (double)pt.nslots * 8.0 / G + 2.0 * (double)nmine * 8.0 + 8.0)
+                                   : (double)pt.nslots * 8.0;
     int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
     if (agree_min(h, &max_cols)) return 1;  // same chunk boundaries on every rank (the exchange depends on them)
     if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
@@ -931,50 +962,105 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       chunks.push_back({p0, p1, (int64_t)pair0(p0, p0, n2), width});
       p0 = p1;
     }
-    CK(cudaEventRecord(h->ev[0], h->stream));
     float ms_first = 0, ms_exch = 0, ms_second = 0;
-    for (const Chunk &ck : chunks) {
-      // ---------------- first half (E.f90:1043-1132) over this rank's share of the chunk's slabs ----------------
+    // ---------------- the chunks: first half -> exchange -> third quarter ----------------
+    // N > 1 ranks: two sets of chunk buffers; the exchange of chunk c runs on its own stream while the first half of chunk c + 1
+    // computes (compute stream: FH(0) FH(1) SH(0) FH(2) SH(1) ...).
+    const bool pipelined = (G > 1) && h->overlap_exchange && chunks.size() > 1;
+    if (G > 1 && !h->comm_stream) {
+      CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_fh[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_ex[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_sh[i], cudaEventDisableTiming));
+      }
+    }
+    cudaStream_t cs = pipelined ? h->comm_stream : h->stream;
+    DevBuf *Hb[2] = {&h->H, &h->Hx}, *H2b[2] = {&h->H2, &h->H2x}, *tabb[2] = {&h->coltab, &h->coltabx};
+    while (h->chunk_ev.size() < 4 * chunks.size() + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->chunk_ev.push_back(e); }
+    std::vector<int64_t> c_ldh(chunks.size(), 0);
+    auto stage_first = [&](size_t c) -> int {
+      const Chunk &ck = chunks[c];
+      const int bsel = pipelined ? (int)(c & 1) : 0;
       int64_t wblk, loc_lo, cnt;  // this rank's slabs of the chunk: local slabs [loc_lo, loc_lo + cnt) (G == 1: the chunk itself)
       shard_plan(nfb, pt.fbeg.data(), ck.base, ck.width, G, h->rank, h->slab_logB, own.data(), &wblk, &loc_lo, &cnt);
       const int64_t ldh = (G > 1) ? std::max<int64_t>(wblk, 1) : ck.width;
-      CK(h->H.ensure(std::max<size_t>((size_t)pt.nslots * ldh, 1) * sizeof(double)));
-      CK(cudaEventRecord(h->ev[1], h->stream));
-      if (cnt > 0 && first_half(h, pl, pt, loc_lo, cnt, h->H.as<double>(), ldh, 0, half_tol)) return 1;
+      c_ldh[c] = ldh;
+      CK(Hb[bsel]->ensure(std::max<size_t>((size_t)pt.nslots * ldh, 1) * sizeof(double)));
+      CK(cudaEventRecord(h->chunk_ev[4 * c], h->stream));
+      // first half (E.f90:1043-1132) over this rank's share of the chunk's slabs
+      if (cnt > 0 && first_half(h, pl, pt, loc_lo, cnt, Hb[bsel]->as<double>(), ldh, 0, half_tol)) return 1;
       flops += 2.0 * h1.nc * nfb * ((double)h1.nc + h1.ns) * (double)cnt;
-      CK(cudaEventRecord(h->ev[2], h->stream));
-      // ---------------- exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203) ----------------
-      AoSource hsrc{SRC_RECT, h->H.as<double>(), ck.width, ldh, 0, 0};
+      CK(cudaEventRecord(h->chunk_ev[4 * c + 1], h->stream));
       if (G > 1) {
-        ProfScope ps(h, 7, (double)pt.nslots * (double)cnt * 8.0);
-        if (exchange_chunk(h, own, ldh, &hsrc)) return 1;
+        // exchange (the it2.tmp bucket file of E.f90:1121-1141, :1189-1203)
+        if (pipelined) {
+          CK(cudaEventRecord(h->ev_fh[bsel], h->stream));
+          CK(cudaStreamWaitEvent(cs, h->ev_fh[bsel], 0));
+          if (c >= 2) CK(cudaStreamWaitEvent(cs, h->ev_sh[bsel], 0));  // the third quarter of chunk c - 2 has read this H2
+        }
+        {
+          ProfScope ps(h, 7, (double)pt.nslots * (double)cnt * 8.0, cs);
+          if (exchange_chunk(h, own, ldh, *Hb[bsel], *H2b[bsel], cs)) return 1;
+        }
+        if (pipelined) CK(cudaEventRecord(h->ev_ex[bsel], cs));
+      }
+      return 0;
+    };
+    auto stage_second = [&](size_t c) -> int {
+      const Chunk &ck = chunks[c];
+      const int bsel = pipelined ? (int)(c & 1) : 0;
+      const int64_t ldh = c_ldh[c];
+      if (pipelined) CK(cudaStreamWaitEvent(h->stream, h->ev_ex[bsel], 0));
+      CK(cudaEventRecord(h->chunk_ev[4 * c + 2], h->stream));
+      AoSource hsrc{SRC_RECT, Hb[bsel]->as<double>(), ck.width, ldh, 0, 0};
+      if (G > 1) {
         // column table: chunk column -> (sending rank's block, its local column)
         RankStarts st{};
         for (int r = 0; r < G; ++r) st.lo[r] = slabs_owned_below(ck.base, h->slab_logB, G, r);
-        CK(h->coltab.ensure((size_t)ck.width * sizeof(int64_t)));
+        CK(tabb[bsel]->ensure((size_t)ck.width * sizeof(int64_t)));
         column_table_kernel<<<(unsigned)ceil_div(ck.width, 256), 256, 0, h->stream>>>(ck.base, ck.width, h->slab_logB, G, (int64_t)nmine, ldh, st,
-                                                                                     h->coltab.as<int64_t>());
+                                                                                     tabb[bsel]->as<int64_t>());
         CK(cudaGetLastError());
-        hsrc = AoSource{SRC_RECT_TABLE, h->H2.as<double>(), ck.width, ldh, (int64_t)nmine, 0, 0, reinterpret_cast<const double *>(h->coltab.p)};
+        hsrc = AoSource{SRC_RECT_TABLE, H2b[bsel]->as<double>(), ck.width, ldh, (int64_t)nmine, 0, 0, reinterpret_cast<const double *>(tabb[bsel]->p)};
       }
-      CK(cudaEventRecord(h->ev[3], h->stream));
-      // ---------------- third quarter of the chunk, accumulated into T3 (own slots) ----------------
+      // third quarter of the chunk, accumulated into T3 (own slots)
       if (nmine > 0) {
         // rows of hsrc are numbered from this rank's first slot when the data came through the exchange
-        AoSource src2 = hsrc;
         int lo = s_lo, hi = s_hi;
         if (G > 1) { lo = 0; hi = nmine; }
-        if (second_half_partial(h, pl, src2, ck, lo, hi, h->T3.as<double>() + (G > 1 ? 0 : 0), ldt2)) return 1;
+        if (second_half_partial(h, pl, hsrc, ck, lo, hi, h->T3.as<double>(), ldt2)) return 1;
         const double nrw = n2 - ck.p0, pc = ck.p1 - ck.p0, ncv = n2 - ck.p1;
         flops += 2.0 * (double)nmine * nf2 * (nrw * pc + pc * ncv);
       }
-      CK(cudaEventRecord(h->ev[4], h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      prof_drain(h);
-      float ms;
-      CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_first += ms;
-      CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); ms_exch += ms;
-      CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); ms_second += ms;
+      CK(cudaEventRecord(h->chunk_ev[4 * c + 3], h->stream));
+      if (pipelined) CK(cudaEventRecord(h->ev_sh[bsel], h->stream));
+      return 0;
+    };
+    cudaEvent_t ev_begin = h->chunk_ev[4 * chunks.size()], ev_end = h->chunk_ev[4 * chunks.size() + 1];
+    CK(cudaEventRecord(ev_begin, h->stream));
+    if (pipelined) {
+      if (stage_first(0)) return 1;
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        if (c + 1 < chunks.size() && stage_first(c + 1)) return 1;
+        if (stage_second(c)) return 1;
+      }
+    } else {
+      for (size_t c = 0; c < chunks.size(); ++c)
+        if (stage_first(c) || stage_second(c)) return 1;
+    }
+    CK(cudaEventRecord(ev_end, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (G > 1) CK(cudaStreamSynchronize(cs));
+    prof_drain(h);
+    {
+      float ms, total = 0;
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        CK(cudaEventElapsedTime(&ms, h->chunk_ev[4 * c], h->chunk_ev[4 * c + 1])); ms_first += ms;
+        CK(cudaEventElapsedTime(&ms, h->chunk_ev[4 * c + 2], h->chunk_ev[4 * c + 3])); ms_second += ms;
+      }
+      CK(cudaEventElapsedTime(&total, ev_begin, ev_end));
+      ms_exch = std::max(0.0f, total - ms_first - ms_second);  // what the compute stream spent waiting for an exchange
     }
     // ---------------- fourth quarter (E.f90:1230-1239) + consumer, in groups of whole f-blocks ----------------
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -1140,27 +1226,27 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
 // All-to-all of one chunk of the half-transformed block between the halves.  Every rank holds
 // H[slot][its own wblk columns of the chunk] for ALL slots; afterwards it holds, for ITS slots, all columns as G
 // blocks [g][slot_local][wblk], which the chunk expansion reads in place through the chunk's column table (SRC_RECT_TABLE).
-int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, AoSource *src_out) {
+int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk, DevBuf &Hsrc, DevBuf &H2dst, cudaStream_t st) {
   const int G = h->nranks;
   if (!h->comm && !h->lgroup) return fail(h, "multi-GPU transform without a communicator");
   const int mine = own[h->rank + 1] - own[h->rank];
-  CK(h->H2.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
+  CK(H2dst.ensure(std::max<size_t>((size_t)std::max(mine, 1) * wblk * G, 1) * sizeof(double)));
   if (h->lgroup) {
     // in-process group: every rank PULLS its slots' rows from every peer's H with peer copies on its own stream
     LocalGroup &L = *h->lgroup;
     const int r = h->rank;
-    L.H[r] = h->H.as<double>();
-    CK(cudaEventRecord(L.ready[r], h->stream));  // my first half of this chunk is complete behind this event
+    L.H[r] = Hsrc.as<double>();
+    CK(cudaEventRecord(L.ready[r], st));  // my first half of this chunk is complete behind this event
     if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the exchange");
     for (int g = 0; g < G; ++g) {
-      CK(cudaStreamWaitEvent(h->stream, L.ready[g], 0));
+      CK(cudaStreamWaitEvent(st, L.ready[g], 0));
       if (mine > 0 && wblk > 0)
-        CK(cudaMemcpyPeerAsync(h->H2.as<double>() + (size_t)g * mine * wblk, h->device, L.H[g] + (size_t)own[r] * wblk, L.device[g],
-                               (size_t)mine * wblk * sizeof(double), h->stream));
+        CK(cudaMemcpyPeerAsync(H2dst.as<double>() + (size_t)g * mine * wblk, h->device, L.H[g] + (size_t)own[r] * wblk, L.device[g],
+                               (size_t)mine * wblk * sizeof(double), st));
     }
-    CK(cudaEventRecord(L.done[r], h->stream));
+    CK(cudaEventRecord(L.done[r], st));
     if (!L.barrier()) return fail(h, "in-process group: a rank did not reach the exchange");
-    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(h->stream, L.done[g], 0));  // my H is rewritten only after every peer has pulled
+    for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(st, L.done[g], 0));  // my H is rewritten only after every peer has pulled
     h->launches += 1;
     return 0;
   }
@@ -1168,13 +1254,12 @@ int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk
   for (int g = 0; g < G && rc == 0; ++g) {
     const size_t send_n = (size_t)(own[g + 1] - own[g]) * wblk;   // rows own[g]..own[g+1] of H (row stride wblk)
     const size_t recv_n = (size_t)mine * wblk;
-    if (send_n) rc = g_nccl.Send(h->H.as<double>() + (size_t)own[g] * wblk, send_n * sizeof(double), /*ncclChar*/ 0, g, h->comm, h->stream);
-    if (rc == 0 && recv_n) rc = g_nccl.Recv(h->H2.as<double>() + (size_t)g * mine * wblk, recv_n * sizeof(double), 0, g, h->comm, h->stream);
+    if (send_n) rc = g_nccl.Send(Hsrc.as<double>() + (size_t)own[g] * wblk, send_n * sizeof(double), /*ncclChar*/ 0, g, h->comm, st);
+    if (rc == 0 && recv_n) rc = g_nccl.Recv(H2dst.as<double>() + (size_t)g * mine * wblk, recv_n * sizeof(double), 0, g, h->comm, st);
   }
   if (rc == 0) rc = g_nccl.GroupEnd();
   if (rc != 0) return fail(h, std::string("NCCL all-to-all failed: ") + g_nccl.GetErrorString(rc));
   h->launches += 1;
-  (void)src_out;
   return 0;
 }
 
@@ -1220,7 +1305,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
   for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); a.release_list(); a.seg_counts.release(); }
-  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->coltab, &h->seg, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
+  DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->coltab, &h->coltabx, &h->Hx, &h->H2x, &h->seg, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
                     &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v};
   for (DevBuf *b : bufs) b->release();
@@ -1229,6 +1314,9 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_scattered[i]) cudaEventDestroy(h->ev_scattered[i]); }
   for (int i = 0; i < 2; ++i) { if (h->sink_host[i]) cudaFreeHost(h->sink_host[i]); if (h->ev_q4[i]) cudaEventDestroy(h->ev_q4[i]); if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {h->ev_fh[i], h->ev_ex[i], h->ev_sh[i]}) if (e) cudaEventDestroy(e);
+  for (auto &ev : h->chunk_ev) cudaEventDestroy(ev);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1574,12 +1662,12 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   const double spf = std::max(pl.max_slots_per_f, 1);
   const double per_out = (double)pl.h2.ns * pl.h2.nf * 8.0;
   const double out_need = std::max(std::min(4.0e9, spf * per_out * nf), spf * per_out);
-  const double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->T3.cap +
+  const double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->T3.cap +
                                (double)h->X.cap + (double)h->T1t.cap) - 2.0 * (double)h->workspace_bytes - out_need - (double)((size_t)1 << 30);
   // per first-window value: third-quarter accumulators of its slots (own share) + a chunk of at least 8 pair rows of H
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
-  const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
+  const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? (h->overlap_exchange ? 4.0 : 3.0) / G : 1.0);
   const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 / G : 0.0;  // T1list[own slab][nu][f]
   int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
   if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
@@ -1660,6 +1748,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->slab_logB = (int)value; return 0;
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_OVERLAP_EXCHANGE:
+      h->overlap_exchange = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_STORED_FUSED:
       h->stored_fused = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_Q1_DEBUG:
@@ -1823,8 +1913,7 @@ int lowdin_it_debug_first_quarter(lowdin_it_handle h, int a, int b, int f_first,
   const int64_t ldx = roundup2(nc), ldt = roundup2(nc);
   if (pl.src.kind == SRC_LIST && list_first_quarter(h, pl, pt)) return 1;
   const int64_t B = first_half_batch(h, pl, nf, nslabs);
-  const bool dense = (pl.src.kind == SRC_RANKK) || ((pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT) && !q1_load_eligible(h, pl.src, pl.h1.C, pl.h1.ldc));
-  if (dense) CK(h->X.ensure((size_t)B * nc * ldx * sizeof(double)));
+  if (x_per_slab(h, pl)) CK(h->X.ensure((size_t)B * x_per_slab(h, pl) * sizeof(double)));
   CK(h->T1t.ensure((size_t)B * nf * ldt * sizeof(double)));
   for (int64_t s = 0; s < nslabs; s += B) {
     const int64_t bc = std::min<int64_t>(B, nslabs - s);

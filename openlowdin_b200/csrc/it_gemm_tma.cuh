@@ -838,22 +838,24 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
 // chunks; the element (mu,nu) of the slab is read from where the symmetric packing keeps it:
 //     nu >= mu: pair = base(mu) + nu  -- the 4 lanes of a lane group read 2 x 64 contiguous bytes of packed row mu;
 //     nu <  mu: pair = base(nu) + mu  -- the 8 lane groups read 64 contiguous bytes of packed row nu (8 consecutive mu);
-// so both triangles arrive in whole 32-byte sectors, each packed element being read twice (once per triangle; the second read is
-// an L2 hit), and nothing is written back: per slab 8 M bytes of HBM reads instead of 8 M + 16 N^2 (dense slab written, then read
-// by the GEMM).  SRC_RECT reads row `slab` of a rectangular [slab][pair] tensor (inter-species AO storage, and the row-sharded
-// intra tensors of a communicator); SRC_SYM_PACKED adds the second level of the packing: (slab | pair) lives at
-// [min][max] (C.f90:264-272).  The loads of k-tile t + 1 are in flight while k-tile t is stored (two register sets).
+// so both triangles arrive in whole 32-byte sectors, each element of the M-vector being read twice (once per triangle; the second
+// read is an L2 hit), and nothing is written back: per slab 8 M bytes of HBM reads instead of 8 M + 16 N^2 (dense slab written, then
+// read by the GEMM).  The source is row `slab` of a rectangular [slab][pair] tensor: the inter-species AO storage, the row-sharded
+// intra tensors of a communicator, or -- for the packed intra tensor of one GPU -- the batch of M-vectors that
+// complete_rows_kernel (it_kernels.cuh) has just assembled from both halves of the packing (C.f90:264-272).  (Resolving the packing
+// per element here instead was measured at 6.5 TF/s at N_bf = 500: one page and one sector per 8-byte element.)
+// The loads of k-tile t + 1 are in flight while k-tile t is stored (two register sets).
 // =================================================================================================================
 struct Q1LoadArgs {
-  const double *data;  // SRC_RECT: [slab][ld]; SRC_SYM_PACKED: packed tensor
-  int64_t M, ld;       // pairs per slab vector; row stride (SRC_RECT)
+  const double *data;  // [slab][ld]
+  int64_t M, ld;       // pairs per slab vector; row stride
   int64_t slab0;
   int bc, nc, nfb;
   double *T1t;
   int64_t ldt;
 };
 
-template <int TN, int STAGES, int KIND>
+template <int TN, int STAGES>
 __global__ void __launch_bounds__(512, 1) q1_load_ws5_kernel(const __grid_constant__ CUtensorMap mapB, Q1LoadArgs q) {
   constexpr int BK = 16, BM = 256, BN = TN * 8;
   constexpr int NCW = 8, NGW = 8;  // DMMA warps (32 rows each) / loader warps (32 rows each)
@@ -900,7 +902,7 @@ __global__ void __launch_bounds__(512, 1) q1_load_ws5_kernel(const __grid_consta
       const uint32_t mu0 = (uint32_t)(rb * BM + gw * 32 + grp);
       const uint32_t nu0 = (uint32_t)(kt * BK + 2 * tig);
       const uint32_t nus[4] = {nu0, nu0 + 1u, nu0 + 8u, nu0 + 9u};
-      const double *row = (KIND == SRC_RECT) ? q.data + slab * q.ld : q.data;
+      const double *row = q.data + slab * q.ld;
 #pragma unroll
       for (int rg = 0; rg < 4; ++rg) {
         const uint32_t mu = mu0 + 8u * rg;
@@ -911,11 +913,7 @@ __global__ void __launch_bounds__(512, 1) q1_load_ws5_kernel(const __grid_consta
           double v = 0.0;
           if (mu < n && nu < n) {
             const uint32_t pair = (nu >= mu) ? base_mu + nu : pair_base(nu, n) + mu;
-            if (KIND == SRC_RECT) v = __ldg(row + pair);
-            else {
-              const int64_t lo = slab < (int64_t)pair ? slab : (int64_t)pair, hi = slab < (int64_t)pair ? (int64_t)pair : slab;
-              v = __ldg(row + (lo * q.M - (lo * (lo + 1)) / 2 + hi));
-            }
+            v = __ldg(row + pair);
           }
           x[4 * rg + c] = v;
         }

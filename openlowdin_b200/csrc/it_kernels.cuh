@@ -287,6 +287,53 @@ __global__ void column_table_kernel(int64_t base, int64_t width, int logB, int G
   tab[c] = (int64_t)r * rows * ld + (slab_local(slab, logB, G) - st.lo[r]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step 1 of the two-step unpack of a PACKED intra tensor (E.f90:1047-1063): the full M-vectors of a batch of slabs.
+//   R[z][pair] = (slab0 + z | pair) = P[min][max],  z < bc, pair < M,   row stride ldr (even)
+// The packing keeps (slab | pair) in row `slab` only for pair >= slab; for pair < slab it lives in row `pair`, column `slab` -- a
+// stride-M gather if done slab by slab (one 32-byte sector and one page per 8-byte element: the expansion kernel of round 1 ran at
+// 0.38 of the HBM rate because of it).  Here a CTA owns a 32 x 32 tile of (slab, pair): the part with pair >= slab is read along
+// pair (row `slab` is contiguous), the part with pair < slab along SLAB (row `pair` holds the 32 slabs of the tile contiguously)
+// and turned in shared memory, so every read and every write is a run of whole sectors.  Each packed element is read twice over
+// the whole tensor (once as (lo | hi), once as (hi | lo)) and the full square is written once.
+// grid = (ceil(M/32), ceil(bc/32)), block = 256.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) complete_rows_kernel(const double *__restrict__ P, int64_t M, int64_t slab0, int bc, int64_t ldr,
+                                                            double *__restrict__ R) {
+  __shared__ double tile[32][33];  // [slab within tile][pair within tile]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;            // first pair of the tile
+  const int z0 = blockIdx.y * 32;                         // first slab of the tile, relative to slab0
+  const int64_t s_lo = slab0 + z0, s_hi = s_lo + 31;      // slab range of the tile (s_hi may exceed the batch)
+  // part A: pair >= slab, lanes along pair
+  if (p0 + 31 >= s_lo) {
+    const int64_t pair = p0 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int zz = w + 8 * k;
+      const int64_t slab = s_lo + zz;
+      if (z0 + zz < bc && pair < M && pair >= slab) tile[zz][lane] = __ldg(P + (slab * M - (slab * (slab + 1)) / 2 + pair));
+    }
+  }
+  // part B: pair < slab, lanes along slab (row `pair` of the packed tensor, columns s_lo .. s_lo + 31)
+  if (p0 < s_hi) {
+    const int64_t slab = s_lo + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pp = w + 8 * k;
+      const int64_t pair = p0 + pp;
+      if (z0 + lane < bc && pair < M && pair < slab) tile[lane][pp] = __ldg(P + (pair * M - (pair * (pair + 1)) / 2 + slab));
+    }
+  }
+  __syncthreads();
+  const int64_t pair = p0 + lane;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int zz = w + 8 * k;
+    if (z0 + zz < bc && pair < M) R[(int64_t)(z0 + zz) * ldr + pair] = tile[zz][lane];
+  }
+}
+
 // Generated AO set -> stored layout on the device (tests and the stored-AO bench leg at sizes whose list cannot come from a host):
 // intra: packed row `slab` holds pairs slab..M-1; inter: rectangular [slab][pair].  grid.x strides over slabs.
 template <int KIND>

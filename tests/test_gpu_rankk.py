@@ -117,16 +117,18 @@ def test_rankk_n500_stream_sums_match_closed_form(O, T, stored):
     pair energy against the closed form; `stored` runs the same tensor materialised in HBM (63 GB packed) through the stored-AO kernels."""
     n = 500
     occ, L, Cm, eps = _large_case(O, T, n, 501)
-    if stored:
-        T.materialize(0, 0)
-    got = T.transform_stream(0, 0, _mp2_win(n, occ), ol.CONV_E, occ_batch=25, epsA=eps)
+    try:
+        if stored:
+            T.materialize(0, 0)
+        got = T.transform_stream(0, 0, _mp2_win(n, occ), ol.CONV_E, occ_batch=25, epsA=eps)
+    finally:
+        T.set_generator(0, 0, 1)                  # release the 63 GB tensor whatever happens
     Tvo = O.rankk_mo_factors(L, Cm, np.arange(occ, n), np.arange(occ))
     want = rankk_stream_sums(Tvo, eps, occ, range(occ))
     assert got[0] == want[0]
     assert abs(got[1] - want[1]) <= 1e-9 * max(1.0, abs(want[1]))
     assert abs(got[2] - want[2]) <= 1e-10 * want[2]
     assert abs(got[3] - want[3]) <= 1e-9 * max(1.0, abs(want[3])), (got[3], want[3])
-    T.set_generator(0, 0, 1)                      # release the 63 GB tensor
 
 
 @pytest.mark.gpu

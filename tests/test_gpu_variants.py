@@ -166,21 +166,21 @@ def test_stored_first_quarter_fused_equals_two_kernel_form(T, n, f_first, nf):
     q, _ = np.linalg.qr(np.random.default_rng(n).standard_normal((n, n)))
     T.set_species(0, np.asfortranarray(q))
     T.set_generator(0, 0, 7 + n)
-    T.materialize(0, 0)                                  # packed M(M+1)/2 tensor in HBM
     M = n * (n + 1) // 2
     starts = (0, M // 2, M - 5)
     try:
+        T.materialize(0, 0)                              # packed M(M+1)/2 tensor in HBM
         T.set_option(T.OPT_STORED_FUSED, 0)
         two = [T.debug_first_quarter(0, 0, f_first, nf, s0, 5) for s0 in starts]
         T.set_option(T.OPT_STORED_FUSED, 1)
         fused = [T.debug_first_quarter(0, 0, f_first, nf, s0, 5) for s0 in starts]
+        X = T.debug_expand(0, 0, M // 2, 1)[0]
     finally:
         T.set_option(T.OPT_STORED_FUSED, 1)
+        T.set_generator(0, 0, 1)                         # release the tensor
     for a, b in zip(fused, two):
         assert np.abs(a - b).max() <= 1e-12
-    X = T.debug_expand(0, 0, M // 2, 1)[0]
     assert np.abs(fused[1][:, 0, :] - (X @ q[:, f_first - 1:f_first - 1 + nf]).T).max() <= 1e-12
-    T.set_generator(0, 0, 1)
 
 
 @pytest.mark.parametrize("gemm_variant", [1, 2])
