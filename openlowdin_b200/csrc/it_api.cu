@@ -477,6 +477,16 @@ void build_pass(const Plan &pl, int f0, int nfb, PassTables &pt) {
   for (auto &e : byconv) { pt.order.push_back(e.second); pt.order_conv.push_back(e.first); }
 }
 
+// The transform's workspaces (chunk buffers, accumulators, result blocks) grow to what the largest transform so far needed --
+// up to all of the free HBM -- and are kept for the next one.  Calls that allocate INPUT storage (a stored AO tensor) give them
+// back first: they are re-created on demand, the tensor is not.
+void release_workspaces(lowdin_it_handle h) {
+  cudaStreamSynchronize(h->stream);
+  DevBuf *ws[] = {&h->X, &h->T1t, &h->H, &h->H2, &h->Hx, &h->H2x, &h->OUT, &h->T3, &h->T1list, &h->coltab, &h->coltabx,
+                  &h->r_i0, &h->r_i1, &h->r_i2, &h->r_i3, &h->r_v, &h->dtmp};
+  for (DevBuf *b : ws) b->release();
+}
+
 int upload_i32(lowdin_it_handle h, DevBuf &buf, const std::vector<int32_t> &v) {
   CK(buf.ensure(std::max<size_t>(v.size(), 1) * sizeof(int32_t)));
   if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -923,6 +933,15 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     const int s_lo = own[h->rank], s_hi = own[h->rank + 1], nmine = s_hi - s_lo;
     // ---- device memory of the pass: T3 accumulators (own slots) + one chunk of half-transformed rows ----
     const size_t t3_bytes = std::max<size_t>((size_t)std::max(nmine, 1) * nf2 * ldt2, 1) * sizeof(double);
+    if (t3_bytes > h->T3.cap) {
+      // the chunk buffers of an earlier transform may hold all the free memory (they take what is left): give them back before growing T3
+      size_t fb = 0, tb = 0;
+      CK(cudaMemGetInfo(&fb, &tb));
+      if (fb < t3_bytes + ((size_t)1 << 30)) {
+        CK(cudaStreamSynchronize(h->stream));
+        for (DevBuf *b : {&h->H, &h->H2, &h->Hx, &h->H2x, &h->OUT, &h->T3}) b->release();
+      }
+    }
     CK(h->T3.ensure(t3_bytes));
     CK(cudaMemsetAsync(h->T3.p, 0, t3_bytes, h->stream));
     if (pl.src.kind == SRC_LIST) {
@@ -934,9 +953,12 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     double out_need = download ? (double)std::max(nmine, 1) * per_out * 8.0
                                : std::min(4.0e9, (double)std::max(nmine, 1) * per_out * 8.0);
     out_need = std::max(out_need, (double)pl.max_slots_per_f * per_out * 8.0);
+    const bool sink_mode = (cons.mode == 1 && cons.sink != nullptr);
+    // a host sink double-buffers its (smaller) groups: two groups of max(workspace, one f-block) must fit
+    const double out_reserve = sink_mode ? 2.0 * std::min(out_need, std::max((double)h->workspace_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
     double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->OUT.cap +
                            (double)h->X.cap + (double)h->T1t.cap) -
-                   out_need - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
+                   std::max(out_need, out_reserve) - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
     // bytes per chunk column: one rank holds H[all slots][its 1/G of the columns] and, after the exchange, H2[its slots][all
     // columns] (counted twice: headroom for NCCL's own buffers) -- the same 3/G of a full column pick_occ_batch assumes
     // (with the exchange overlapped: two sets of both buffers)
@@ -1362,6 +1384,7 @@ int lowdin_it_ao_begin(lowdin_it_handle h, int a, int b, int swapped) {
   AoSet &S = h->ao[a][b];
   const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
   const size_t count = (a == b) ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb);
+  if (count * sizeof(double) > ((size_t)1 << 30)) release_workspaces(h);
   S.release_list();
   S.swapped = swapped;
   if (h->ao_list) {  // keep the list as it comes (16 bytes per integral); the first quarter is then list-driven (it_list.cuh)
@@ -1560,6 +1583,7 @@ int lowdin_it_ao_materialize(lowdin_it_handle h, int a, int b) {
   if (src.kind != SRC_HASH_SYM && src.kind != SRC_HASH_RECT && src.kind != SRC_RANKK) return fail(h, "ao_materialize: the AO set is not a generated one");
   const bool intra = (a == b);
   const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  release_workspaces(h);
   const bool shard = h->nranks > 1;  // on a communicator: the rank's own rows only, as an upload would leave them
   const int64_t nrows = shard ? slabs_owned_below(Mb, h->slab_logB, h->nranks, h->rank) : Mb;
   const size_t count = shard ? std::max<size_t>((size_t)nrows * Ma, 1) : (intra ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb));

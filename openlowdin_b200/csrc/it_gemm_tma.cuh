@@ -75,6 +75,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Consumer release of a ring stage.  The stage's fragments were read with ld.shared; ptxas schedules the mbarrier arrive right behind
+// the ISSUE of the last of those loads, ahead of the DMMAs that wait for their data (SASS of q1_load_ws5_kernel: LDS, LDS, LDS,
+// SYNCS.ARRIVE, DMMA ...).  A shared load that is still in flight when the producer is released can then be overtaken by the
+// producer's refill of the stage: seen on B200 with the loader warps' global loads backing up the memory pipe -- about one
+// 32-row x 24-column piece of one tile in 10^4, always the columns of the last-loaded fragments.  The fence makes every lane's
+// loads of the stage complete before the warp's arrive.
+__device__ __forceinline__ void release_stage(uint32_t empty_bar, int lane) {
+  __threadfence_block();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
@@ -212,8 +223,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
 #pragma unroll
           for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+      release_stage(bars + 8 * (STAGES + s), lane);
       if (producer) {
         // refill, without blocking, every slot that all warps have released (runs ahead into the next tile)
         while (prod_it < total_it && prod_it < it + 1u + (uint32_t)STAGES) {
@@ -453,8 +463,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws_kernel(const __grid_constant
 #pragma unroll
           for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+      release_stage(bars + 8 * (STAGES + s), lane);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -649,8 +658,7 @@ __global__ void __launch_bounds__(384, 1) q1_gen_ws2_kernel(const __grid_constan
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[1][i].y, fb[1][j].y);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));  // both halves of stage s are in registers or consumed
+      release_stage(bars + 8 * (STAGES + s), lane);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -813,8 +821,7 @@ __global__ void __launch_bounds__(512, 1) q1_gen_ws5_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+      release_stage(bars + 8 * (STAGES + s), lane);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -981,8 +988,7 @@ __global__ void __launch_bounds__(512, 1) q1_load_ws5_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+      release_stage(bars + 8 * (STAGES + s), lane);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
