@@ -391,7 +391,7 @@ def test_stream_sink_delivers_every_mo_integral(O, T, qb):
                         x = vals[t, ks, kf]
                         if abs(x) > 1e-10:
                             got[row, pid(r - 1, s - 1, n2)] = x
-        T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 16)
+        T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 12)
         try:
             sums = T.transform_stream_sink(a, b, win, ol.CONV_E, sink, occ_batch=qb)
         finally:
