@@ -562,9 +562,9 @@ def main():
         T.set_species(1, Cs)
         T.set_generator(1, 1, g["seed"], 1)
         worst = 0.0
-        for cols, qb in ((0, 0), (60, 4), (1, 2)):
+        for cols, qb_small in ((0, 0), (60, 4), (1, 2)):
             T.set_option(T.OPT_CHUNK_COLS, cols)
-            sm = torch.tensor(T.transform_stream(1, 1, mp2_window_e(g["n"], g["occ"]), ol.CONV_E, occ_batch=qb,
+            sm = torch.tensor(T.transform_stream(1, 1, mp2_window_e(g["n"], g["occ"]), ol.CONV_E, occ_batch=qb_small,
                                                  epsA=synthetic_eps(g["occ"], g["n"])), dtype=torch.float64, device=dev)
             dist.all_reduce(sm)
             sm = sm.tolist()

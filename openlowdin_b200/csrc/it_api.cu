@@ -166,7 +166,7 @@ struct lowdin_it_ctx {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_fh[2] = {}, ev_ex[2] = {}, ev_sh[2] = {};
   std::vector<cudaEvent_t> chunk_ev;         // four timing events per chunk (first half begin/end, second half begin/end)
-  int overlap_exchange = 1;                  // N > 1 ranks: 1 = double-buffered chunks, exchange on its own stream under the next chunk's first half
+  int overlap_exchange = 1;                  // N > 1 ranks: double-buffered chunks, exchange on its own stream under the next chunk's first half: 0 never, 1 when memory allows wide chunks, 2 always
   DevBuf coltab;                             // column table of the chunk after the exchange (SRC_RECT_TABLE)
   DevBuf seg;                                // download mode: kept entries per window pair (convention order)
   size_t workspace_bytes = (size_t)1 << 30;  // target size of the X / T1t batch buffers
@@ -961,12 +961,18 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
                    std::max(out_need, out_reserve) - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
     // bytes per chunk column: one rank holds H[all slots][its 1/G of the columns] and, after the exchange, H2[its slots][all
     // columns] (counted twice: headroom for NCCL's own buffers) -- the same 3/G of a full column pick_occ_batch assumes
-    // (with the exchange overlapped: two sets of both buffers)
-    const double per_col = (G > 1) ? (h->overlap_exchange ? 2.0 * ((double)pt.nslots * 8.0 / G + (double)nmine * 8.0) + 8.0
-                                                          : (double)pt.nslots * 8.0 / G + 2.0 * (double)nmine * 8.0 + 8.0)
-                                   : (double)pt.nslots * 8.0;
+    const double per_col = (G > 1) ? (double)pt.nslots * 8.0 / G + 2.0 * (double)nmine * 8.0 + 8.0 : (double)pt.nslots * 8.0;
     int64_t max_cols = (int64_t)std::max(avail / per_col, 0.0);
     if (agree_min(h, &max_cols)) return 1;  // same chunk boundaries on every rank (the exchange depends on them)
+    // Overlapping the exchange takes two sets of both buffers, i.e. chunks 3/4 as wide -- more chunks, more read-modify-write passes
+    // over T3.  Measured at N_bf = 1500 (profiles/r02n_*): with ~24 chunks per pass (2 GPUs) the narrower chunks cost more than the
+    // hidden exchange gains (47.3 against 50.1 TF/s); with memory to spare (<= 12 chunks per pass) the exchange is what is left to
+    // hide.  1 = decide per pass (from the agreed width, so every rank decides alike), 2 = always, 0 = never.
+    bool use_overlap = false;
+    if (G > 1 && h->overlap_exchange) {
+      use_overlap = (h->overlap_exchange == 2) || ((double)max_cols * 12.0 >= (double)pl.nslabs1);
+      if (use_overlap) max_cols = max_cols * 3 / 4;
+    }
     if (max_cols < 2 * (int64_t)n2 && max_cols < pl.nslabs1) return fail(h, "not enough device memory for one chunk of half-transformed integrals; lower occ_batch");
     if (h->chunk_cols_limit > 0) max_cols = std::min<int64_t>(max_cols, h->chunk_cols_limit);
     // chunks: rows [p0,p1) of the pair triangle, even boundaries, as many rows as fit
@@ -988,7 +994,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     // ---------------- the chunks: first half -> exchange -> third quarter ----------------
     // N > 1 ranks: two sets of chunk buffers; the exchange of chunk c runs on its own stream while the first half of chunk c + 1
     // computes (compute stream: FH(0) FH(1) SH(0) FH(2) SH(1) ...).
-    const bool pipelined = (G > 1) && h->overlap_exchange && chunks.size() > 1;
+    const bool pipelined = use_overlap && chunks.size() > 1;
     if (G > 1 && !h->comm_stream) {
       CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; ++i) {
@@ -1691,7 +1697,7 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   // per first-window value: third-quarter accumulators of its slots (own share) + a chunk of at least 8 pair rows of H
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
-  const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? (h->overlap_exchange ? 4.0 : 3.0) / G : 1.0);
+  const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
   const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 / G : 0.0;  // T1list[own slab][nu][f]
   int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
   if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
@@ -1773,7 +1779,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_OVERLAP_EXCHANGE:
-      h->overlap_exchange = value ? 1 : 0; return 0;
+      if (value < 0 || value > 2) return fail(h, "overlap option must be 0, 1 or 2");
+      h->overlap_exchange = (int)value; return 0;
     case LOWDIN_IT_OPT_STORED_FUSED:
       h->stored_fused = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_Q1_DEBUG:

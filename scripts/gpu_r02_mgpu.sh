@@ -5,8 +5,8 @@ TAG=${1:-r02m}; NG=${2:-2}; STEPS=${3:-1}
 mkdir -p gpurun_out
 O=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511"
-( timeout 400 $TR scripts/mgpu_check.py > $O/${TAG}_mgpu_check_g$NG.log 2>&1; echo "exit $?" >> $O/${TAG}_mgpu_check_g$NG.log ); grep -v "^W\|^\[W\|warn" $O/${TAG}_mgpu_check_g$NG.log | tail -22
-( timeout 300 python -m pytest tests/test_multi_gpu.py tests/test_gpu_local_group.py -m gpu -q -p timeout --timeout 250 > $O/${TAG}_pytest_mgpu.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest_mgpu.log ); tail -4 $O/${TAG}_pytest_mgpu.log
+( [ "$SKIPCHECK" = "1" ] || timeout 400 $TR scripts/mgpu_check.py > $O/${TAG}_mgpu_check_g$NG.log 2>&1; echo "exit $?" >> $O/${TAG}_mgpu_check_g$NG.log ); grep -v "^W\|^\[W\|warn" $O/${TAG}_mgpu_check_g$NG.log | tail -22
+( [ "$SKIPCHECK" = "1" ] || timeout 300 python -m pytest tests/test_multi_gpu.py tests/test_gpu_local_group.py -m gpu -q -p timeout --timeout 250 > $O/${TAG}_pytest_mgpu.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest_mgpu.log ); tail -4 $O/${TAG}_pytest_mgpu.log
 for OV in 1 0; do
   ( timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $NG --steps $STEPS --warmup 1 --no-cpu-baseline --overlap $OV > $O/${TAG}_bench_n1500_g${NG}_ov$OV.json 2> $O/${TAG}_bench_n1500_g${NG}_ov$OV.err; echo "exit $?" >> $O/${TAG}_bench_n1500_g${NG}_ov$OV.err )
   python - <<PY

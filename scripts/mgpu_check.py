@@ -76,8 +76,9 @@ def species_pairs_across_ranks(rank, world, local, dev):
 
 def collective_download(T, rank, world, local):
     """lowdin_it_transform on the communicator with a STORED tensor (every rank is pushed the whole list and keeps the rows it
-    owns), per-rank downloads, merged by window-pair segments on rank 0 into ONE moint.dat: byte-identical to the file a single
-    GPU writes (TransformIntegralsE.f90:1242-1268 record order)."""
+    owns), per-rank downloads, merged by window-pair segments on rank 0 into ONE moint.dat: the same entries in the same order as
+    the file a single GPU writes (TransformIntegralsE.f90:1242-1268 record order), values equal to rounding (the ranks' GEMM batches
+    have other shapes than the single GPU's, so the last bit may differ; byte identity is reported, not required)."""
     import tempfile
     n, occ, S = 17, 5, 64
     packed = O.hash_packed_intra(808, n)

@@ -21,7 +21,7 @@ def _close(Ts):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("G,logB,overlap", [(2, 5, 1), (3, 0, 1), (4, 1, 1), (2, 2, 0), (3, 1, 0)])
+@pytest.mark.parametrize("G,logB,overlap", [(2, 5, 2), (3, 0, 2), (4, 1, 1), (2, 2, 0), (3, 1, 0)])
 def test_local_group_intra_mp2_matches_oracle(O, G, logB, overlap):
     n, occ, seed = 24, 6, 31337
     packed = O.hash_packed_intra(seed, n)
@@ -35,7 +35,7 @@ def test_local_group_intra_mp2_matches_oracle(O, G, logB, overlap):
         for cols, qb in ((0, 0), (60, 4), (1, 2), (200, 3)):
             def work(r, T):
                 T.set_option(T.OPT_SLAB_BLOCK_LOG, logB)
-                T.set_option(T.OPT_OVERLAP_EXCHANGE, overlap)     # exchange of chunk c under the first half of chunk c + 1, or on one stream
+                T.set_option(T.OPT_OVERLAP_EXCHANGE, overlap)     # exchange of chunk c under the first half of chunk c + 1 (2 = always, 1 = when chunks are wide), or on one stream
                 T.set_species(0, Cm)
                 T.set_generator(0, 0, seed)
                 T.set_option(T.OPT_CHUNK_COLS, cols)
