@@ -604,6 +604,10 @@ def main():
     # stay a pure function of the canonical index evaluated where they are consumed.
     # the same passes as the timed region above, at most one whole transform (npass passes)
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, npass))
+    if e2e_steps:
+        # the sink's pinned two-slot ring, allocated once, outside the timed region (like `pinned` below); a block holds at least the
+        # pairs of one occupied orbital: (N-O)^2 O doubles
+        T.set_option(T.OPT_SINK_BLOCK_BYTES, max(256 << 20, (n - occ) ** 2 * occ * 8))
     pinned = torch.from_numpy(np.ascontiguousarray(Cm.T)).pin_memory()  # column-major C(mu,p) == row-major C^T
     Cpin = pinned.numpy().T
     barrier()

@@ -216,13 +216,24 @@ int load_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_h
   char name[256];
   if (lowdin_host_ints_filename(0, a, b, name, &swapped)) return 1;
   if (lowdin_it_ao_begin(h, 0, slot_b, swapped)) return hfail(lowdin_it_last_error(h));
+  // every per-thread stream file as RAW bytes, up to 64 MiB of whole stacks per call: the device decodes the blocks
+  // `pp, qq, rr, ss, shellIntegrals` (terminator, index check, scatter: TransformIntegralsC.f90:258-296)
+  const size_t S = (size_t)ctl->integral_stack_size, block = 24 * S;
+  const size_t per_read = std::max<size_t>(1, ((size_t)64 << 20) / block);
+  std::vector<unsigned char> raw(per_read * block);
   for (int tid = 0; tid < ctl->nfiles; ++tid) {
     if (lowdin_host_ints_filename(tid, a, b, name, &swapped)) return 1;
-    int rc = for_each_stack(join(ctl->scratch_dir, name), ctl->integral_stack_size,
-                            [&](const int32_t *p, const int32_t *q, const int32_t *r, const int32_t *s, const double *v, int n) {
-                              return lowdin_it_ao_push_stacks(h, p, q, r, s, v, n) ? hfail(lowdin_it_last_error(h)) : 0;
-                            });
-    if (rc) return rc;
+    const std::string path = join(ctl->scratch_dir, name);
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return hfail("cannot open " + path);
+    for (;;) {
+      const size_t got = fread(raw.data(), 1, raw.size(), f);
+      if (got == 0) break;
+      if (got % block) { fclose(f); return hfail("truncated stack in " + path); }  // the reference trusts filesize/24/S
+      if (lowdin_it_ao_push_blocks(h, raw.data(), (int64_t)(got / block), (int)S)) { fclose(f); return hfail(lowdin_it_last_error(h)); }
+      if (got < raw.size()) break;
+    }
+    fclose(f);
   }
   if (lowdin_it_ao_end(h)) return hfail(lowdin_it_last_error(h));
   return 0;

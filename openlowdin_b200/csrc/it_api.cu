@@ -161,6 +161,7 @@ struct lowdin_it_ctx {
   int slab_logB = 5;                         // block-cyclic distribution of the first half's slabs: blocks of 2^slab_logB slabs (it_kernels.cuh, slab_owner)
   void *sink_host[2] = {nullptr, nullptr};   // pinned host ring of the dense-block sink (lowdin_it_transform_stream_sink)
   size_t sink_host_cap = 0;
+  size_t sink_group_bytes = (size_t)256 << 20;  // size of one dense result block handed to the sink (LOWDIN_IT_OPT_SINK_BLOCK_BYTES)
   cudaEvent_t ev_q4[2] = {}, ev_d2h[2] = {};
   DevBuf Hx, H2x, coltabx;                   // second set of chunk buffers: the exchange of chunk c overlaps the first half of chunk c + 1
   cudaStream_t comm_stream = nullptr;
@@ -955,7 +956,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     out_need = std::max(out_need, (double)pl.max_slots_per_f * per_out * 8.0);
     const bool sink_mode = (cons.mode == 1 && cons.sink != nullptr);
     // a host sink double-buffers its (smaller) groups: two groups of max(workspace, one f-block) must fit
-    const double out_reserve = sink_mode ? 2.0 * std::min(out_need, std::max((double)h->workspace_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
+    const double out_reserve = sink_mode ? 2.0 * std::min(out_need, std::max((double)h->sink_group_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
     double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->OUT.cap +
                            (double)h->X.cap + (double)h->T1t.cap) -
                    std::max(out_need, out_reserve) - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
@@ -1096,9 +1097,9 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     if (nmine > 0) {
       const int fr_lo = (int)((int64_t)nfb * h->rank / G), fr_hi = (int)((int64_t)nfb * (h->rank + 1) / G);
       const bool sinking = (cons.mode == 1 && cons.sink != nullptr);
-      // with a host sink the groups are smaller (one workspace, 1 GiB: finer pipelining of Q4, device-to-host copy and the host's consumer) and
+      // with a host sink the groups are smaller (256 MiB by default: finer pipelining of Q4, device-to-host copy and the host's consumer) and
       // OUT is double-buffered: the copy of group g overlaps the fourth quarter of group g + 1
-      const double group_bytes = sinking ? std::min(out_need, std::max((double)h->workspace_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
+      const double group_bytes = sinking ? std::min(out_need, std::max((double)h->sink_group_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
       const int64_t out_slots_cap = download ? nmine : std::max<int64_t>(pl.max_slots_per_f, (int64_t)(group_bytes / (per_out * 8.0)));
       const size_t out_elems = std::max<size_t>((size_t)out_slots_cap * per_out, 1);
       CK(h->OUT.ensure(out_elems * (sinking ? 2 : 1) * sizeof(double)));
@@ -1778,6 +1779,20 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->slab_logB = (int)value; return 0;
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_SINK_BLOCK_BYTES: {
+      // block size of the host sink; the pinned two-slot ring is allocated HERE (page-locking gigabytes takes seconds when eight
+      // processes of a box do it at once: a caller does it once, outside its timed region)
+      if (value < (1 << 12)) return fail(h, "sink block too small");
+      CK(cudaSetDevice(h->device));
+      h->sink_group_bytes = (size_t)value;
+      if (h->sink_host_cap < (size_t)value) {
+        for (int i = 0; i < 2; ++i) { if (h->sink_host[i]) cudaFreeHost(h->sink_host[i]); h->sink_host[i] = nullptr; }
+        h->sink_host_cap = 0;
+        for (int i = 0; i < 2; ++i) CK(cudaHostAlloc(&h->sink_host[i], (size_t)value, cudaHostAllocDefault));
+        h->sink_host_cap = (size_t)value;
+      }
+      return 0;
+    }
     case LOWDIN_IT_OPT_OVERLAP_EXCHANGE:
       if (value < 0 || value > 2) return fail(h, "overlap option must be 0, 1 or 2");
       h->overlap_exchange = (int)value; return 0;

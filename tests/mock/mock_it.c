@@ -95,6 +95,17 @@ int lowdin_it_ao_push_stacks(lowdin_it_handle h, const int32_t *p, const int32_t
   return 0;
 }
 
+int lowdin_it_ao_push_blocks(lowdin_it_handle h, const void *blocks, int64_t nblocks, int S) {
+  const unsigned char *raw = (const unsigned char *)blocks;
+  for (int64_t t = 0; t < nblocks; ++t) {
+    const int32_t *p = (const int32_t *)(raw + (size_t)t * 24 * S);
+    int rc = lowdin_it_ao_push_stacks(h, p, p + S, p + 2 * S, p + 3 * S, (const double *)(p + 4 * S), S);
+    if (rc) return rc;
+    for (int i = 0; i < S; ++i) if (p[i] == -1) return 0; /* the terminator ends this call's stream */
+  }
+  return 0;
+}
+
 int lowdin_it_ao_end(lowdin_it_handle h) {
   if (!h || h->up_a < 0) return mfail(h, "ao_end without ao_begin");
   h->up_a = h->up_b = -1;

@@ -391,10 +391,10 @@ def test_stream_sink_delivers_every_mo_integral(O, T, qb):
                         x = vals[t, ks, kf]
                         if abs(x) > 1e-10:
                             got[row, pid(r - 1, s - 1, n2)] = x
-        T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 12)
+        T.set_option(T.OPT_SINK_BLOCK_BYTES, 1 << 12)      # one first-contracted index per block: several blocks, both ring slots reused
         try:
             sums = T.transform_stream_sink(a, b, win, ol.CONV_E, sink, occ_batch=qb)
         finally:
-            T.set_option(T.OPT_WORKSPACE_BYTES, 1 << 30)
+            T.set_option(T.OPT_SINK_BLOCK_BYTES, 256 << 20)
         assert nblocks[0] >= 3 and sums[0] == len(v)
         assert np.abs(got - ref).max() <= 1e-12
