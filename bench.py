@@ -665,8 +665,8 @@ def main():
         gemm_cats = ("q1", "q2", "q3", "q4")
         dom = max(stats, key=lambda c: stats[c]["ms"])
         st = stats[dom]
-        kname = {"q1": "q1_gen_kernel (slab generation + first quarter)", "q2": "dgemm_tn_kernel<EpiScatterH> (second quarter)",
-                 "q3": "dgemm_tn_kernel<EpiAccT> (third quarter, chunked)", "q4": "dgemm_tn_kernel<EpiOut> (fourth quarter)",
+        kname = {"q1": "q1_gen_ws5_kernel (slab generation + first quarter)", "q2": "dgemm_tma_kernel<EpiScatterH> (second quarter)",
+                 "q3": "dgemm_tma_kernel<EpiAccT> (third quarter, chunked)", "q4": "dgemm_tma_kernel<EpiOut> (fourth quarter)",
                  "expand1": "expand_block_kernel (first half)", "expand2": "expand_block_kernel (second half)",
                  "consume": "reduce_block_kernel", "exchange": "NCCL all-to-all"}.get(dom, dom)
         traffic = None

@@ -119,6 +119,12 @@ int lowdin_host_atomic_to_molecular_one_species(lowdin_it_handle h, const lowdin
                                                 int64_t *nonzero);
 int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
                                                 const lowdin_host_species *b, int64_t *nonzero);
+/* The same for a ONE-PROCESS host driving several GPUs (the reference's transformation program is one process): `handles` are
+ * the members of an in-process group (lowdin_it_comm_init_local).  The .ints streams are read once and pushed to every handle
+ * (each keeps the rows of the AO tensor it owns), the transform is collective, ONE moint.dat is written with the entries in the
+ * single-GPU order.  b == NULL: one species. */
+int lowdin_host_group_atomic_to_molecular(lowdin_it_handle *handles, int nhandles, const lowdin_host_control *ctl,
+                                          const lowdin_host_species *a, const lowdin_host_species *b, int64_t *nonzero);
 
 /* ---- the program's species loop (IntegralTransformation.f90:171-355) and its division among devices ------------
  * One entry per transformer call the reference program would make, in program order: species i (skipped under PT2 when

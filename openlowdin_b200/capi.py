@@ -275,7 +275,7 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
-    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES = 8, 9, 10, 11, 12, 13, 14, 15, 16
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES, OPT_GEMM_TALL = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT, DEFAULT_FRAG_PERM = 5, 2, 1  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):
@@ -420,7 +420,7 @@ HOST_SYMBOLS = [
     "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
     "lowdin_host_atomic_to_molecular_two_species", "lowdin_host_plan_program", "lowdin_host_run_program",
     "lowdin_host_write_moint_d_intra", "lowdin_host_write_moint_d_inter", "lowdin_host_wfn_read", "lowdin_host_wfn_append",
-    "lowdin_host_wfn_load_species",
+    "lowdin_host_wfn_load_species", "lowdin_host_group_atomic_to_molecular",
 ]
 
 
@@ -486,6 +486,7 @@ def _host():
     L.lowdin_host_write_moint_pairs.argtypes = [C.c_char_p, C.c_int, _i64p, _i64p, _f64p, C.c_int64]
     L.lowdin_host_atomic_to_molecular_one_species.argtypes = [C.c_void_p, PC, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
+    L.lowdin_host_group_atomic_to_molecular.argtypes = [C.POINTER(C.c_void_p), C.c_int, PC, PS, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_plan_program.argtypes = [PC, PS, C.c_int, C.c_int, C.POINTER(HostTask), C.c_int, C.POINTER(C.c_int)]
     L.lowdin_host_run_program.argtypes = [C.c_void_p, PC, PS, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L.lowdin_host_write_moint_d_intra.argtypes = [C.c_char_p, C.c_int, _f64p, C.POINTER(C.c_int64)]
@@ -556,6 +557,15 @@ def host_transform_one_species(T, ctl, a):
 def host_transform_two_species(T, ctl, a, b):
     n = C.c_int64()
     _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h if T is not None else None, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
+    return n.value
+
+
+def host_group_transform(transformers, ctl, a, b=None):
+    """File to file on an in-process group of GPUs: one moint.dat, entries in the single-GPU order."""
+    n = C.c_int64()
+    arr = (C.c_void_p * len(transformers))(*[t.h for t in transformers])
+    _hck(_host().lowdin_host_group_atomic_to_molecular(arr, len(transformers), C.byref(ctl), C.byref(a), C.byref(b) if b is not None else None,
+                                                       C.byref(n)))
     return n.value
 
 

@@ -210,12 +210,15 @@ int write_record(FILE *f, const void *a, size_t na, const void *b, size_t nb, co
   return fwrite(&len, 4, 1, f) != 1;
 }
 
-int load_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b) {
+// hs[0..nh): one handle, or the handles of an in-process group (lowdin_it_comm_init_local): every handle is pushed every byte and
+// keeps the rows of the AO tensor it owns
+int load_ints(lowdin_it_handle *hs, int nh, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b) {
   const int slot_b = b ? 1 : 0;
   int swapped = 0;
   char name[256];
   if (lowdin_host_ints_filename(0, a, b, name, &swapped)) return 1;
-  if (lowdin_it_ao_begin(h, 0, slot_b, swapped)) return hfail(lowdin_it_last_error(h));
+  for (int d = 0; d < nh; ++d)
+    if (lowdin_it_ao_begin(hs[d], 0, slot_b, swapped)) return hfail(lowdin_it_last_error(hs[d]));
   // every per-thread stream file as RAW bytes, up to 64 MiB of whole stacks per call: the device decodes the blocks
   // `pp, qq, rr, ss, shellIntegrals` (terminator, index check, scatter: TransformIntegralsC.f90:258-296)
   const size_t S = (size_t)ctl->integral_stack_size, block = 24 * S;
@@ -230,12 +233,14 @@ int load_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_h
       const size_t got = fread(raw.data(), 1, raw.size(), f);
       if (got == 0) break;
       if (got % block) { fclose(f); return hfail("truncated stack in " + path); }  // the reference trusts filesize/24/S
-      if (lowdin_it_ao_push_blocks(h, raw.data(), (int64_t)(got / block), (int)S)) { fclose(f); return hfail(lowdin_it_last_error(h)); }
+      for (int d = 0; d < nh; ++d)
+        if (lowdin_it_ao_push_blocks(hs[d], raw.data(), (int64_t)(got / block), (int)S)) { fclose(f); return hfail(lowdin_it_last_error(hs[d])); }
       if (got < raw.size()) break;
     }
     fclose(f);
   }
-  if (lowdin_it_ao_end(h)) return hfail(lowdin_it_last_error(h));
+  for (int d = 0; d < nh; ++d)
+    if (lowdin_it_ao_end(hs[d])) return hfail(lowdin_it_last_error(hs[d]));
   return 0;
 }
 
@@ -283,11 +288,12 @@ int run_and_write_d(const lowdin_host_control *ctl, const lowdin_host_species *a
   return 0;
 }
 
-int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b,
+int run_and_write(lowdin_it_handle *hs, int nh, const lowdin_host_control *ctl, const lowdin_host_species *a, const lowdin_host_species *b,
                   int64_t *nonzero) {
   if (check_ctl(ctl)) return 1;
   if (ctl->method == 'D') return run_and_write_d(ctl, a, b, nonzero);
-  if (!h || !a || !a->coeff) return hfail("null handle / species");
+  if (!hs || nh < 1 || !hs[0] || !a || !a->coeff) return hfail("null handle / species");
+  lowdin_it_handle h = hs[0];
   int win[8], symmetric = 0;
   if (lowdin_host_windows(ctl, a, b, win, &symmetric)) return 1;
   if (ctl->verbose) {  // the "Transformation boundaries" table of C.f90:1614-1620
@@ -295,13 +301,16 @@ int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowd
     const char *nm = "pqrs";
     for (int w = 0; w < 4; ++w) printf("                   %c%6d%6d\n", nm[w], win[2 * w], win[2 * w + 1]);
   }
-  if (lowdin_it_set_species(h, 0, a->nao, a->coeff, a->ldc, a->ncols)) return hfail(lowdin_it_last_error(h));
-  if (b && lowdin_it_set_species(h, 1, b->nao, b->coeff, b->ldc, b->ncols)) return hfail(lowdin_it_last_error(h));
-  if (load_ints(h, ctl, a, b)) return 1;
+  for (int d = 0; d < nh; ++d) {
+    if (lowdin_it_set_species(hs[d], 0, a->nao, a->coeff, a->ldc, a->ncols)) return hfail(lowdin_it_last_error(hs[d]));
+    if (b && lowdin_it_set_species(hs[d], 1, b->nao, b->coeff, b->ldc, b->ncols)) return hfail(lowdin_it_last_error(hs[d]));
+  }
+  if (load_ints(hs, nh, ctl, a, b)) return 1;
   const int conv = (ctl->method == 'E') ? LOWDIN_IT_CONV_E : LOWDIN_IT_CONV_C;
-  if (lowdin_it_transform(h, 0, b ? 1 : 0, win, conv, symmetric, 1e-10)) return hfail(lowdin_it_last_error(h));
+  // one handle: lowdin_it_transform; a group: the collective transform on every handle at once, merged downloads below
+  if (lowdin_it_group_transform(hs, nh, 0, b ? 1 : 0, win, conv, symmetric, 1e-10)) return hfail(lowdin_it_last_error(h));
   int64_t n = 0;
-  if (lowdin_it_result_count(h, &n)) return hfail(lowdin_it_last_error(h));
+  if (lowdin_it_group_result_count(hs, nh, &n)) return hfail(lowdin_it_last_error(h));
   const std::string prefix = b ? trimmed(a->name, 32) + "." + trimmed(b->name, 32) : trimmed(a->name, 32);  // C.f90:192, :788
   const std::string path = join(ctl->scratch_dir, prefix + "moint.dat");
   const size_t m = (size_t)std::max<int64_t>(n, 1);
@@ -309,11 +318,11 @@ int run_and_write(lowdin_it_handle h, const lowdin_host_control *ctl, const lowd
   int rc;
   if (conv == LOWDIN_IT_CONV_E) {
     std::vector<int64_t> ij(m), kl(m);
-    if (lowdin_it_download_pairs(h, ij.data(), kl.data(), v.data())) return hfail(lowdin_it_last_error(h));
+    if (lowdin_it_group_download_pairs(hs, nh, ij.data(), kl.data(), v.data())) return hfail(lowdin_it_last_error(h));
     rc = lowdin_host_write_moint_pairs(path.c_str(), ctl->integral_stack_size, ij.data(), kl.data(), v.data(), n);
   } else {
     std::vector<int32_t> p(m), q(m), r(m), s(m);
-    if (lowdin_it_download_quads(h, p.data(), q.data(), r.data(), s.data(), v.data())) return hfail(lowdin_it_last_error(h));
+    if (lowdin_it_group_download_quads(hs, nh, p.data(), q.data(), r.data(), s.data(), v.data())) return hfail(lowdin_it_last_error(h));
     rc = lowdin_host_write_moint_quads(path.c_str(), ctl->integral_stack_size, p.data(), q.data(), r.data(), s.data(), v.data(), n);
   }
   if (rc) return rc;
@@ -525,13 +534,21 @@ int lowdin_host_write_moint_pairs(const char *path, int S, const int64_t *ij, co
 
 int lowdin_host_atomic_to_molecular_one_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
                                                 int64_t *nonzero) {
-  return run_and_write(h, ctl, a, nullptr, nonzero);
+  return run_and_write(&h, 1, ctl, a, nullptr, nonzero);
 }
 
 int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
                                                 const lowdin_host_species *b, int64_t *nonzero) {
   if (!b) return hfail("second species missing");
-  return run_and_write(h, ctl, a, b, nonzero);
+  return run_and_write(&h, 1, ctl, a, b, nonzero);
+}
+
+// The same calls for a ONE-PROCESS host driving several GPUs: `handles` are the members of an in-process group
+// (lowdin_it_comm_init_local).  The .ints streams are read once and pushed to every handle (each keeps the rows of the AO tensor
+// it owns), the transform is collective, and ONE moint.dat is written with the entries in the single-GPU order.
+int lowdin_host_group_atomic_to_molecular(lowdin_it_handle *handles, int nhandles, const lowdin_host_control *ctl,
+                                          const lowdin_host_species *a, const lowdin_host_species *b, int64_t *nonzero) {
+  return run_and_write(handles, nhandles, ctl, a, b, nonzero);
 }
 
 // ---- transformer-D record layout ------------------------------------------------------------------------------
@@ -699,7 +716,7 @@ int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, 
       else printf("\n Integrals transformation for: %s\n\n", trimmed(a->name, 32).c_str());
     }
     int64_t n = 0;
-    if (run_and_write(h, ctl, a, b, &n)) return 1;
+    if (run_and_write(&h, 1, ctl, a, b, &n)) return 1;
     total += n;
     ++calls;
   }

@@ -174,6 +174,7 @@ struct lowdin_it_ctx {
   int q1_variant = 5;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
+  int gemm_tall = 0;                         // TMA GEMM: 192 x 64 tiles when the rows are a multiple of 192 plus a few (probe; LOWDIN_IT_OPT_GEMM_TALL)
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
   int stored_fused = 1;                      // stored AO tensors: 1 = fused unpack + first quarter (q1_load_ws5_kernel), 0 = expansion kernel + DMMA GEMM
   int q1_dbg = 0;                            // probe switches of the warp-specialised first quarter (Q1WsArgs::dbg)
@@ -318,9 +319,11 @@ cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi
 }
 
 template <class Epi>
-cudaError_t launch_gemm_one(lowdin_it_handle h, const GemmArgs &g, const Epi &epi, bool tma) {
+cudaError_t launch_gemm_one(lowdin_it_handle h, const GemmArgs &g, const Epi &epi, bool tma, bool tall = false) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   const int n = g.N;
+  if constexpr (Epi::kSplitRowTail)
+    if (tall && tma) return launch_gemm_tma_cfg<192, 64, 4, 2>(h, g, epi);  // 48 x 32 warp tiles: 10 fragment loads per 48 DMMAs
 #define LOWDIN_GEMM_CFG(BM, BN, WM, WN) (tma ? launch_gemm_tma_cfg<BM, BN, WM, WN>(h, g, epi) : launch_gemm_cfg<BM, BN, WM, WN>(h, g, epi))
   if (n <= 8) return LOWDIN_GEMM_CFG(256, 8, 8, 1);
   if (n <= 16) return LOWDIN_GEMM_CFG(256, 16, 8, 1);
@@ -347,6 +350,17 @@ cudaError_t launch_gemm(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
     // row tail (<= 80 rows) runs as a second launch with the operands exchanged, so that the tail becomes the N
     // dimension and gets an 8..80-wide tile.  Only when the tail launch itself has >= 3 waves of 128-row tiles: measured
     // on B200 (profiles/r01f_variant_probe.log) 1350 x 89440 x 1500 gains 1.7 %, 1350 x 8400 x 1500 would lose 11 %.
+    // Rows that are nearly a multiple of 192 (1350 virtuals = 7 x 192 + 6): 192 x 64 tiles leave a tail of a few rows instead of
+    // 70 (LOWDIN_IT_OPT_GEMM_TALL).
+    const int tail192 = g.M % 192, main192 = g.M - tail192;
+    if (tma && h->gemm_tall && ceil_div(g.N, 64) >= 3 * (int64_t)h->num_sms && main192 >= 192 && tail192 <= 16 && (g.M % 128) > 16) {
+      GemmArgs gm = g;
+      gm.M = main192;
+      cudaError_t e = launch_gemm_one(h, gm, epi, true, true);
+      if (e != cudaSuccess || tail192 == 0) return e;
+      GemmArgs gt{g.B, g.A + (int64_t)main192 * g.lda, g.N, tail192, g.K, g.ldb, g.lda, 0, 0};
+      return launch_gemm_one(h, gt, EpiSwapped<Epi>{epi, main192}, tma_eligible(gt));
+    }
     const int tail = g.M % 128, main = g.M - tail;
     if (tma && h->split_row_tail && ceil_div(g.N, 128) >= 3 * (int64_t)h->num_sms && main >= 128 && tail > 0 && tail <= 80) {
       GemmArgs gm = g;
@@ -1779,6 +1793,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->slab_logB = (int)value; return 0;
     case LOWDIN_IT_OPT_AO_LIST:
       h->ao_list = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_GEMM_TALL:
+      h->gemm_tall = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_SINK_BLOCK_BYTES: {
       // block size of the host sink; the pinned two-slot ring is allocated HERE (page-locking gigabytes takes seconds when eight
       // processes of a box do it at once: a caller does it once, outside its timed region)

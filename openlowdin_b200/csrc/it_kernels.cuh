@@ -456,6 +456,7 @@ struct EpiOut {
 // (n + row_off, m) of the original problem.  Used for the row tail of a tall-skinny-by-wide product (see launch_gemm).
 template <class Epi>
 struct EpiSwapped {
+  static constexpr bool kSplitRowTail = false;
   static constexpr bool kRowCoalesced = false;
   Epi epi; int row_off;
   __device__ __forceinline__ void operator()(int z, int m, int n, double v) const { epi(z, n + row_off, m, v); }

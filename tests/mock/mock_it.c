@@ -157,6 +157,16 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
   return 0;
 }
 
+/* group calls: the mock is one handle */
+int lowdin_it_group_transform(lowdin_it_handle *hs, int n, int a, int b, const int win[8], int conv, int symmetric, double tol) {
+  (void)n; return lowdin_it_transform(hs[0], a, b, win, conv, symmetric, tol);
+}
+int lowdin_it_group_result_count(lowdin_it_handle *hs, int n, int64_t *count) { (void)n; return lowdin_it_result_count(hs[0], count); }
+int lowdin_it_group_download_pairs(lowdin_it_handle *hs, int n, int64_t *ij, int64_t *kl, double *v) { (void)n; return lowdin_it_download_pairs(hs[0], ij, kl, v); }
+int lowdin_it_group_download_quads(lowdin_it_handle *hs, int n, int32_t *p, int32_t *q, int32_t *r, int32_t *s, double *v) {
+  (void)n; return lowdin_it_download_quads(hs[0], p, q, r, s, v);
+}
+
 int lowdin_it_transform_all(const double *coeff, double *ints, int nao) { orc_transform_d_intra(coeff, ints, nao); return 0; }
 int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, double *ints, int nao, int onao) {
   orc_transform_d_inter(coeff, ocoeff, ints, nao, onao);

@@ -190,3 +190,44 @@ def test_upload_before_group_is_rejected(O):
             capi.group_transform(Ts, 0, 0, [1, n] * 4, ol.CONV_E)
     finally:
         _close(Ts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["C", "E"])
+def test_host_mirror_group_file_to_file(O, T, tmp_path, method):
+    """The reference host's call on a group of 3 GPUs (lowdin_host_group_atomic_to_molecular): the .ints streams are read once and
+    pushed to every handle, ONE moint.dat comes out -- the same records as the single-handle call writes, and the oracle's integrals."""
+    import shutil
+    n, occ, S, nfiles = 13, 4, 64, 2
+    packed = O.hash_packed_intra(61, n)
+    Cm = O.random_orthonormal(n, n)
+    lst = O.canonical_list_intra(packed, n)
+    for t in range(nfiles):
+        capi.host_write_ints_file(str(tmp_path / f"{t}E-.ints"), S, *[x[t::nfiles] for x in lst])
+    ctl = capi.host_control(method, "MP2", stack=S, nfiles=nfiles, scratch_dir=str(tmp_path))
+    sp = capi.host_species("E-", 1, n, occ, coeff=Cm)
+    cnt1 = capi.host_transform_one_species(T, ctl, sp)
+    shutil.copy(tmp_path / "E-moint.dat", tmp_path / "one.dat")
+    Ts = _group(3)
+    try:
+        for t in Ts:
+            t.set_option(t.OPT_SLAB_BLOCK_LOG, 1)
+            t.set_option(t.OPT_CHUNK_COLS, 25)
+        cnt = capi.host_group_transform(Ts, ctl, sp)
+    finally:
+        _close(Ts)
+    assert cnt == cnt1 > 0
+    a, b = open(tmp_path / "one.dat", "rb").read(), open(tmp_path / "E-moint.dat", "rb").read()
+    assert len(a) == len(b)
+    if method == "E":      # records: int64 ij[S], kl[S], float64 v[S] between 4-byte markers
+        rec = 4 + 24 * S + 4
+        for o in range(0, len(a), rec):
+            assert a[o:o + 4 + 16 * S] == b[o:o + 4 + 16 * S]                       # same pair ids in the same order
+            va, vb = np.frombuffer(a, np.float64, S, o + 4 + 16 * S), np.frombuffer(b, np.float64, S, o + 4 + 16 * S)
+            assert np.abs(va - vb).max() <= 1e-13
+    else:
+        rec = 4 + 24 * S + 4
+        for o in range(0, len(a), rec):
+            assert a[o:o + 4 + 16 * S] == b[o:o + 4 + 16 * S]                       # same p,q,r,s in the same order
+            va, vb = np.frombuffer(a, np.float64, S, o + 4 + 16 * S), np.frombuffer(b, np.float64, S, o + 4 + 16 * S)
+            assert np.abs(va - vb).max() <= 1e-13

@@ -396,5 +396,5 @@ def test_stream_sink_delivers_every_mo_integral(O, T, qb):
             sums = T.transform_stream_sink(a, b, win, ol.CONV_E, sink, occ_batch=qb)
         finally:
             T.set_option(T.OPT_SINK_BLOCK_BYTES, 256 << 20)
-        assert nblocks[0] >= 3 and sums[0] == len(v)
+        assert nblocks[0] >= (3 if a == b else 1) and sums[0] == len(v)     # the inter case is smaller than one 4 KiB block
         assert np.abs(got - ref).max() <= 1e-12

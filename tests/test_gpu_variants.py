@@ -36,6 +36,19 @@ def test_tma_gemm_vs_numpy(tma, m, n, k):
     assert np.abs(got - ref).max() <= 4e-16 * k + 1e-14
 
 
+@pytest.mark.parametrize("m,n,k", [(1350, 30000, 40), (198, 29000, 33), (390, 28500, 17), (1350, 700, 96)])
+def test_tall_tile_gemm_vs_numpy(T, m, n, k):
+    """192 x 64 tiles (LOWDIN_IT_OPT_GEMM_TALL): rows = multiple of 192 plus a few, >= 3 waves of column tiles; the last shape does not qualify."""
+    rng = np.random.default_rng(m + n)
+    A, B = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (n, k))
+    T.set_option(T.OPT_GEMM_TALL, 1)
+    try:
+        got = T.debug_gemm(A, B)
+    finally:
+        T.set_option(T.OPT_GEMM_TALL, 0)
+    assert np.abs(got - A @ B.T).max() <= 4e-16 * k + 1e-14
+
+
 def test_tma_gemm_matches_cp_async_variant(T):
     rng = np.random.default_rng(5)
     A, B = rng.uniform(-1, 1, (3000, 777)), rng.uniform(-1, 1, (290, 777))
