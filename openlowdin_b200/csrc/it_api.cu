@@ -971,6 +971,23 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     const bool sink_mode = (cons.mode == 1 && cons.sink != nullptr);
     // a host sink double-buffers its (smaller) groups: two groups of max(workspace, one f-block) must fit
     const double out_reserve = sink_mode ? 2.0 * std::min(out_need, std::max((double)h->sink_group_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
+    {
+      // OUT is sized HERE, before the chunk buffers take what is left: a pass with a host sink needs two groups where the same pass
+      // without one needed a single group, and the chunk buffers of that earlier pass may hold all the free memory (N_bf = 2000: one
+      // f-block of results is 5.2 GB)
+      const double gb = sink_mode ? std::min(out_need, std::max((double)h->sink_group_bytes, (double)pl.max_slots_per_f * per_out * 8.0)) : out_need;
+      const int64_t cap_slots = download ? std::max(nmine, 1) : std::max<int64_t>(pl.max_slots_per_f, (int64_t)(gb / (per_out * 8.0)));
+      const size_t need = std::max<size_t>((size_t)cap_slots * per_out, 1) * (sink_mode ? 2 : 1) * sizeof(double);
+      if (need > h->OUT.cap) {
+        if (free_b + h->OUT.cap < need + ((size_t)1 << 29)) {
+          CK(cudaStreamSynchronize(h->stream));
+          if (h->comm_stream) CK(cudaStreamSynchronize(h->comm_stream));
+          for (DevBuf *b : {&h->H, &h->H2, &h->Hx, &h->H2x, &h->X, &h->T1t}) b->release();
+        }
+        CK(h->OUT.ensure(need));
+        CK(cudaMemGetInfo(&free_b, &total_b));
+      }
+    }
     double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->OUT.cap +
                            (double)h->X.cap + (double)h->T1t.cap) -
                    std::max(out_need, out_reserve) - 2.0 * (double)h->workspace_bytes - (double)((size_t)1 << 29);
@@ -1706,7 +1723,9 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   const int G = h->nranks;
   const double spf = std::max(pl.max_slots_per_f, 1);
   const double per_out = (double)pl.h2.ns * pl.h2.nf * 8.0;
-  const double out_need = std::max(std::min(4.0e9, spf * per_out * nf), spf * per_out);
+  // results buffer: 4 GB of groups, or two f-blocks when one alone is larger (the host sink double-buffers its groups, and the same
+  // occupied batch must serve the pass with and without a sink)
+  const double out_need = std::max(std::min(4.0e9, spf * per_out * nf), std::min(2.0, (double)nf) * spf * per_out);
   const double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->T3.cap +
                                (double)h->X.cap + (double)h->T1t.cap) - 2.0 * (double)h->workspace_bytes - out_need - (double)((size_t)1 << 30);
   // per first-window value: third-quarter accumulators of its slots (own share) + a chunk of at least 8 pair rows of H

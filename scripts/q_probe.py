@@ -33,14 +33,3 @@ for kind, name in ((4, "rmw"), (5, "red")):
             print("q3", name, slots, k, "FAILED", e, flush=True)
 json.dump(out, open(f"gpurun_out/{tag}_q_probe.json", "w"), indent=1)
 
-# second / fourth quarter shape: 1350 rows x many columns, 128 x 128 tiles + 70-row tail launch vs 192 x 64 tiles + 6-row tail
-out2 = {}
-for tall in (0, 1):
-    T.set_option(T.OPT_GEMM_TALL, tall)
-    for (m, n, k) in [(1350, 89440, 1500), (1350, 28000, 1500), (900, 51200, 1000), (450, 53550, 500)]:
-        ms, _ = T.kernel_bench(1, m, n, k, iters=3)
-        tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-        out2[f"gemm_tall{tall}_{m}x{n}x{k}"] = {"ms": ms, "TFLOP/s": tf}
-        print("gemm tall", tall, m, n, k, "ms", round(ms, 3), "TF/s", round(tf, 2), flush=True)
-T.set_option(T.OPT_GEMM_TALL, 0)
-json.dump(out2, open(f"gpurun_out/{tag}_gemm_tall_probe.json", "w"), indent=1)
