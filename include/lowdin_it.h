@@ -76,6 +76,24 @@ int lowdin_it_ao_set_generator(lowdin_it_handle h, int slotA, int slotB, int kin
  * (p q|r s) = sum_k (Ca^T La^k Ca)[p,q] (Cb^T Lb^k Cb)[r,s], i.e. an O(K N^3) oracle at any N.  La: host [K][M_a] values of the
  * K symmetric matrices at the pairs (mu<=nu) in xy order; Lb likewise for species B (ignored for slotB == slotA). */
 int lowdin_it_ao_set_rankk(lowdin_it_handle h, int slotA, int slotB, int K, const double *La, const double *Lb);
+/* ---- row f4 of SURVEY.md section 8: the AO integrals evaluated on the device -----------------------------------------
+ * The basis of a species as the reference hands it to libint2, one call per shell of LibintInterface::add_shell(alpha, coeff,
+ * origin, l, nprim) (Libint2Iface.cpp:83-130): Cartesian shells (components in libint2's order: lx = l..0, ly = l-lx..0),
+ * contraction coefficients of unit-normalised primitives (libint2::Shell::renorm), every function divided by the square root of
+ * its self overlap (`norma`).  first_prim indexes `exponents` / `coefficients`.  l <= 3.  The species must have been set
+ * (lowdin_it_set_species) with nao = the number of Cartesian functions of the shells. */
+typedef struct { int l, nprim, first_prim; double origin[3]; } lowdin_it_shell;
+int lowdin_it_set_basis(lowdin_it_handle h, int slot, int nshells, const lowdin_it_shell *shells, const double *exponents,
+                        const double *coefficients);
+int lowdin_it_basis_norma(lowdin_it_handle h, int slot, double *norma /* [nao] */);
+/* (p q|r s) of the pair (slotA, slotB) evaluated on the device into the stored AO tensor (packed / rectangular / the rows this rank
+ * owns on a communicator), as if the `.ints` streams of LibintInterface::compute_2body_disk (Libint2Iface.cpp:219-416; slotA ==
+ * slotB) or ::compute_coupling_disk (:930-1110) had been uploaded: raw values <= 1e-10 are dropped (:369, :1053), the others scaled
+ * by norma.  The reference's density-weighted Schwarz screening (:300-330) is not applied: every integral is evaluated. */
+int lowdin_it_ao_compute(lowdin_it_handle h, int slotA, int slotB);
+/* The stored AO tensor back on the host (one rank): packed M(M+1)/2 doubles (intra, row lo holds hi = lo..M-1) or [M_b][M_a]. */
+int lowdin_it_ao_download(lowdin_it_handle h, int slotA, int slotB, double *out, int64_t capacity);
+
 /* Turn a generated AO set into a STORED one on the device (packed M(M+1)/2 / rectangular M_b x M_a), as if its whole
  * list had been uploaded: the stored-AO kernels at sizes whose list no host could hold (bench leg, tests). */
 int lowdin_it_ao_materialize(lowdin_it_handle h, int slotA, int slotB);

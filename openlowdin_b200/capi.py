@@ -26,12 +26,29 @@ ABI_SYMBOLS = [
     "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
     "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter", "lowdin_it_result_segments", "lowdin_it_group_transform",
     "lowdin_it_group_result_count", "lowdin_it_group_download_pairs", "lowdin_it_group_download_quads",
-    "lowdin_it_transform_stream_sink",
+    "lowdin_it_transform_stream_sink", "lowdin_it_set_basis", "lowdin_it_basis_norma", "lowdin_it_ao_compute", "lowdin_it_ao_download",
 ]
 
 
 class LowdinITError(RuntimeError):
     pass
+
+
+class Shell(C.Structure):
+    """lowdin_it_shell: one Cartesian shell as LibintInterface::add_shell receives it (Libint2Iface.cpp:83)."""
+    _fields_ = [("l", C.c_int), ("nprim", C.c_int), ("first_prim", C.c_int), ("origin", C.c_double * 3)]
+
+
+def pack_shells(shells):
+    """[(l, origin(3), exponents, coefficients), ...] -> (Shell array, exponents, coefficients, number of Cartesian functions)."""
+    arr = (Shell * len(shells))()
+    ex, co, nbf = [], [], 0
+    for i, (l, origin, e, c) in enumerate(shells):
+        assert len(e) == len(c)
+        arr[i] = Shell(l, len(e), len(ex), (C.c_double * 3)(*origin))
+        ex += list(e); co += list(c)
+        nbf += (l + 1) * (l + 2) // 2
+    return arr, np.array(ex, dtype=np.float64), np.array(co, dtype=np.float64), nbf
 
 
 class Block(C.Structure):
@@ -106,6 +123,10 @@ def load():
     L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
     L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
     L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_set_basis.argtypes = [H, C.c_int, C.c_int, C.POINTER(Shell), _f64p, _f64p]
+    L.lowdin_it_basis_norma.argtypes = [H, C.c_int, _f64p]
+    L.lowdin_it_ao_compute.argtypes = [H, C.c_int, C.c_int]
+    L.lowdin_it_ao_download.argtypes = [H, C.c_int, C.c_int, _f64p, C.c_int64]
     L.lowdin_it_result_segments.argtypes = [H, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
     L.lowdin_it_group_transform.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_double]
     L.lowdin_it_group_result_count.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_int64)]
@@ -181,6 +202,27 @@ class Transformer:
 
     def materialize(self, a, b):
         self._ck(self.L.lowdin_it_ao_materialize(self.h, a, b))
+
+    def set_basis(self, slot, shells):
+        """shells: [(l, origin, exponents, coefficients), ...] (see pack_shells); the species must be set with nao = number of functions."""
+        arr, ex, co, nbf = pack_shells(shells)
+        self._ck(self.L.lowdin_it_set_basis(self.h, slot, len(shells), arr, ex, co))
+        return nbf
+
+    def basis_norma(self, slot):
+        out = np.zeros(self.n[slot])
+        self._ck(self.L.lowdin_it_basis_norma(self.h, slot, out))
+        return out
+
+    def compute_ao(self, a, b):
+        """Row f4: the AO integrals of the pair evaluated on the device into the stored tensor (no .ints stream)."""
+        self._ck(self.L.lowdin_it_ao_compute(self.h, a, b))
+
+    def download_ao(self, a, b):
+        Ma, Mb = self.n[a] * (self.n[a] + 1) // 2, self.n[b] * (self.n[b] + 1) // 2
+        out = np.zeros(Ma * (Ma + 1) // 2 if a == b else Ma * Mb)
+        self._ck(self.L.lowdin_it_ao_download(self.h, a, b, out, out.size))
+        return out if a == b else out.reshape(Mb, Ma)
 
     def debug_first_quarter(self, a, b, f_first, nf, slab0, nslabs):
         out = np.zeros((nf, nslabs, self.n[a]))

@@ -8,6 +8,7 @@
 #include "it_kernels.cuh"
 #include "it_gemm_tma.cuh"
 #include "it_list.cuh"
+#include "it_eri.cuh"
 #include "../../include/lowdin_it.h"
 
 #include <dlfcn.h>
@@ -48,6 +49,9 @@ struct Species {
   int n = 0, ncols = 0;
   int64_t M = 0, ldc = 0;
   DevBuf C, Cs, pi, pj;  // Cs = C * 2^-53 (exact): B operand of the warp-specialised fused first quarter (bits_to_unscaled)
+  DevBuf bs_shells, bs_fn, bs_expo, bs_coef;  // basis of the species (lowdin_it_set_basis): shells, functions (+ norma), primitives
+  int bs_nbf = 0;
+  std::vector<double> bs_norma;
 };
 
 struct AoSet {
@@ -1363,7 +1367,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); }
+  for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); s.bs_shells.release(); s.bs_fn.release(); s.bs_expo.release(); s.bs_coef.release(); }
   for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); a.release_list(); a.seg_counts.release(); }
   DevBuf *bufs[] = {&h->st[0], &h->st[1], &h->up_state, &h->T1list, &h->Cw, &h->coltab, &h->coltabx, &h->Hx, &h->H2x, &h->seg, &h->X, &h->T1t, &h->H, &h->H2, &h->OUT, &h->T3, &h->order, &h->tab, &h->sa, &h->sb,
                     &h->ss, &h->sf, &h->blockcount, &h->blockoff, &h->sums, &h->running, &h->overflow, &h->epsA, &h->epsB, &h->dtmp, &h->agree,
@@ -1645,6 +1649,99 @@ int lowdin_it_ao_materialize(lowdin_it_handle h, int a, int b) {
   return 0;
 }
 
+// ---- row f4: the AO integrals evaluated on the device (it_eri.cuh) ---------------------------------------------
+int lowdin_it_set_basis(lowdin_it_handle h, int slot, int nshells, const lowdin_it_shell *shells, const double *exponents,
+                        const double *coefficients) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 7 || !h->sp[slot].n) return fail(h, "set_basis: species not set (lowdin_it_set_species first)");
+  if (nshells < 1 || !shells || !exponents || !coefficients) return fail(h, "set_basis: null argument");
+  CK(cudaSetDevice(h->device));
+  Species &S = h->sp[slot];
+  EriHostBasis hb;
+  if (!eri_prepare_basis(nshells, shells, exponents, coefficients, hb)) return fail(h, "set_basis: " + hb.err);
+  const std::vector<EriShell> &sh = hb.sh;
+  const std::vector<EriFunction> &fn = hb.fn;
+  const std::vector<double> &expo = hb.expo, &coef = hb.coef;
+  const int nprim = (int)expo.size();
+  S.bs_norma.clear();
+  for (const EriFunction &f : fn) S.bs_norma.push_back(f.norma);
+  if ((int)fn.size() != S.n) return fail(h, "set_basis: the shells hold " + std::to_string(fn.size()) + " Cartesian functions, the species has " + std::to_string(S.n));
+  CK(S.bs_shells.ensure(sh.size() * sizeof(EriShell)));
+  CK(S.bs_fn.ensure(fn.size() * sizeof(EriFunction)));
+  CK(S.bs_expo.ensure(nprim * sizeof(double)));
+  CK(S.bs_coef.ensure(nprim * sizeof(double)));
+  CK(cudaMemcpyAsync(S.bs_shells.p, sh.data(), sh.size() * sizeof(EriShell), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.bs_fn.p, fn.data(), fn.size() * sizeof(EriFunction), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.bs_expo.p, expo.data(), nprim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.bs_coef.p, coef.data(), nprim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  S.bs_nbf = (int)fn.size();
+  return 0;
+}
+
+int lowdin_it_basis_norma(lowdin_it_handle h, int slot, double *norma) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 7 || !h->sp[slot].bs_nbf || !norma) return fail(h, "basis_norma: basis not set");
+  std::copy(h->sp[slot].bs_norma.begin(), h->sp[slot].bs_norma.end(), norma);
+  return 0;
+}
+
+int lowdin_it_ao_compute(lowdin_it_handle h, int a, int b) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->sp[a].bs_nbf || !h->sp[b].bs_nbf) return fail(h, "ao_compute: basis not set (lowdin_it_set_basis)");
+  if (h->ao_list) return fail(h, "ao_compute fills the stored tensor; unset LOWDIN_IT_OPT_AO_LIST");
+  CK(cudaSetDevice(h->device));
+  AoSet &S = h->ao[a][b];
+  const bool intra = (a == b);
+  const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  release_workspaces(h);
+  S.release_list();
+  const bool shard = h->nranks > 1;  // on a communicator: the rows this rank owns in the first half, whole M-vectors (as an upload leaves them)
+  const int64_t nrows = shard ? slabs_owned_below(Mb, h->slab_logB, h->nranks, h->rank) : Mb;
+  const size_t count = shard ? std::max<size_t>((size_t)nrows * Ma, 1) : (intra ? (size_t)(Ma * (Ma + 1) / 2) : (size_t)(Ma * Mb));
+  CK(S.data.ensure(count * sizeof(double)));
+  double *dst = S.data.as<double>();
+  const Species &A = h->sp[a], &B = h->sp[b];
+  EriBasis ba{A.bs_shells.as<EriShell>(), A.bs_fn.as<EriFunction>(), A.bs_expo.as<double>(), A.bs_coef.as<double>(), A.bs_nbf};
+  EriBasis bb{B.bs_shells.as<EriShell>(), B.bs_fn.as<EriFunction>(), B.bs_expo.as<double>(), B.bs_coef.as<double>(), B.bs_nbf};
+  const int mode = shard ? 2 : (intra ? 0 : 1);
+  const int64_t col_tiles = ceil_div(Ma, 128);
+  if (col_tiles > 65535) return fail(h, "ao_compute: basis too large for one launch");
+  cudaEvent_t e0 = h->ev[5], e1 = h->ev[0];
+  CK(cudaEventRecord(e0, h->stream));
+  if (nrows > 0) {
+    dim3 grid((unsigned)nrows, (unsigned)col_tiles);
+    eri_fill_kernel<<<grid, 128, 0, h->stream>>>(ba, bb, mode, Ma, nrows, h->slab_logB, h->nranks, h->rank, intra ? 1 : 0, dst);
+    h->launches += 1;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  h->timers[0] = ms * 1e-3;  // reported like an upload
+  S.swapped = 0;
+  S.sharded = shard;
+  S.src = shard ? AoSource{SRC_RECT, dst, Ma, Ma, nrows, 0} : (intra ? AoSource{SRC_SYM_PACKED, dst, Ma, 0, 0, 0} : AoSource{SRC_RECT, dst, Ma, Ma, Mb, 0});
+  S.valid = true;
+  return 0;
+}
+
+/* the stored AO tensor of a pair back on the host (single rank): packed M(M+1)/2 (intra) or [M_b][M_a] (inter) */
+int lowdin_it_ao_download(lowdin_it_handle h, int a, int b, double *out, int64_t capacity) {
+  if (!h) return 1;
+  if (a < 0 || a > 7 || b < 0 || b > 7 || !h->ao[a][b].valid) return fail(h, "ao_download: AO set not available");
+  const AoSet &S = h->ao[a][b];
+  if (S.sharded || (S.src.kind != SRC_SYM_PACKED && S.src.kind != SRC_RECT)) return fail(h, "ao_download: the AO set is not a whole stored tensor");
+  const int64_t Ma = h->sp[a].M, Mb = h->sp[b].M;
+  const int64_t count = (a == b) ? Ma * (Ma + 1) / 2 : Ma * Mb;
+  if (!out || capacity < count) return fail(h, "ao_download: buffer too small");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(out, S.data.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int lowdin_it_transform(lowdin_it_handle h, int a, int b, const int win[8], int conv, int symmetric, double drop_tol) {
   if (!h) return 1;
   CK(cudaSetDevice(h->device));
@@ -1737,8 +1834,27 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
   const int qmax = (int)qmax64;
   const int passes = (int)ceil_div(nf, qmax);
+  // Among the batch sizes that need the fewest passes, the one whose first quarters run best: the fused first-quarter kernels take the
+  // window columns in balanced groups of <= 64 (launch_q1_gen), and a group of w columns runs at eff(w) of the tensor rate (kernels
+  // alone on B200, profiles/r02i_q_probe.log: 16 -> 14.0, 32 -> 23.7, 40 -> 25.8, 48 -> 26.9, 56 -> 28.2, 64 -> 28.9 TFLOP/s).
+  // 150 occupied orbitals on one GPU (<= 60 per pass): 56 + 56 + 38 rather than 3 x 50; on two (<= 120 per pass): 112 + 38 (groups of
+  // 56) rather than 80 + 70 (groups of 40 and 32).  Ties go to the smaller batch (wider chunks).
+  auto q1_cost = [](int nfb) {
+    static const double eff[9] = {1.0, 7.5, 14.0, 19.5, 23.7, 25.8, 26.9, 28.2, 28.9};  // per 8 columns
+    const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
+    double c = 0.0;
+    for (int gi = 0; gi < groups; ++gi) {
+      const int u = units / groups + (gi < units % groups ? 1 : 0);
+      if (u > 0) c += 8.0 * u / eff[std::min(u, 8)];
+    }
+    return c;
+  };
   int qb = (int)ceil_div(nf, passes);
-  if (qb > 8 && qb < nf) { const int q8 = (qb + 7) & ~7; if (q8 <= qmax) qb = q8; }  // DMMA n-tile granularity
+  double best = -1.0;
+  for (int q = qb; q <= std::min(qmax, nf); ++q) {
+    const double c = (nf / q) * q1_cost(q) + (nf % q ? q1_cost(nf % q) : 0.0);
+    if (best < 0.0 || c < best * (1.0 - 2e-3)) { best = c; qb = q; }
+  }
   *used = std::min(qb, nf);
   return 0;
 }

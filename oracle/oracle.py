@@ -786,3 +786,66 @@ def p2_poles(a, species, aux, ionize_mo=0, factor_ss=1.0, factor_os=1.0, max_ite
             residual = abs(omega - last)
         out.append((pa, koop, omega, 1.0 / dsigma, it))
     return out
+
+
+# ---- row f4: two-particle AO integrals over contracted Cartesian Gaussians (eri_oracle.c; Libint2Iface.cpp:83-130, :219-416) ----
+class OrcShell(C.Structure):
+    _fields_ = [("l", C.c_int), ("nprim", C.c_int), ("first_prim", C.c_int), ("origin", C.c_double * 3)]
+
+
+def _eri_pack(shells):
+    """[(l, origin(3), exponents, coefficients), ...] -> (OrcShell array, exponents, coefficients, number of Cartesian functions)"""
+    arr = (OrcShell * len(shells))()
+    ex, co, nbf = [], [], 0
+    for i, (l, origin, e, c) in enumerate(shells):
+        arr[i] = OrcShell(l, len(e), len(ex), (C.c_double * 3)(*origin))
+        ex += list(e); co += list(c)
+        nbf += (l + 1) * (l + 2) // 2
+    return arr, np.array(ex, dtype=np.float64), np.array(co, dtype=np.float64), nbf
+
+
+def _eri_lib():
+    L = lib()
+    if not getattr(L, "_eri_bound", False):
+        PS = C.POINTER(OrcShell)
+        L.orc_eri_norma.argtypes = [C.c_int, PS, _f64p, _f64p, _f64p]
+        L.orc_eri_packed_intra.argtypes = [C.c_int, PS, _f64p, _f64p, _f64p]
+        L.orc_eri_rect_inter.argtypes = [C.c_int, PS, _f64p, _f64p, C.c_int, PS, _f64p, _f64p, _f64p]
+        L.orc_eri_one.argtypes = [C.c_int, PS, _f64p, _f64p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_eri_one.restype = C.c_double
+        L._eri_bound = True
+    return L
+
+
+def eri_norma(shells):
+    arr, ex, co, nbf = _eri_pack(shells)
+    out = np.zeros(nbf)
+    _eri_lib().orc_eri_norma(len(shells), arr, ex, co, out)
+    return out
+
+
+def eri_packed_intra(shells):
+    """The packed AO tensor the transformer stores (row lo: hi = lo..M-1), |raw| <= 1e-10 dropped, values * norma^4."""
+    arr, ex, co, nbf = _eri_pack(shells)
+    M = nbf * (nbf + 1) // 2
+    out = np.zeros(M * (M + 1) // 2)
+    _eri_lib().orc_eri_packed_intra(len(shells), arr, ex, co, out)
+    return out
+
+
+def eri_rect_inter(shells_a, shells_b):
+    aa, ea, ca, na = _eri_pack(shells_a)
+    ab, eb, cb, nb = _eri_pack(shells_b)
+    out = np.zeros((nb * (nb + 1) // 2, na * (na + 1) // 2))
+    _eri_lib().orc_eri_rect_inter(len(shells_a), aa, ea, ca, len(shells_b), ab, eb, cb, out)
+    return out
+
+
+def eri_one(shells, i, j, k, l):
+    arr, ex, co, _ = _eri_pack(shells)
+    return _eri_lib().orc_eri_one(len(shells), arr, ex, co, i, j, k, l)
+
+
+def sto3g_1s(zeta, origin):
+    """STO-3G 1s shell of Slater exponent zeta (Hehre, Stewart & Pople 1969): exponents scale with zeta^2."""
+    return (0, tuple(origin), [2.227660584 * zeta ** 2, 0.405771156 * zeta ** 2, 0.109818 * zeta ** 2], [0.154328967, 0.535328142, 0.444634542])

@@ -29,3 +29,19 @@ def build():
 def load():
     L = C.CDLL(build())
     return L
+
+
+ERI_OUT = os.path.join(HERE, "_build", "libmock_eri.so")
+
+
+def build_eri():
+    """The product's ERI evaluator (it_eri.cuh, __host__ __device__) compiled for the host by nvcc: CPU check of the device algorithm."""
+    os.makedirs(os.path.dirname(ERI_OUT), exist_ok=True)
+    src = os.path.join(HERE, "eri_host.cu")
+    deps = [src, os.path.join(ROOT, "openlowdin_b200", "csrc", "it_eri.cuh"), os.path.join(ROOT, "openlowdin_b200", "csrc", "it_kernels.cuh")]
+    if os.path.exists(ERI_OUT) and all(os.path.getmtime(s) < os.path.getmtime(ERI_OUT) for s in deps):
+        return ERI_OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-fopenmp",
+                    "-ccbin", "/usr/bin/g++", "-o", ERI_OUT, src, "-lgomp"], check=True)
+    return ERI_OUT

@@ -1,0 +1,130 @@
+"""Row f4 on the GPU: the AO two-particle integrals evaluated on the device (lowdin_it_set_basis / lowdin_it_ao_compute,
+it_eri.cuh; replaces Libint2Iface.cpp:219-416 and :930-1110) against the CPU oracle (oracle/eri_oracle.c, an independent
+algorithm) and the textbook H2 / STO-3G values; then the whole chain basis -> AO integrals -> MO integrals with no `.ints` stream."""
+import numpy as np
+import pytest
+
+import openlowdin_b200 as ol
+from openlowdin_b200 import capi
+from eri_cases import SZABO_H2, h2_sto3g, nbf, nuclear_like, water_like
+from helpers import dense_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(got, ref):
+    both = (got != 0) & (ref != 0)
+    assert np.abs(got - ref)[both].max() < 2e-12, np.abs(got - ref)[both].max()
+    edge = (got != 0) != (ref != 0)       # dropped on one side only: raw value at the reference's 1e-10 filter
+    assert np.abs(got - ref)[edge].max(initial=0.0) < 1e-8
+
+
+def test_h2_sto3g_textbook_values(O, T):
+    sh = h2_sto3g(O)
+    T.set_species(0, np.eye(2))
+    assert T.set_basis(0, sh) == 2
+    T.compute_ao(0, 0)
+    packed = T.download_ao(0, 0)
+    M, pid = 3, {(0, 0): 0, (0, 1): 1, (1, 0): 1, (1, 1): 2}
+    for (i, j, k, l), ref in SZABO_H2.items():
+        lo, hi = sorted((pid[(i, j)], pid[(k, l)]))
+        assert abs(packed[lo * M - lo * (lo + 1) // 2 + hi] - ref) < 1e-4
+    assert np.allclose(T.basis_norma(0), O.eri_norma(sh), rtol=1e-14)
+    _cmp(packed, O.eri_packed_intra(sh))
+
+
+@pytest.mark.parametrize("with_f", [False, True])
+def test_spdf_basis_matches_oracle(O, T, with_f):
+    sh = water_like(with_f)
+    n = nbf(sh)
+    T.set_species(0, O.random_orthonormal(n, 5))
+    T.set_basis(0, sh)
+    T.compute_ao(0, 0)
+    ref = O.eri_packed_intra(sh)
+    _cmp(T.download_ao(0, 0), ref)
+    assert np.abs(ref).max() > 1.0
+
+
+def test_inter_species_matches_oracle_and_transforms(O, T):
+    """Electron-like basis x nucleus-like basis (compute_coupling_disk), then the inter-species MP2 transform of the computed tensor."""
+    sa, sb = water_like(), nuclear_like()
+    na, nb = nbf(sa), nbf(sb)
+    Ca, Cb = O.random_orthonormal(na, 7), O.random_orthonormal(nb, 8)
+    T.set_species(1, Ca); T.set_species(2, Cb)
+    T.set_basis(1, sa); T.set_basis(2, sb)
+    T.compute_ao(1, 2)
+    rect = O.eri_rect_inter(sa, sb)
+    _cmp(T.download_ao(1, 2), rect)
+    win = O.windows_e_inter("MP2", na, nb, 5, 1)
+    ij, kl, v = T.transform(1, 2, win, ol.CONV_E)
+    rij, rkl, rv = O.transform_e_inter(Ca, Cb, rect, win)
+    Ma, Mb = O.npairs(na), O.npairs(nb)
+    assert np.abs(dense_pairs(ij, kl, v, Ma, Mb) - dense_pairs(rij, rkl, rv, Ma, Mb)).max() <= 1e-10
+
+
+@pytest.mark.parametrize("conv", ["E", "C"])
+def test_basis_to_mo_integrals_without_ints_stream(O, T, conv):
+    """basis -> AO integrals (device) -> MO integrals: equal to the oracle's transform of the oracle's AO integrals, and to the
+    path through a canonical list uploaded in the .ints stack layout (what the reference's two programs exchange)."""
+    sh = water_like()
+    n, occ = nbf(sh), 5
+    Cm = O.random_orthonormal(n, 11)
+    eps = O.synthetic_eps(occ, n)
+    T.set_species(0, Cm)
+    T.set_basis(0, sh)
+    T.compute_ao(0, 0)
+    packed = O.eri_packed_intra(sh)
+    M = O.npairs(n)
+    if conv == "E":
+        win = O.windows_e_intra("MP2", n, occ)
+        ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+        rij, rkl, rv = O.transform_e_intra(Cm, packed, win)
+        assert np.abs(dense_pairs(ij, kl, v, M, M) - dense_pairs(rij, rkl, rv, M, M)).max() <= 1e-10
+        e2 = T.transform_stream(0, 0, win, ol.CONV_E, epsA=eps)[3]
+        assert abs(e2 - O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps)) <= 1e-9
+        # the same integrals as a stored list in the .ints layout
+        T.upload_ao(0, 0, *O.canonical_list_intra(T.download_ao(0, 0), n), stack=512)
+        ij2, kl2, v2 = T.transform(0, 0, win, ol.CONV_E)
+        assert np.array_equal(ij, ij2) and np.array_equal(kl, kl2) and np.abs(v - v2).max() <= 1e-13
+    else:
+        from helpers import dense_quads
+        win, sym = O.windows_c_intra("MP2", n, occ)
+        p, q, r, s, v = T.transform(0, 0, win, ol.CONV_C, symmetric=sym)
+        rp, rq, rr, rs, rv = O.transform_c_intra(Cm, packed, win, sym)
+        assert np.abs(dense_quads(p, q, r, s, v, n, n) - dense_quads(rp, rq, rr, rs, rv, n, n)).max() <= 1e-10
+
+
+def test_computed_tensor_on_a_group_of_ranks(O):
+    """On a communicator every rank evaluates the rows of the AO tensor it owns; the collective transform gives the 1-rank result."""
+    sh = water_like()
+    n, occ = nbf(sh), 5
+    Cm = O.random_orthonormal(n, 13)
+    eps = O.synthetic_eps(occ, n)
+    win = O.windows_e_intra("MP2", n, occ)
+    rij, rkl, rv = O.transform_e_intra(Cm, O.eri_packed_intra(sh), win)
+    want = np.array([len(rv), rv.sum(), (rv * rv).sum(), O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)])
+    Ts = [ol.Transformer(0) for _ in range(3)]
+    capi.local_group(Ts)
+    try:
+        def work(r, T):
+            T.set_option(T.OPT_SLAB_BLOCK_LOG, 2)
+            T.set_species(0, Cm)
+            T.set_basis(0, sh)
+            T.compute_ao(0, 0)
+            T.set_option(T.OPT_CHUNK_COLS, 70)
+            return T.transform_stream(0, 0, win, ol.CONV_E, epsA=eps, lam=2.0)
+        got = np.sum(capi.run_ranks(Ts, work), axis=0)
+        assert abs(got[0] - want[0]) <= 2 and np.abs(got[1:] - want[1:]).max() <= 1e-9, (got, want)
+    finally:
+        for t in Ts:
+            t.close()
+
+
+def test_basis_errors(T):
+    T.set_species(3, np.eye(3))
+    with pytest.raises(ol.LowdinITError, match="Cartesian functions"):
+        T.set_basis(3, [(0, (0, 0, 0), [1.0], [1.0])])                 # 1 function for a species of 3
+    with pytest.raises(ol.LowdinITError, match="l <= 3"):
+        T.set_basis(3, [(4, (0, 0, 0), [1.0], [1.0])])
+    with pytest.raises(ol.LowdinITError, match="basis not set"):
+        T.compute_ao(3, 3)
