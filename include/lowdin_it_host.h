@@ -126,6 +126,13 @@ int lowdin_host_atomic_to_molecular_two_species(lowdin_it_handle h, const lowdin
 int lowdin_host_group_atomic_to_molecular(lowdin_it_handle *handles, int nhandles, const lowdin_host_control *ctl,
                                           const lowdin_host_species *a, const lowdin_host_species *b, int64_t *nonzero);
 
+/* Row f4: the integrals program's stream files (<tid><name>.ints, ctl->nfiles of them, in ctl->scratch_dir) from integrals
+ * EVALUATED ON THE DEVICE for the basis given to lowdin_it_set_basis(h, slot_a / slot_b): the entries compute_2body_disk
+ * (Libint2Iface.cpp:219-416; b == NULL) or compute_coupling_disk (:930-1110) write, in tensor order.  The AO set of the pair stays
+ * resident, so a transform can follow without reading the files back.  *nonzero = entries written. */
+int lowdin_host_write_computed_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
+                                    const lowdin_host_species *b, int slot_a, int slot_b, int64_t *nonzero);
+
 /* ---- the program's species loop (IntegralTransformation.f90:171-355) and its division among devices ------------
  * One entry per transformer call the reference program would make, in program order: species i (skipped under PT2 when
  * IONIZE_SPECIES is set and does not name it, :176-185), then every pair (i, j>i) (skipped under PT2 unless one of the

@@ -462,7 +462,7 @@ HOST_SYMBOLS = [
     "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
     "lowdin_host_atomic_to_molecular_two_species", "lowdin_host_plan_program", "lowdin_host_run_program",
     "lowdin_host_write_moint_d_intra", "lowdin_host_write_moint_d_inter", "lowdin_host_wfn_read", "lowdin_host_wfn_append",
-    "lowdin_host_wfn_load_species", "lowdin_host_group_atomic_to_molecular",
+    "lowdin_host_wfn_load_species", "lowdin_host_group_atomic_to_molecular", "lowdin_host_write_computed_ints",
 ]
 
 
@@ -528,6 +528,7 @@ def _host():
     L.lowdin_host_write_moint_pairs.argtypes = [C.c_char_p, C.c_int, _i64p, _i64p, _f64p, C.c_int64]
     L.lowdin_host_atomic_to_molecular_one_species.argtypes = [C.c_void_p, PC, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
+    L.lowdin_host_write_computed_ints.argtypes = [C.c_void_p, PC, PS, PS, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     L.lowdin_host_group_atomic_to_molecular.argtypes = [C.POINTER(C.c_void_p), C.c_int, PC, PS, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_plan_program.argtypes = [PC, PS, C.c_int, C.c_int, C.POINTER(HostTask), C.c_int, C.POINTER(C.c_int)]
     L.lowdin_host_run_program.argtypes = [C.c_void_p, PC, PS, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
@@ -599,6 +600,14 @@ def host_transform_one_species(T, ctl, a):
 def host_transform_two_species(T, ctl, a, b):
     n = C.c_int64()
     _hck(_host().lowdin_host_atomic_to_molecular_two_species(T.h if T is not None else None, C.byref(ctl), C.byref(a), C.byref(b), C.byref(n)))
+    return n.value
+
+
+def host_write_computed_ints(T, ctl, a, b, slot_a, slot_b=None):
+    """Row f4 file form: the .ints stream files of a species (b None) or a pair from integrals evaluated on the device."""
+    n = C.c_int64()
+    _hck(_host().lowdin_host_write_computed_ints(T.h, C.byref(ctl), C.byref(a), C.byref(b) if b is not None else None, slot_a,
+                                                 slot_a if slot_b is None else slot_b, C.byref(n)))
     return n.value
 
 

@@ -551,6 +551,62 @@ int lowdin_host_group_atomic_to_molecular(lowdin_it_handle *handles, int nhandle
   return run_and_write(handles, nhandles, ctl, a, b, nonzero);
 }
 
+// ---- row f4: the integrals program's stream files from integrals evaluated on the device ------------------------
+// The entries LibintInterface::compute_2body_disk (Libint2Iface.cpp:219-416; p >= q, r >= s, (p,q) >= (r,s), 1-based) or
+// ::compute_coupling_disk (:930-1110; p <= q, r <= s) write -- the same set, in tensor order instead of shell-quartet order --
+// spread over ctl->nfiles stream files as the reference's threads spread theirs.
+int lowdin_host_write_computed_ints(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *a,
+                                    const lowdin_host_species *b, int slot_a, int slot_b, int64_t *nonzero) {
+  if (check_ctl(ctl)) return 1;
+  if (!h || !a) return hfail("null handle / species");
+  const bool intra = (b == nullptr);
+  if (intra) slot_b = slot_a;
+  if (lowdin_it_ao_compute(h, slot_a, slot_b)) return hfail(lowdin_it_last_error(h));
+  const int64_t na = a->nao, nb = intra ? a->nao : b->nao;
+  const int64_t Ma = na * (na + 1) / 2, Mb = nb * (nb + 1) / 2;
+  const int64_t count = intra ? Ma * (Ma + 1) / 2 : Ma * Mb;
+  std::vector<double> t((size_t)count);
+  if (lowdin_it_ao_download(h, slot_a, slot_b, t.data(), count)) return hfail(lowdin_it_last_error(h));
+  auto pair_table = [](int64_t n, std::vector<int32_t> &lo, std::vector<int32_t> &hi) {
+    for (int64_t i = 0; i < n; ++i) for (int64_t j = i; j < n; ++j) { lo.push_back((int32_t)i + 1); hi.push_back((int32_t)j + 1); }
+  };
+  std::vector<int32_t> alo, ahi, blo, bhi;
+  pair_table(na, alo, ahi);
+  if (!intra) pair_table(nb, blo, bhi);
+  std::vector<int32_t> p, q, r, s;
+  std::vector<double> v;
+  if (intra) {
+    for (int64_t lo = 0; lo < Ma; ++lo)
+      for (int64_t hi = lo; hi < Ma; ++hi) {
+        const double x = t[(size_t)(lo * Ma - lo * (lo + 1) / 2 + hi)];
+        if (x == 0.0) continue;  // dropped on the device by the reference's raw-value filter
+        int32_t pp = ahi[hi], qq = alo[hi], rr = ahi[lo], ss = alo[lo];  // p >= q, r >= s
+        if (pp < rr || (pp == rr && qq < ss)) { std::swap(pp, rr); std::swap(qq, ss); }
+        p.push_back(pp); q.push_back(qq); r.push_back(rr); s.push_back(ss); v.push_back(x);
+      }
+  } else {
+    for (int64_t rs = 0; rs < Mb; ++rs)
+      for (int64_t pq = 0; pq < Ma; ++pq) {
+        const double x = t[(size_t)(rs * Ma + pq)];
+        if (x == 0.0) continue;
+        p.push_back(alo[pq]); q.push_back(ahi[pq]); r.push_back(blo[rs]); s.push_back(bhi[rs]); v.push_back(x);
+      }
+  }
+  const int64_t n = (int64_t)v.size();
+  for (int tid = 0; tid < ctl->nfiles; ++tid) {
+    char name[256];
+    int swapped = 0;
+    if (lowdin_host_ints_filename(tid, a, b, name, &swapped)) return 1;
+    if (swapped) return hfail("write_computed_ints: give the pair in file order (lower species id first)");
+    const int64_t lo = n * tid / ctl->nfiles, hi = n * (tid + 1) / ctl->nfiles;
+    if (lowdin_host_write_ints_file(join(ctl->scratch_dir, name).c_str(), ctl->integral_stack_size, p.data() + lo, q.data() + lo,
+                                    r.data() + lo, s.data() + lo, v.data() + lo, hi - lo))
+      return 1;
+  }
+  if (nonzero) *nonzero = n;
+  return 0;
+}
+
 // ---- transformer-D record layout ------------------------------------------------------------------------------
 namespace {
 inline int64_t index2(int64_t i, int64_t j) { return i > j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }  // ReadIntegrals.f90:175-186

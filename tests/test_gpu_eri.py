@@ -128,3 +128,37 @@ def test_basis_errors(T):
         T.set_basis(3, [(4, (0, 0, 0), [1.0], [1.0])])
     with pytest.raises(ol.LowdinITError, match="basis not set"):
         T.compute_ao(3, 3)
+
+
+def test_computed_ints_files_feed_the_file_to_file_transform(O, T, tmp_path):
+    """The integrals program's drop-in: .ints stream files written from device-evaluated integrals (reference index conventions:
+    p >= q, r >= s, (p,q) >= (r,s), 1-based; terminator), then the ordinary file-to-file transformer call on those files."""
+    sh = water_like()
+    n, occ, S = nbf(sh), 5, 300
+    Cm = O.random_orthonormal(n, 17)
+    ctl = capi.host_control("E", "MP2", stack=S, nfiles=3, scratch_dir=str(tmp_path))
+    sp = capi.host_species("E-", 1, n, occ, coeff=Cm)
+    T.set_species(0, Cm)
+    T.set_basis(0, sh)
+    cnt = capi.host_write_computed_ints(T, ctl, sp, None, 0)
+    packed = O.eri_packed_intra(sh)
+    assert abs(cnt - np.count_nonzero(packed)) <= 4          # entries at the 1e-10 raw-value filter may differ
+    got = np.zeros_like(packed)
+    M = O.npairs(n)
+    total = 0
+    for t in range(3):
+        (p, q, r, s, v), nread = capi.host_read_ints_file(str(tmp_path / f"{t}E-.ints"), S, packed.size)
+        assert nread == len(v)
+        total += len(v)
+        assert np.all(p >= q) and np.all(r >= s) and np.all((p > r) | ((p == r) & (q >= s)))
+        p, q, r, s = (x.astype(np.int64) for x in (p, q, r, s))
+        pid = lambda lo, hi: lo * n - lo * (lo - 1) // 2 + (hi - lo)     # noqa: E731  0-based row-wise upper pair id, lo <= hi
+        lo_hi = np.sort(np.stack([pid(q - 1, p - 1), pid(s - 1, r - 1)]), axis=0)
+        got[lo_hi[0] * M - lo_hi[0] * (lo_hi[0] + 1) // 2 + lo_hi[1]] = v
+    assert total == cnt
+    both = (got != 0) & (packed != 0)
+    assert np.abs(got - packed)[both].max() < 2e-12
+    # the reference host's transformer call on those files
+    nmo = capi.host_transform_one_species(T, ctl, sp)
+    rij, rkl, rv = O.transform_e_intra(Cm, packed, O.windows_e_intra("MP2", n, occ))
+    assert abs(nmo - len(rv)) <= 2
