@@ -144,8 +144,12 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
         raw = pin((total // stack_size + 1) * 24 * stack_size, torch.uint8)
         nblk = raw_ints_blocks(lst, total, stack_size, raw)
 
+    host_ms = {"set_species": 0.0, "ao_upload": 0.0, "transform": 0.0, "download": 0.0}   # wall time of the calls as the host sees them
+
     def step():
+        t_a = time.perf_counter()
         T.set_species(0, Cpin)
+        t_b = time.perf_counter()
         T._ck(L.lowdin_it_ao_begin(h, 0, 0, 0))
         if mode == "blocks":
             T._ck(L.lowdin_it_ao_push_blocks(h, raw.ctypes.data, nblk, stack_size))
@@ -154,15 +158,22 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
                 b = min(total + 1, a + push_entries)
                 T._ck(L.lowdin_it_ao_push_stacks(h, lst[0][a:b], lst[1][a:b], lst[2][a:b], lst[3][a:b], lst[4][a:b], b - a))
         T._ck(L.lowdin_it_ao_end(h))
+        t_c = time.perf_counter()
         T._ck(L.lowdin_it_transform(h, 0, 0, win, capi.CONV_E, 0, 1e-10))
+        t_d = time.perf_counter()
         T._ck(L.lowdin_it_result_count(h, C.byref(cnt)))
         if cnt.value > cap:
             raise RuntimeError("more results than window pairs")
         T._ck(L.lowdin_it_download_pairs(h, o_ij, o_kl, o_v))
+        t_e = time.perf_counter()
+        for k, dt_ in (("set_species", t_b - t_a), ("ao_upload", t_c - t_b), ("transform", t_d - t_c), ("download", t_e - t_d)):
+            host_ms[k] += dt_ * 1e3
         return cnt.value
 
     step()                                    # warm-up (allocations, first-launch costs)
     torch.cuda.synchronize()
+    for k in host_ms:
+        host_ms[k] = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         kept = step()
@@ -186,6 +197,7 @@ def stored_ao_e2e(torch, ol, capi, dev_index, n, occ, steps, push_entries=1 << 2
             "h2d_bytes_per_step": int(total * 24 + n * n * 8), "d2h_bytes_per_step": int(kept * 24), "mo_integrals_kept": int(kept),
             "device_ms": {"ao_upload_scatter": tm["ao_upload"] * 1e3, "first_half": tm["first_half"] * 1e3,
                           "second_half": tm["second_half"] * 1e3, "compaction": tm["consume"] * 1e3, "download": tm["download"] * 1e3},
+            "host_ms_per_call": {k: x / steps for k, x in host_ms.items()},
             "same_index_lists_as_generated": same, "max_abs_diff_vs_generated": diff,
             "_result": (o_ij[:kept].copy(), o_kl[:kept].copy(), stored)}
 

@@ -1704,14 +1704,12 @@ int lowdin_it_ao_compute(lowdin_it_handle h, int a, int b) {
   const Species &A = h->sp[a], &B = h->sp[b];
   EriBasis ba{A.bs_shells.as<EriShell>(), A.bs_fn.as<EriFunction>(), A.bs_expo.as<double>(), A.bs_coef.as<double>(), A.bs_nbf};
   EriBasis bb{B.bs_shells.as<EriShell>(), B.bs_fn.as<EriFunction>(), B.bs_expo.as<double>(), B.bs_coef.as<double>(), B.bs_nbf};
-  const int mode = shard ? 2 : (intra ? 0 : 1);
-  const int64_t col_tiles = ceil_div(Ma, 128);
-  if (col_tiles > 65535) return fail(h, "ao_compute: basis too large for one launch");
+  EriFillArgs fa{ba, bb, shard ? 2 : (intra ? 0 : 1), Ma, nrows, h->slab_logB, h->nranks, h->rank, intra ? 1 : 0, dst};
+  if (ceil_div(Ma, ERI_FILL_THREADS) > 65535) return fail(h, "ao_compute: basis too large for one launch");
   cudaEvent_t e0 = h->ev[5], e1 = h->ev[0];
   CK(cudaEventRecord(e0, h->stream));
   if (nrows > 0) {
-    dim3 grid((unsigned)nrows, (unsigned)col_tiles);
-    eri_fill_kernel<<<grid, 128, 0, h->stream>>>(ba, bb, mode, Ma, nrows, h->slab_logB, h->nranks, h->rank, intra ? 1 : 0, dst);
+    eri_fill_kernel<<<eri_fill_grid(fa), ERI_FILL_THREADS, 0, h->stream>>>(fa);
     h->launches += 1;
     CK(cudaGetLastError());
   }

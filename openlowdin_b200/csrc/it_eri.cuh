@@ -214,25 +214,36 @@ __host__ __device__ __forceinline__ void eri_pair_decode(int64_t pair, int n, in
 
 // One thread per stored element.  mode 0: intra packed (row = slab `lo`, pairs hi = lo..Ma-1); mode 1: rectangular rows
 // [row][Ma] with the slab of row r = r (inter-species, A = pair species, B = slab species) ; mode 2: rows a rank owns on a
-// communicator (slab = slab_global(row)), A == B allowed.  blockIdx.y = row, blockIdx.x * blockDim.x + threadIdx.x = column.
-__global__ void __launch_bounds__(128) eri_fill_kernel(EriBasis A, EriBasis B, int mode, int64_t Ma, int64_t nrows, int logB, int G, int rank,
-                                                        int strict, double *__restrict__ dst) {
-  const int64_t row = blockIdx.y;
-  if (row >= nrows) return;
-  const int64_t slab = (mode == 2) ? slab_global(row, logB, G, rank) : row;
-  const int64_t col0 = (mode == 0) ? slab : 0;
-  const int64_t pair = col0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pair >= Ma) return;
+// communicator (slab = slab_global(row)), A == B allowed.  Grid: x = row, y = tile of 128 columns (eri_fill_grid).
+constexpr int ERI_FILL_THREADS = 128;
+struct EriFillArgs {
+  EriBasis A, B;
+  int mode;
+  int64_t Ma, nrows;
+  int logB, G, rank, strict;
+  double *dst;
+};
+inline dim3 eri_fill_grid(const EriFillArgs &a) { return dim3((unsigned)a.nrows, (unsigned)((a.Ma + ERI_FILL_THREADS - 1) / ERI_FILL_THREADS)); }
+
+__host__ __device__ inline void eri_fill_element(const EriFillArgs &a, int64_t block_x, int64_t block_y, int thread) {
+  const int64_t row = block_x;
+  if (row >= a.nrows) return;
+  const int64_t slab = (a.mode == 2) ? slab_global(row, a.logB, a.G, a.rank) : row;
+  const int64_t col0 = (a.mode == 0) ? slab : 0;
+  const int64_t pair = col0 + block_y * ERI_FILL_THREADS + thread;
+  if (pair >= a.Ma) return;
   int i, j, k, l;
-  eri_pair_decode(pair, A.nbf, i, j);
-  eri_pair_decode(slab, B.nbf, k, l);
-  const EriFunction fa = A.fn[i], fb = A.fn[j], fc = B.fn[k], fd = B.fn[l];
-  const double raw = eri_raw(A, fa, fb, B, fc, fd);
+  eri_pair_decode(pair, a.A.nbf, i, j);
+  eri_pair_decode(slab, a.B.nbf, k, l);
+  const EriFunction fa = a.A.fn[i], fb = a.A.fn[j], fc = a.B.fn[k], fd = a.B.fn[l];
+  const double raw = eri_raw(a.A, fa, fb, a.B, fc, fd);
   // the reference keeps |raw| > 1e-10 within one species (Libint2Iface.cpp:369) and |raw| >= 1e-10 between two (:1053)
-  const bool keep = strict ? (fabs(raw) > 1.0e-10) : (fabs(raw) >= 1.0e-10);
+  const bool keep = a.strict ? (fabs(raw) > 1.0e-10) : (fabs(raw) >= 1.0e-10);
   const double v = keep ? raw * fa.norma * fb.norma * fc.norma * fd.norma : 0.0;
-  double *out = (mode == 0) ? dst + (slab * Ma - (slab * (slab + 1)) / 2) : dst + row * Ma;
+  double *out = (a.mode == 0) ? a.dst + (slab * a.Ma - (slab * (slab + 1)) / 2) : a.dst + row * a.Ma;
   out[pair] = v;
 }
+
+__global__ void __launch_bounds__(ERI_FILL_THREADS) eri_fill_kernel(EriFillArgs a) { eri_fill_element(a, blockIdx.x, blockIdx.y, threadIdx.x); }
 
 }  // namespace lowdin

@@ -52,3 +52,43 @@ def test_device_algorithm_matches_oracle_spdf(O, host_eri, with_f):
     edge = (got != 0) != (ref != 0)           # dropped by one side only: raw value at the 1e-10 filter
     assert np.abs(got - ref)[edge].max(initial=0.0) < 1e-8
     assert np.abs(ref).max() > 1.0            # the (ss|ss) core integrals are of order 1..5
+
+
+@pytest.fixture(scope="module")
+def host_fill():
+    import build_mock
+    from openlowdin_b200 import capi
+    L = C.CDLL(build_mock.build_eri())
+    f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    PS = C.POINTER(capi.Shell)
+    L.mock_eri_fill.argtypes = [C.c_int, C.c_int, PS, f64, f64, C.c_int, PS, f64, f64, C.c_int, C.c_int, C.c_int, f64, C.POINTER(C.c_int64)]
+
+    def run(mode, sa, sb, count, logB=0, G=1, rank=0):
+        aa, ea, ca, _ = capi.pack_shells(sa)
+        ab, eb, cb, _ = capi.pack_shells(sb)
+        dst = np.full(count, np.nan)
+        nrows = C.c_int64()
+        assert L.mock_eri_fill(mode, len(sa), aa, ea, ca, len(sb), ab, eb, cb, logB, G, rank, dst, C.byref(nrows)) == 0
+        return dst, nrows.value
+    return run
+
+
+def test_kernel_grid_mapping_of_the_three_storage_modes(O, host_fill):
+    """eri_fill_element over eri_fill_grid on the host: every element of the packed tensor / the inter-species rectangle / a rank's
+    rows is written exactly where the transformer reads it."""
+    from eri_cases import nuclear_like
+    sa, sb = water_like()[:5], nuclear_like()     # 13 and 10 functions: 91 and 55 pairs
+    na, nb = nbf(sa), nbf(sb)
+    Ma, Mb = na * (na + 1) // 2, nb * (nb + 1) // 2
+    ref = O.eri_packed_intra(sa)
+    got, _ = host_fill(0, sa, sa, Ma * (Ma + 1) // 2)
+    assert not np.isnan(got).any() and np.abs(got - ref).max() < 2e-12
+    rect = O.eri_rect_inter(sa, sb)
+    got, nrows = host_fill(1, sa, sb, Ma * Mb)
+    assert nrows == Mb and not np.isnan(got).any() and np.abs(got.reshape(Mb, Ma) - rect).max() < 2e-12
+    # rows of rank 1 of 3, blocks of 4 slabs: local row r is global slab (r // 4 * 3 + 1) * 4 + r % 4, the whole symmetric M-vector
+    sq = np.zeros((Ma, Ma)); iu = np.triu_indices(Ma); sq[iu] = ref; sq = sq + np.triu(sq, 1).T
+    owned = [s for s in range(Ma) if (s >> 2) % 3 == 1]
+    got, nrows = host_fill(2, sa, sa, len(owned) * Ma, logB=2, G=3, rank=1)
+    assert nrows == len(owned) and not np.isnan(got).any()
+    assert np.abs(got.reshape(len(owned), Ma) - sq[owned]).max() < 2e-12
