@@ -170,6 +170,12 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
  * element (its local slot `row`, global slab `slab`) at lowdin_it_exchanged_offset(). */
 int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t chunk_width, int nranks, int rank, int log_block,
                          int *own, int64_t *wblk, int64_t *loc_lo, int64_t *count);
+/* The occupied batch lowdin_it_transform_stream picks when occ_batch == 0, as a pure function (host logic, no device): n_first
+ * first-window values, at most q_max per pass (memory), slots_per_first window pairs per first-window value, second-half window
+ * sizes n_first2 / basis nao2, first-pair basis nao1, nslabs AO-pair slabs of npairs1 doubles, avail_bytes of device memory for the
+ * third-quarter accumulators + chunk buffers of one rank, stored != 0 when the AO tensor is re-read by every pass. */
+int lowdin_it_occ_batch_model(int n_first, int q_max, int nranks, int64_t slots_per_first, int n_first2, int nao2, int nao1, int64_t nslabs,
+                              int64_t npairs1, double avail_bytes, int stored);
 int lowdin_it_slab_owner(int64_t slab, int nranks, int log_block);
 int64_t lowdin_it_slab_local(int64_t slab, int nranks, int log_block);
 int64_t lowdin_it_slab_global(int64_t local_slab, int nranks, int rank, int log_block);

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
     "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter", "lowdin_it_result_segments", "lowdin_it_group_transform",
     "lowdin_it_group_result_count", "lowdin_it_group_download_pairs", "lowdin_it_group_download_quads",
-    "lowdin_it_transform_stream_sink", "lowdin_it_set_basis", "lowdin_it_basis_norma", "lowdin_it_ao_compute", "lowdin_it_ao_download",
+    "lowdin_it_transform_stream_sink", "lowdin_it_occ_batch_model", "lowdin_it_set_basis", "lowdin_it_basis_norma", "lowdin_it_ao_compute", "lowdin_it_ao_download",
 ]
 
 
@@ -123,6 +123,7 @@ def load():
     L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
     L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
     L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_occ_batch_model.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int]
     L.lowdin_it_set_basis.argtypes = [H, C.c_int, C.c_int, C.POINTER(Shell), _f64p, _f64p]
     L.lowdin_it_basis_norma.argtypes = [H, C.c_int, _f64p]
     L.lowdin_it_ao_compute.argtypes = [H, C.c_int, C.c_int]
@@ -681,3 +682,9 @@ def host_wfn_load_species(path, name, sid, nao, occ, core=0, active=0):
     _hck(_host().lowdin_host_wfn_load_species(path.encode(), C.byref(sp), coeff, eps.ctypes.data))
     sp._keep, sp.eps = coeff, eps
     return sp
+
+
+def occ_batch_model(n_first, q_max, nranks, slots_per_first, n_first2, nao2, nao1, nslabs, npairs1, avail_bytes, stored=False):
+    """The occupied batch the streaming transform picks (pure host logic, lowdin_it_occ_batch_model)."""
+    return load().lowdin_it_occ_batch_model(n_first, q_max, nranks, slots_per_first, n_first2, nao2, nao1, nslabs, npairs1,
+                                            float(avail_bytes), int(stored))

@@ -1810,6 +1810,48 @@ int lowdin_it_download_quads(lowdin_it_handle h, int32_t *p, int32_t *q, int32_t
   return 0;
 }
 
+// Occupied batch (first-window values per pass) from a cost model of what depends on it, everything else (second and fourth
+// quarter, bytes exchanged) being the same for every choice:
+//  * first quarter: the fused kernels take the window columns in balanced groups of <= 64 (launch_q1_gen) and a group of w columns
+//    runs at eff(w) of the tensor rate (kernels alone on B200, profiles/r02i_q_probe.log: 16 -> 14.0, 32 -> 23.7, 40 -> 25.8,
+//    48 -> 26.9, 56 -> 28.2, 64 -> 28.9 TFLOP/s);
+//  * third quarter: its flops at ~33 TFLOP/s plus one read-modify-write sweep of the accumulators T3 per chunk at ~6 TB/s, the number
+//    of chunks following from the memory the batch leaves for the chunk buffers;
+//  * a stored AO tensor is read again by every pass (row completion + fused first quarter: ~24 M_a bytes per slab).
+// More passes are not a cost in themselves: 150 occupied orbitals on TWO GPUs run better as 56 + 56 + 38 (wide chunks, third quarter
+// ~28 TFLOP/s) than as 110 + 40 (measured: third quarter 14.3 TFLOP/s, profiles/r02t_bench_n1500_g2.json) or 80 + 70 (first quarter in
+// groups of 40 and 32 columns, 24.2 TFLOP/s, profiles/r02n_*).  Pure function of its arguments: every rank decides alike.
+int occ_batch_model(int nf, int qmax, int G, double spf, int nf2, int n2, int n1, double nslabs1, double Ma, double avail, bool stored) {
+  static const double eff[9] = {1.0, 7.5, 14.0, 19.5, 23.7, 25.8, 26.9, 28.2, 28.9};  // TFLOP/s per group of 8 u columns
+  auto q1_cost = [&](int nfb) {  // seconds of first quarter per slab of the pass, times 1e12 / (2 n1^2)
+    const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
+    double c = 0.0;
+    for (int gi = 0; gi < groups; ++gi) {
+      const int u = units / groups + (gi < units % groups ? 1 : 0);
+      if (u > 0) c += 8.0 * u / eff[std::min(u, 8)];
+    }
+    return c;
+  };
+  const double ldt2 = (double)roundup2(n2), slabs_own = nslabs1 / G;
+  auto pass_cost = [&](int q) {
+    const double t3 = spf * q * nf2 * ldt2 * 8.0 / G;
+    const double per_col = (G > 1) ? spf * q * 8.0 / G + 2.0 * (spf * q / G) * 8.0 + 8.0 : spf * q * 8.0;
+    const double cols = std::max(std::min((avail - t3) / per_col, nslabs1), 2.0 * n2);
+    const double nchunks = std::max(1.0, nslabs1 / cols);
+    const double t_q1 = slabs_own * 2.0 * n1 * (double)n1 * q1_cost(q) * 1e-12;
+    const double t_q3 = 2.0 * (spf * q / G) * nf2 * (double)n2 * n2 / 33e12 + nchunks * t3 / 6e12;
+    const double t_ao = stored ? slabs_own * Ma * 24.0 / 5e12 : 0.0;
+    return t_q1 + t_q3 + t_ao;
+  };
+  int best_q = std::max(1, std::min(qmax, nf));
+  double best = -1.0;
+  for (int q = std::max(1, std::min(qmax, nf)); q >= 1; --q) {  // from the largest batch down: ties go to fewer passes
+    const double c = (nf / q) * pass_cost(q) + (nf % q ? pass_cost(nf % q) : 0.0);
+    if (best < 0.0 || c < best * (1.0 - 1.5e-2)) { best = c; best_q = q; }  // a smaller batch must win by more than the model's noise
+  }
+  return best_q;
+}
+
 static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int *used) {
   const int nf = std::max(pl.h1.nf, 1);
   if (requested > 0) { *used = std::min(requested, nf); return 0; }
@@ -1821,39 +1863,20 @@ static int pick_occ_batch(lowdin_it_handle h, const Plan &pl, int requested, int
   // results buffer: 4 GB of groups, or two f-blocks when one alone is larger (the host sink double-buffers its groups, and the same
   // occupied batch must serve the pass with and without a sink)
   const double out_need = std::max(std::min(4.0e9, spf * per_out * nf), std::min(2.0, (double)nf) * spf * per_out);
-  const double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->T3.cap +
-                               (double)h->X.cap + (double)h->T1t.cap) - 2.0 * (double)h->workspace_bytes - out_need - (double)((size_t)1 << 30);
+  double avail = 0.92 * ((double)free_b + (double)h->H.cap + (double)h->OUT.cap + (double)h->H2.cap + (double)h->Hx.cap + (double)h->H2x.cap + (double)h->T3.cap +
+                         (double)h->X.cap + (double)h->T1t.cap) - 2.0 * (double)h->workspace_bytes - out_need - (double)((size_t)1 << 30);
+  // the same figure on every rank (collective when occ_batch == 0 on a communicator: every rank must make this call)
+  int64_t avail64 = (int64_t)std::max(avail, 0.0);
+  if (agree_min(h, &avail64)) return 1;
+  avail = (double)avail64;
   // per first-window value: third-quarter accumulators of its slots (own share) + a chunk of at least 8 pair rows of H
   const double t3_per_f = spf * (double)pl.h2.nf * (double)roundup2(pl.h2.nc) * 8.0 / G;
   const double cols_min = (double)std::min<int64_t>(pl.nslabs1, 8LL * pl.h2.nc);
   const double hc_per_f = spf * 8.0 * cols_min * (G > 1 ? 3.0 / G : 1.0);
   const double list_per_f = (pl.src.kind == SRC_LIST) ? (double)pl.nslabs1 * pl.h1.nc * 8.0 / G : 0.0;  // T1list[own slab][nu][f]
-  int64_t qmax64 = (int64_t)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
-  if (agree_min(h, &qmax64)) return 1;  // collective when occ_batch == 0 on a communicator: every rank must make this call
-  const int qmax = (int)qmax64;
-  const int passes = (int)ceil_div(nf, qmax);
-  // Among the batch sizes that need the fewest passes, the one whose first quarters run best: the fused first-quarter kernels take the
-  // window columns in balanced groups of <= 64 (launch_q1_gen), and a group of w columns runs at eff(w) of the tensor rate (kernels
-  // alone on B200, profiles/r02i_q_probe.log: 16 -> 14.0, 32 -> 23.7, 40 -> 25.8, 48 -> 26.9, 56 -> 28.2, 64 -> 28.9 TFLOP/s).
-  // 150 occupied orbitals on one GPU (<= 60 per pass): 56 + 56 + 38 rather than 3 x 50; on two (<= 120 per pass): 112 + 38 (groups of
-  // 56) rather than 80 + 70 (groups of 40 and 32).  Ties go to the smaller batch (wider chunks).
-  auto q1_cost = [](int nfb) {
-    static const double eff[9] = {1.0, 7.5, 14.0, 19.5, 23.7, 25.8, 26.9, 28.2, 28.9};  // per 8 columns
-    const int groups = (int)ceil_div(nfb, 64), units = (int)ceil_div(nfb, 8);
-    double c = 0.0;
-    for (int gi = 0; gi < groups; ++gi) {
-      const int u = units / groups + (gi < units % groups ? 1 : 0);
-      if (u > 0) c += 8.0 * u / eff[std::min(u, 8)];
-    }
-    return c;
-  };
-  int qb = (int)ceil_div(nf, passes);
-  double best = -1.0;
-  for (int q = qb; q <= std::min(qmax, nf); ++q) {
-    const double c = (nf / q) * q1_cost(q) + (nf % q ? q1_cost(nf % q) : 0.0);
-    if (best < 0.0 || c < best * (1.0 - 2e-3)) { best = c; qb = q; }
-  }
-  *used = std::min(qb, nf);
+  const int qmax = (int)std::max(1.0, std::min((double)nf, avail / (t3_per_f + hc_per_f + list_per_f)));
+  const bool stored = (pl.src.kind == SRC_SYM_PACKED || pl.src.kind == SRC_RECT);
+  *used = occ_batch_model(nf, qmax, G, spf, pl.h2.nf, pl.h2.nc, pl.h1.nc, (double)pl.nslabs1, (double)h->sp[pl.a].M, avail, stored);
   return 0;
 }
 
@@ -2057,6 +2080,11 @@ int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t c
     return 1;
   shard_plan(nfb, fbeg, chunk_base, chunk_width, nranks, rank, log_block, own, wblk, loc_lo, count);
   return 0;
+}
+int lowdin_it_occ_batch_model(int n_first, int q_max, int nranks, int64_t slots_per_first, int n_first2, int nao2, int nao1, int64_t nslabs,
+                              int64_t npairs1, double avail_bytes, int stored) {
+  return occ_batch_model(n_first, q_max, std::max(nranks, 1), (double)slots_per_first, n_first2, nao2, nao1, (double)nslabs, (double)npairs1, avail_bytes,
+                         stored != 0);
 }
 int lowdin_it_slab_owner(int64_t slab, int nranks, int log_block) { return nranks > 1 ? slab_owner(slab, log_block, nranks) : 0; }
 int64_t lowdin_it_slab_local(int64_t slab, int nranks, int log_block) { return nranks > 1 ? slab_local(slab, log_block, nranks) : slab; }

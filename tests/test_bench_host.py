@@ -213,3 +213,26 @@ def test_transformer_d_leg_with_stand_in(O):
     assert calls == [(M * (M + 1) // 2,)] * 2                    # one warm-up call, one timed call
     assert out["max_abs_diff"] <= 1e-10 and out["reference_ms"] > 0 and out["gpu_ms"] > 0
     assert out["d2h_bytes"] == 8 * M * (M + 1) // 2
+
+
+def test_occupied_batch_model_decisions():
+    """lowdin_it_occ_batch_model (host logic): the batch sizes the cost model picks for the N_bf = 1500 MP2 window (150 occupied,
+    1350 virtuals) with ~157 GB for accumulators + chunk buffers per GPU -- one column group of the fused first quarter per pass
+    unless the whole window fits with wide chunks."""
+    from openlowdin_b200 import capi
+    n, occ, virt = 1500, 150, 1350
+    M = n * (n + 1) // 2
+    avail = 157e9
+
+    def pick(G, qmax, stored=False):
+        return capi.occ_batch_model(occ, qmax, G, virt, occ, n, n, M, M, avail, stored)
+    q1 = pick(1, 60)
+    assert 48 <= q1 <= 56 and -(-occ // q1) == 3           # one GPU: three passes of one <= 56-column group
+    q2 = pick(2, 120)
+    assert 48 <= q2 <= 64 and -(-occ // q2) == 3           # two GPUs: NOT 110 + 40 (measured: third quarter at 14 TFLOP/s)
+    assert pick(8, 150) == 150                             # eight GPUs: the whole window in one pass (6 chunks)
+    assert pick(1, 7) == 7                                 # memory-bound small batches: the largest that fits
+    # N_bf = 2000 on one GPU: 25 fit; nothing smaller is better
+    n2, occ2, virt2 = 2000, 200, 1800
+    M2 = n2 * (n2 + 1) // 2
+    assert capi.occ_batch_model(occ2, 25, 1, virt2, occ2, n2, n2, M2, M2, avail, False) in (24, 25)
