@@ -475,6 +475,7 @@ def main():
     ap.add_argument("--frag-perm", type=int, default=-1, help="fragment-row permutation of the TMA kernels: 0 / 1 (-1 = library default)")
     ap.add_argument("--overlap", type=int, default=-1, help="N>1: all-to-all of chunk c under the first half of chunk c+1: 0 / 1 (-1 = library default)")
     ap.add_argument("--gemm-tall", type=int, default=-1, help="192 x 64 tiles for the second / fourth quarter when the rows are a multiple of 192 plus a few: 0 / 1 (-1 = library default)")
+    ap.add_argument("--q3-two-cta", type=int, default=-1, help="third quarter: products with K <= this value as two 4-warp CTAs per SM (0 = off, -1 = library default)")
     ap.add_argument("--q3-red", type=int, default=-1, help="third-quarter accumulation by red.global.add.f64: 0 / 1 (-1 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -532,6 +533,8 @@ def main():
         T.set_option(T.OPT_OVERLAP_EXCHANGE, args.overlap)
     if args.gemm_tall >= 0:
         T.set_option(T.OPT_GEMM_TALL, args.gemm_tall)
+    if args.q3_two_cta >= 0:
+        T.set_option(T.OPT_Q3_TWO_CTA, args.q3_two_cta)
     T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 

@@ -210,6 +210,7 @@ int lowdin_it_group_download_quads(lowdin_it_handle *handles, int nranks, int32_
                                          * M(M+1)/2 dense tensor); the first quarter is then LIST-DRIVEN: every integral is scattered with its <= 4 images into the
                                          * quarter-transformed slabs (the DIRECT first quarter of Libint2Iface.cpp:793-853 / TransformIntegralsC.f90:545-558) */
 #define LOWDIN_IT_OPT_SLAB_BLOCK_LOG 12 /* log2 of the block of consecutive AO-pair slabs one rank owns in the block-cyclic first half (default 5); set before uploading */
+#define LOWDIN_IT_OPT_Q3_TWO_CTA 18       /* third quarter: accumulating products whose K (pair rows of the chunk) is <= this value run as two independent 4-warp CTAs per SM, so that one tile's read-modify-write epilogue overlaps the other's DMMAs; 0 = off */
 #define LOWDIN_IT_OPT_GEMM_TALL 17        /* TMA GEMM: 1 = 192 x 64 tiles for few-rows x many-columns products whose row count is a multiple of 192 plus <= 16 (1350 = 7 x 192 + 6) */
 #define LOWDIN_IT_OPT_SINK_BLOCK_BYTES 16 /* size of one dense block handed to the host sink (default 256 MiB; at least one first-contracted index worth of pairs is always sent); setting it allocates the pinned two-slot ring at once */
 #define LOWDIN_IT_OPT_OVERLAP_EXCHANGE 15 /* N > 1 ranks: two sets of chunk buffers, the all-to-all of chunk c on its own stream under the first half of chunk c + 1: 0 = never, 1 (default) = when the pass needs at most ~12 chunks (the second buffer set makes chunks 3/4 as wide), 2 = always */

@@ -318,7 +318,7 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
-    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES, OPT_GEMM_TALL = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES, OPT_GEMM_TALL, OPT_Q3_TWO_CTA = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT, DEFAULT_FRAG_PERM = 5, 2, 1  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):

@@ -178,6 +178,7 @@ struct lowdin_it_ctx {
   int q1_variant = 5;                        // fused first quarter: 1 = shared-memory ring for the coefficient window, 2 = L1 path, no barrier, 3 = warp-specialised
   int gemm_variant = 2;                      // quarter-transform GEMM: 1 = cp.async ring (dgemm_tn_kernel), 2 = TMA + mbarrier persistent (dgemm_tma_kernel)
   int num_sms = 148;
+  int q3_two_cta = 0;                        // third quarter: products with K <= this value run as two 4-warp CTAs per SM (0 = off; LOWDIN_IT_OPT_Q3_TWO_CTA)
   int gemm_tall = 0;                         // TMA GEMM: 192 x 64 tiles when the rows are a multiple of 192 plus a few (probe; LOWDIN_IT_OPT_GEMM_TALL)
   int split_row_tail = 1;                    // TMA GEMM: run the <= 80-row tail of a few-rows x many-columns product as a swapped second launch
   int stored_fused = 1;                      // stored AO tensors: 1 = fused unpack + first quarter (q1_load_ws5_kernel), 0 = expansion kernel + DMMA GEMM
@@ -300,23 +301,26 @@ inline bool tma_eligible(const GemmArgs &g) {
          g.strideA == 0 && g.strideB == 0 && tensor_map_encoder() != nullptr;
 }
 
-template <int BM, int BN, int WM, int WN, class Epi>
+template <int BM, int BN, int WM, int WN, class Epi, int OCC = 1>
 cudaError_t launch_gemm_tma_cfg(lowdin_it_handle h, const GemmArgs &g, const Epi &epi) {
   constexpr int TNW = BN / WN / 8;
   constexpr bool staged = Epi::kRowCoalesced && (BM / WM / 8 == 4);  // row-coalescing epilogue: 32-row warp tiles only
   constexpr size_t staging = staged ? (size_t)WM * WN * TNW * 8 * TMA_STAGE_LDM * 8 : 0;
-  constexpr int ST_RAW = (int)((200704 + (staged ? 26624 : 0) - staging) / ((BM + BN) * 128));
+  // OCC CTAs share the SM's 228 KB (1 KB of it reserved per CTA)
+  constexpr int ST_RAW = (OCC == 1) ? (int)((200704 + (staged ? 26624 : 0) - staging) / ((BM + BN) * 128))
+                                    : (int)((233472 / OCC - 1024 - 1024 - 128 - staging) / ((BM + BN) * 128));
   constexpr int ST = ST_RAW > 8 ? 8 : ST_RAW;
+  static_assert(ST >= 2, "ring too short");
   constexpr size_t smem = tma_gemm_smem_bytes<BM, BN, ST>(staged ? WM * WN : 0, TNW);
-  static_assert(smem <= 232448, "shared memory per CTA");
+  static_assert(smem <= 232448 / OCC, "shared memory per CTA");
   const int perm = h->frag_perm ? 1 : 0;
-  auto kern = perm ? dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, true> : dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, false>;
+  auto kern = perm ? dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, true, OCC> : dgemm_tma_kernel<BM, BN, WM, WN, ST, Epi, false, OCC>;
   static uint64_t configured[2] = {0, 0};
   if (cudaError_t e = ensure_dyn_smem(kern, smem, h->device, configured[perm]); e != cudaSuccess) return e;
   CUtensorMap mapA, mapB;
   if (!make_operand_map(&mapA, g.A, g.M, g.K, g.lda, BM) || !make_operand_map(&mapB, g.B, g.N, g.K, g.ldb, BN)) return cudaErrorInvalidValue;
   const int64_t ntiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
-  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, h->num_sms);
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)OCC * h->num_sms);
   kern<<<grid, WM * WN * 32, smem, h->stream>>>(mapA, mapB, TmaGemmShape{g.M, g.N, g.K}, epi);
   h->launches += 1;
   return cudaGetLastError();
@@ -328,6 +332,16 @@ cudaError_t launch_gemm_one(lowdin_it_handle h, const GemmArgs &g, const Epi &ep
   const int n = g.N;
   if constexpr (Epi::kSplitRowTail)
     if (tall && tma) return launch_gemm_tma_cfg<192, 64, 4, 2>(h, g, epi);  // 48 x 32 warp tiles: 10 fragment loads per 48 DMMAs
+  if constexpr (Epi::kRowCoalesced) {
+    // third-quarter accumulation with a short K (the rank-pc update of a chunk): per 128 x 80 tile the
+    // read-modify-write of the accumulators takes as long as the DMMAs; two 4-warp CTAs per SM overlap the two
+    // (LOWDIN_IT_OPT_Q3_TWO_CTA; same warp tiles, same arithmetic)
+    if (tma && h->q3_two_cta && g.K <= h->q3_two_cta && n > 32) {
+      const int64_t q80 = ceil_div(n, 80) * 80, q64 = ceil_div(n, 64) * 64;
+      if (n > 64 && q80 <= q64) return launch_gemm_tma_cfg<64, 80, 2, 2, Epi, 2>(h, g, epi);
+      return launch_gemm_tma_cfg<64, 64, 2, 2, Epi, 2>(h, g, epi);
+    }
+  }
 #define LOWDIN_GEMM_CFG(BM, BN, WM, WN) (tma ? launch_gemm_tma_cfg<BM, BN, WM, WN>(h, g, epi) : launch_gemm_cfg<BM, BN, WM, WN>(h, g, epi))
   if (n <= 8) return LOWDIN_GEMM_CFG(256, 8, 8, 1);
   if (n <= 16) return LOWDIN_GEMM_CFG(256, 16, 8, 1);
@@ -1951,6 +1965,9 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->ao_list = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_GEMM_TALL:
       h->gemm_tall = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_Q3_TWO_CTA:
+      if (value < 0 || value > 4096) return fail(h, "LOWDIN_IT_OPT_Q3_TWO_CTA: 0 (off) or the largest K handled by the two-CTA kernels");
+      h->q3_two_cta = (int)value; return 0;
     case LOWDIN_IT_OPT_SINK_BLOCK_BYTES: {
       // block size of the host sink; the pinned two-slot ring is allocated HERE (page-locking gigabytes takes seconds when eight
       // processes of a box do it at once: a caller does it once, outside its timed region)

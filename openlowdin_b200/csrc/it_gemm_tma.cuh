@@ -123,8 +123,10 @@ constexpr size_t tma_gemm_smem_bytes(int warps = 0, int tn = 0) {
   return (size_t)STAGES * (BM + BN) * 128 + 2 * STAGES * 8 + 1024 + (size_t)warps * tn * 8 * TMA_STAGE_LDM * 8;
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, class Epi, bool PERM = false>
-__global__ void __launch_bounds__(WM *WN * 32, 1)
+// OCC = CTAs resident per SM: 2 for the short-K accumulating products of the third quarter, whose read-modify-write epilogue is as
+// long as their main loop -- two independent CTAs of 4 warps per SM let one tile's epilogue run under the other's DMMAs.
+template <int BM, int BN, int WM, int WN, int STAGES, class Epi, bool PERM = false, int OCC = 1>
+__global__ void __launch_bounds__(WM *WN * 32, OCC)
     dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaGemmShape g, Epi epi) {
   constexpr int BK = 16;
   constexpr int NCW = WM * WN;  // warps; all of them consume, lane 0 of warp 0 also produces

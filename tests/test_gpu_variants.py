@@ -323,3 +323,31 @@ def test_perm_n500_stream_sums_identical(T):
     assert got[0] == ref[0]
     for a, b in zip(got[1:], ref[1:]):
         assert abs(a - b) <= 1e-9 * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("n,occ,cols", [(70, 36, 300), (96, 66, 500), (96, 66, 0)])
+def test_third_quarter_two_cta_kernels(O, T, n, occ, cols):
+    """LOWDIN_IT_OPT_Q3_TWO_CTA: the short-K accumulating products of the third quarter as two 4-warp CTAs per SM (64 x 64 and
+    64 x 80 tiles) give the integrals of the default kernels; the first case is also checked against the oracle."""
+    seed = 777
+    Cm = O.random_orthonormal(n, n)
+    eps = O.synthetic_eps(occ, n)
+    win = O.windows_e_intra("MP2", n, occ)
+    T.set_species(0, Cm)
+    T.set_generator(0, 0, seed)
+    T.set_option(T.OPT_CHUNK_COLS, cols)
+    try:
+        ref = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=0, epsA=eps, lam=2.0)
+        ij, kl, v = T.transform(0, 0, win, ol.CONV_E)
+        T.set_option(T.OPT_Q3_TWO_CTA, 256)
+        got = T.transform_stream(0, 0, win, ol.CONV_E, occ_batch=0, epsA=eps, lam=2.0)
+        ij2, kl2, v2 = T.transform(0, 0, win, ol.CONV_E)
+    finally:
+        T.set_option(T.OPT_Q3_TWO_CTA, 0)
+        T.set_option(T.OPT_CHUNK_COLS, 0)
+    assert got[0] == ref[0] and np.abs(got[1:] - ref[1:]).max() <= 1e-9 * max(1.0, np.abs(ref[1:]).max())
+    assert np.array_equal(ij, ij2) and np.array_equal(kl, kl2) and np.abs(v - v2).max() <= 1e-12
+    if n == 70:
+        rij, rkl, rv = O.transform_e_intra(Cm, O.hash_packed_intra(seed, n), win)
+        assert len(rv) == len(v2) and np.abs(np.sort(rv) - np.sort(v2)).max() <= 1e-10
+        assert abs(got[3] - O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)) <= 1e-9
