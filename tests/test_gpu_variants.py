@@ -350,4 +350,5 @@ def test_third_quarter_two_cta_kernels(O, T, n, occ, cols):
     if n == 70:
         rij, rkl, rv = O.transform_e_intra(Cm, O.hash_packed_intra(seed, n), win)
         assert len(rv) == len(v2) and np.abs(np.sort(rv) - np.sort(v2)).max() <= 1e-10
-        assert abs(got[3] - O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)) <= 1e-9
+        e = O.mp2_intra_from_pairs(rij, rkl, rv, n, occ, eps, lam=2.0)     # ~ -1.8e5 for this synthetic input: relative tolerance
+        assert abs(got[3] - e) <= 1e-12 * abs(e)
