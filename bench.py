@@ -475,6 +475,7 @@ def main():
     ap.add_argument("--frag-perm", type=int, default=-1, help="fragment-row permutation of the TMA kernels: 0 / 1 (-1 = library default)")
     ap.add_argument("--overlap", type=int, default=-1, help="N>1: all-to-all of chunk c under the first half of chunk c+1: 0 / 1 (-1 = library default)")
     ap.add_argument("--gemm-tall", type=int, default=-1, help="192 x 64 tiles for the second / fourth quarter when the rows are a multiple of 192 plus a few: 0 / 1 (-1 = library default)")
+    ap.add_argument("--exchange-dma", type=int, default=-1, help="N>1 on one node: all-to-all as peer-to-peer DMA (1) or ncclSend/ncclRecv (0); -1 = library default")
     ap.add_argument("--q3-two-cta", type=int, default=-1, help="third quarter: products with K <= this value as two 4-warp CTAs per SM (0 = off, -1 = library default)")
     ap.add_argument("--q3-red", type=int, default=-1, help="third-quarter accumulation by red.global.add.f64: 0 / 1 (-1 = library default)")
     args = ap.parse_args()
@@ -535,6 +536,8 @@ def main():
         T.set_option(T.OPT_GEMM_TALL, args.gemm_tall)
     if args.q3_two_cta >= 0:
         T.set_option(T.OPT_Q3_TWO_CTA, args.q3_two_cta)
+    if args.exchange_dma >= 0:
+        T.set_option(T.OPT_EXCHANGE_DMA, args.exchange_dma)
     T.set_generator(0, 0, SEED, args.gen)
     npass, qb = T.num_passes(0, 0, win, ol.CONV_E, args.occ_batch)
 
@@ -613,6 +616,7 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t0
     stats = T.kernel_stats()
+    exchange_dma = T.exchange_is_dma()
     T.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -724,6 +728,8 @@ def main():
                                        f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
                                        f"({npass} passes = the whole transform)",
                            "nbf": n, "occ": occ, "gen": args.gen, "occ_batch": qb, "passes_per_transform": npass,
+                           "exchange": ("none (one GPU)" if world == 1 else "peer-to-peer DMA over cudaIpc-mapped chunk buffers" if exchange_dma
+                                        else "grouped ncclSend/ncclRecv"),
                            "l2": "working set larger than L2 (each pass re-streams the third-quarter accumulators and chunk buffers, tens of GB)",
                            "flops_per_step": flops / args.steps, "fp64_pct_of_cublas_dgemm_per_gpu": 100.0 * value / 1e3 / fp64_peak / world,
                            "fp64_pct_of_nominal_37tf_per_gpu": 100.0 * value / 37000.0 / world, "cublas_dgemm_tflops_measured": fp64_peak, "wall_ms_per_step": wall_s / args.steps * 1e3},

@@ -170,6 +170,8 @@ int lowdin_it_transform_inter_all(const double *coeff, const double *ocoeff, dou
  * element (its local slot `row`, global slab `slab`) at lowdin_it_exchanged_offset(). */
 int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t chunk_width, int nranks, int rank, int log_block,
                          int *own, int64_t *wblk, int64_t *loc_lo, int64_t *count);
+/* 1 when the all-to-all of this handle's communicator runs as peer-to-peer DMA (LOWDIN_IT_OPT_EXCHANGE_DMA and the node link was set up), else 0 */
+int lowdin_it_exchange_is_dma(lowdin_it_handle h);
 /* The occupied batch lowdin_it_transform_stream picks when occ_batch == 0, as a pure function (host logic, no device): n_first
  * first-window values, at most q_max per pass (memory), slots_per_first window pairs per first-window value, second-half window
  * sizes n_first2 / basis nao2, first-pair basis nao1, nslabs AO-pair slabs of npairs1 doubles, avail_bytes of device memory for the
@@ -210,6 +212,7 @@ int lowdin_it_group_download_quads(lowdin_it_handle *handles, int nranks, int32_
                                          * M(M+1)/2 dense tensor); the first quarter is then LIST-DRIVEN: every integral is scattered with its <= 4 images into the
                                          * quarter-transformed slabs (the DIRECT first quarter of Libint2Iface.cpp:793-853 / TransformIntegralsC.f90:545-558) */
 #define LOWDIN_IT_OPT_SLAB_BLOCK_LOG 12 /* log2 of the block of consecutive AO-pair slabs one rank owns in the block-cyclic first half (default 5); set before uploading */
+#define LOWDIN_IT_OPT_EXCHANGE_DMA 19     /* NCCL communicator whose ranks share one node: 1 (default) = the all-to-all between the halves as peer-to-peer DMA pulls over cudaIpc-mapped chunk buffers (no SMs taken from the persistent compute kernels), 0 = grouped ncclSend/ncclRecv; set alike on every rank */
 #define LOWDIN_IT_OPT_Q3_TWO_CTA 18       /* third quarter: accumulating products whose K (pair rows of the chunk) is <= this value run as two independent 4-warp CTAs per SM, so that one tile's read-modify-write epilogue overlaps the other's DMMAs; 0 = off */
 #define LOWDIN_IT_OPT_GEMM_TALL 17        /* TMA GEMM: 1 = 192 x 64 tiles for few-rows x many-columns products whose row count is a multiple of 192 plus <= 16 (1350 = 7 x 192 + 6) */
 #define LOWDIN_IT_OPT_SINK_BLOCK_BYTES 16 /* size of one dense block handed to the host sink (default 256 MiB; at least one first-contracted index worth of pairs is always sent); setting it allocates the pinned two-slot ring at once */

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "lowdin_it_ao_push_blocks", "lowdin_it_ao_set_rankk", "lowdin_it_ao_materialize", "lowdin_it_comm_init_local",
     "lowdin_it_debug_first_half", "lowdin_it_debug_first_quarter", "lowdin_it_result_segments", "lowdin_it_group_transform",
     "lowdin_it_group_result_count", "lowdin_it_group_download_pairs", "lowdin_it_group_download_quads",
-    "lowdin_it_transform_stream_sink", "lowdin_it_occ_batch_model", "lowdin_it_set_basis", "lowdin_it_basis_norma", "lowdin_it_ao_compute", "lowdin_it_ao_download",
+    "lowdin_it_transform_stream_sink", "lowdin_it_occ_batch_model", "lowdin_it_exchange_is_dma", "lowdin_it_set_basis", "lowdin_it_basis_norma", "lowdin_it_ao_compute", "lowdin_it_ao_download",
 ]
 
 
@@ -123,6 +123,7 @@ def load():
     L.lowdin_it_ao_set_rankk.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p, C.c_void_p]
     L.lowdin_it_ao_materialize.argtypes = [H, C.c_int, C.c_int]
     L.lowdin_it_comm_init_local.argtypes = [C.POINTER(H), C.c_int]
+    L.lowdin_it_exchange_is_dma.argtypes = [H]
     L.lowdin_it_occ_batch_model.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int]
     L.lowdin_it_set_basis.argtypes = [H, C.c_int, C.c_int, C.POINTER(Shell), _f64p, _f64p]
     L.lowdin_it_basis_norma.argtypes = [H, C.c_int, _f64p]
@@ -309,6 +310,9 @@ class Transformer:
     def comm_init(self, rank, nranks, uid: bytes):
         self._ck(self.L.lowdin_it_comm_init(self.h, rank, nranks, uid))
 
+    def exchange_is_dma(self):
+        return bool(self.L.lowdin_it_exchange_is_dma(self.h))
+
     def timers(self):
         t = np.zeros(8)
         self._ck(self.L.lowdin_it_timers(self.h, t))
@@ -318,7 +322,7 @@ class Transformer:
     CATEGORIES = ("expand1", "q1", "q2", "expand2", "q3", "q4", "consume", "exchange")
 
     OPT_WORKSPACE_BYTES, OPT_CHUNK_COLS, OPT_Q1_VARIANT, OPT_BENCH_GEN, OPT_GEMM_VARIANT, OPT_SPLIT_ROW_TAIL, OPT_FRAG_PERM = 1, 2, 3, 4, 5, 6, 7
-    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES, OPT_GEMM_TALL, OPT_Q3_TWO_CTA = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
+    OPT_ASYNC_PUSH, OPT_STAGING_BYTES, OPT_Q3_RED, OPT_AO_LIST, OPT_SLAB_BLOCK_LOG, OPT_Q1_DEBUG, OPT_STORED_FUSED, OPT_OVERLAP_EXCHANGE, OPT_SINK_BLOCK_BYTES, OPT_GEMM_TALL, OPT_Q3_TWO_CTA, OPT_EXCHANGE_DMA = 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
     DEFAULT_Q1_VARIANT, DEFAULT_GEMM_VARIANT, DEFAULT_FRAG_PERM = 5, 2, 1  # library defaults (it_api.cu); tests restore them after forcing a variant
 
     def set_option(self, option, value):

@@ -12,6 +12,12 @@
 #include "../../include/lowdin_it.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -126,6 +132,54 @@ struct LocalGroup {
   ~LocalGroup() { for (int i = 0; i < 16; ++i) { if (ready[i]) cudaEventDestroy(ready[i]); if (done[i]) cudaEventDestroy(done[i]); } }
 };
 
+// One process per GPU on ONE node: the all-to-all between the halves as peer-to-peer DMA instead of NCCL send/recv kernels.  The
+// compute kernels of both halves are persistent, one CTA per SM with the shared memory full, so an NCCL kernel that overlaps them
+// takes SMs a whole first-half launch was counting on (measured at 2 GPUs, profiles/r02v_*: ~1 s per pass of stall); copy engines
+// take none.  Every rank PULLS the rows of its own slots out of every peer's chunk buffer (cudaIpc-mapped), ordered by interprocess
+// events; the control plane (barrier, IPC handles) is a POSIX shared-memory segment named after the communicator's unique id.
+struct NodeShm {
+  std::atomic<int> count, gen, failed;
+  struct Rank {
+    cudaIpcMemHandle_t mem[2];
+    int has[2];
+    cudaIpcEventHandle_t ready[2], done[2];
+  } r[16];
+};
+struct NodeLink {
+  NodeShm *shm = nullptr;
+  int n = 0;
+  cudaEvent_t ready[2] = {}, done[2] = {};            // mine (interprocess)
+  cudaEvent_t peer_ready[16][2] = {}, peer_done[16][2] = {};
+  void *peer_mem[16][2] = {};                          // mapped for the duration of one pass
+  bool barrier() {
+    NodeShm &S = *shm;
+    if (S.failed.load()) return false;
+    const int g = S.gen.load();
+    if (S.count.fetch_add(1) + 1 == n) { S.count.store(0); S.gen.fetch_add(1); return true; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0; S.gen.load() == g; ++spin) {
+      if (S.failed.load()) return false;
+      if ((spin & 1023) == 1023) {
+        sched_yield();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(300)) { S.failed.store(1); return false; }
+      }
+    }
+    return true;
+  }
+  void unmap_all() {
+    for (int g = 0; g < 16; ++g)
+      for (int b = 0; b < 2; ++b)
+        if (peer_mem[g][b]) { cudaIpcCloseMemHandle(peer_mem[g][b]); peer_mem[g][b] = nullptr; }
+  }
+  ~NodeLink() {
+    unmap_all();
+    for (int b = 0; b < 2; ++b) { if (ready[b]) cudaEventDestroy(ready[b]); if (done[b]) cudaEventDestroy(done[b]); }
+    for (int g = 0; g < 16; ++g)
+      for (int b = 0; b < 2; ++b) { if (peer_ready[g][b]) cudaEventDestroy(peer_ready[g][b]); if (peer_done[g][b]) cudaEventDestroy(peer_done[g][b]); }
+    if (shm) munmap(shm, sizeof(NodeShm));
+  }
+};
+
 }  // namespace
 
 struct lowdin_it_ctx {
@@ -162,6 +216,9 @@ struct lowdin_it_ctx {
   int rank = 0, nranks = 1;
   void *comm = nullptr;                      // NCCL communicator (one process per GPU)
   std::shared_ptr<LocalGroup> lgroup;        // or: in-process group of handles
+  std::unique_ptr<NodeLink> node;            // NCCL form on one node: peer-to-peer DMA exchange (LOWDIN_IT_OPT_EXCHANGE_DMA)
+  int exchange_dma = 1;                      // 1 = use it when the node link could be set up, 0 = NCCL send/recv
+  bool node_mapped = false;                  // the peers' chunk buffers are mapped (inside the chunk loop of a pass)
   int slab_logB = 5;                         // block-cyclic distribution of the first half's slabs: blocks of 2^slab_logB slabs (it_kernels.cuh, slab_owner)
   void *sink_host[2] = {nullptr, nullptr};   // pinned host ring of the dense-block sink (lowdin_it_transform_stream_sink)
   size_t sink_host_cap = 0;
@@ -1115,6 +1172,32 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       if (pipelined) CK(cudaEventRecord(h->ev_sh[bsel], h->stream));
       return 0;
     };
+    const bool dma = (G > 1 && h->node && h->exchange_dma && !h->lgroup);
+    if (dma) {
+      // the chunk buffers at their largest size of the pass, once (peers map them for the whole chunk loop), then the mappings
+      NodeLink &N = *h->node;
+      size_t hmax = 1;
+      for (const Chunk &ck : chunks) {
+        int64_t wblk, lo_, cnt_;
+        shard_plan(nfb, pt.fbeg.data(), ck.base, ck.width, G, h->rank, h->slab_logB, own.data(), &wblk, &lo_, &cnt_);
+        hmax = std::max(hmax, (size_t)pt.nslots * (size_t)std::max<int64_t>(wblk, 1));
+      }
+      NodeShm::Rank &me = N.shm->r[h->rank];
+      for (int b = 0; b < 2; ++b) {
+        me.has[b] = 0;
+        if (b == 1 && !pipelined) continue;
+        CK(Hb[b]->ensure(hmax * sizeof(double)));
+        CK(cudaIpcGetMemHandle(&me.mem[b], Hb[b]->p));
+        me.has[b] = 1;
+      }
+      if (!N.barrier()) return fail(h, "node link: a rank did not reach the pass");
+      for (int g = 0; g < G; ++g) {
+        if (g == h->rank) continue;
+        for (int b = 0; b < 2; ++b)
+          if (N.shm->r[g].has[b]) CK(cudaIpcOpenMemHandle(&N.peer_mem[g][b], N.shm->r[g].mem[b], cudaIpcMemLazyEnablePeerAccess));
+      }
+      h->node_mapped = true;
+    }
     cudaEvent_t ev_begin = h->chunk_ev[4 * chunks.size()], ev_end = h->chunk_ev[4 * chunks.size() + 1];
     CK(cudaEventRecord(ev_begin, h->stream));
     if (pipelined) {
@@ -1130,6 +1213,11 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
     CK(cudaEventRecord(ev_end, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (G > 1) CK(cudaStreamSynchronize(cs));
+    if (dma) {  // nobody keeps a peer's buffer mapped outside the chunk loop: buffers may be freed or grown between passes
+      h->node->unmap_all();
+      h->node_mapped = false;
+      if (!h->node->barrier()) return fail(h, "node link: a rank did not finish the pass");
+    }
     prof_drain(h);
     {
       float ms, total = 0;
@@ -1328,6 +1416,30 @@ int exchange_chunk(lowdin_it_handle h, const std::vector<int> &own, int64_t wblk
     h->launches += 1;
     return 0;
   }
+  if (h->node && h->node_mapped) {
+    // one node, one process per GPU: every rank pulls the rows of its slots from every peer's (IPC-mapped) chunk buffer with copy
+    // engines, starting at its right-hand neighbour so that the G pulls of a step hit G different sources
+    NodeLink &N = *h->node;
+    const int r = h->rank, b = (Hsrc.p == h->Hx.p) ? 1 : 0;
+    CK(cudaEventRecord(N.ready[b], st));  // my first half of this chunk is complete behind this event
+    if (!N.barrier()) return fail(h, "node link: a rank did not reach the exchange");
+    for (int k = 1; k <= G; ++k) {
+      const int g = (r + k) % G;
+      if (g != r) CK(cudaStreamWaitEvent(st, N.peer_ready[g][b], 0));
+      if (mine > 0 && wblk > 0) {
+        const double *src = (g == r) ? Hsrc.as<double>() : static_cast<const double *>(N.peer_mem[g][b]);
+        if (!src) return fail(h, "node link: a peer's chunk buffer is not mapped");
+        CK(cudaMemcpyAsync(H2dst.as<double>() + (size_t)g * mine * wblk, src + (size_t)own[r] * wblk, (size_t)mine * wblk * sizeof(double),
+                           cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    CK(cudaEventRecord(N.done[b], st));
+    if (!N.barrier()) return fail(h, "node link: a rank did not reach the exchange");
+    for (int g = 0; g < G; ++g)
+      if (g != r) CK(cudaStreamWaitEvent(st, N.peer_done[g][b], 0));  // my H is rewritten only after every peer has pulled
+    h->launches += 1;
+    return 0;
+  }
   int rc = g_nccl.GroupStart();
   for (int g = 0; g < G && rc == 0; ++g) {
     const size_t send_n = (size_t)(own[g + 1] - own[g]) * wblk;   // rows own[g]..own[g+1] of H (row stride wblk)
@@ -1380,6 +1492,7 @@ int lowdin_it_destroy(lowdin_it_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  h->node.reset();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto &s : h->sp) { s.C.release(); s.Cs.release(); s.pi.release(); s.pj.release(); s.bs_shells.release(); s.bs_fn.release(); s.bs_expo.release(); s.bs_coef.release(); }
   for (auto &row : h->ao) for (auto &a : row) { a.data.release(); a.fa.release(); a.fb.release(); a.release_list(); a.seg_counts.release(); }
@@ -1965,6 +2078,8 @@ int lowdin_it_set_option(lowdin_it_handle h, int option, int64_t value) {
       h->ao_list = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_GEMM_TALL:
       h->gemm_tall = value ? 1 : 0; return 0;
+    case LOWDIN_IT_OPT_EXCHANGE_DMA:
+      h->exchange_dma = value ? 1 : 0; return 0;
     case LOWDIN_IT_OPT_Q3_TWO_CTA:
       if (value < 0 || value > 4096) return fail(h, "LOWDIN_IT_OPT_Q3_TWO_CTA: 0 (off) or the largest K handled by the two-CTA kernels");
       h->q3_two_cta = (int)value; return 0;
@@ -2098,6 +2213,7 @@ int lowdin_it_shard_plan(int nfb, const int *fbeg, int64_t chunk_base, int64_t c
   shard_plan(nfb, fbeg, chunk_base, chunk_width, nranks, rank, log_block, own, wblk, loc_lo, count);
   return 0;
 }
+int lowdin_it_exchange_is_dma(lowdin_it_handle h) { return (h && h->nranks > 1 && h->node && h->exchange_dma && !h->lgroup) ? 1 : 0; }
 int lowdin_it_occ_batch_model(int n_first, int q_max, int nranks, int64_t slots_per_first, int n_first2, int nao2, int nao1, int64_t nslabs,
                               int64_t npairs1, double avail_bytes, int stored) {
   return occ_batch_model(n_first, q_max, std::max(nranks, 1), (double)slots_per_first, n_first2, nao2, nao1, (double)nslabs, (double)npairs1, avail_bytes,
@@ -2120,6 +2236,64 @@ int lowdin_it_comm_unique_id(char id[128]) {
   return 0;
 }
 
+namespace {
+uint64_t fnv1a(const void *p, size_t n) {
+  uint64_t x = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { x ^= ((const unsigned char *)p)[i]; x *= 1099511628211ull; }
+  return x;
+}
+// Node link of an NCCL communicator whose ranks share one host (NodeLink above).  Collective; never an error: when any step fails
+// on any rank (different hosts, no shared /dev/shm, IPC refused) every rank keeps the NCCL exchange.
+void setup_node_link(lowdin_it_handle h, const char id[128]) {
+  const int G = h->nranks, r = h->rank;
+  char host[256] = {0};
+  gethostname(host, 255);
+  const int64_t hh = (int64_t)(fnv1a(host, strlen(host)) & 0x3fffffffffffffffull);
+  int64_t mn = hh, mx = -hh;
+  if (agree_min(h, &mn) || agree_min(h, &mx) || mn != -mx) return;
+  char name[64];
+  snprintf(name, sizeof name, "/lowdin_it_%016llx", (unsigned long long)fnv1a(id, 128));
+  NodeShm *S = nullptr;
+  int64_t ok = 1;
+  if (r == 0) {
+    shm_unlink(name);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, sizeof(NodeShm)) != 0) ok = 0;
+    if (ok) { void *m = mmap(nullptr, sizeof(NodeShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0); if (m == MAP_FAILED) ok = 0; else { S = (NodeShm *)m; memset(m, 0, sizeof(NodeShm)); } }
+    if (fd >= 0) close(fd);
+  }
+  if (agree_min(h, &ok)) return;  // also the barrier behind which the segment exists
+  if (ok && r != 0) {
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) ok = 0;
+    else { void *m = mmap(nullptr, sizeof(NodeShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0); if (m == MAP_FAILED) ok = 0; else S = (NodeShm *)m; close(fd); }
+  }
+  if (agree_min(h, &ok)) ok = 0;
+  if (r == 0) shm_unlink(name);  // the mappings keep the segment alive
+  if (!ok) { if (S) munmap(S, sizeof(NodeShm)); return; }
+  std::unique_ptr<NodeLink> N(new NodeLink);
+  N->shm = S; N->n = G;
+  int64_t ok2 = 1;
+  for (int b = 0; b < 2 && ok2; ++b) {
+    if (cudaEventCreateWithFlags(&N->ready[b], cudaEventDisableTiming | cudaEventInterprocess) != cudaSuccess ||
+        cudaEventCreateWithFlags(&N->done[b], cudaEventDisableTiming | cudaEventInterprocess) != cudaSuccess ||
+        cudaIpcGetEventHandle(&S->r[r].ready[b], N->ready[b]) != cudaSuccess || cudaIpcGetEventHandle(&S->r[r].done[b], N->done[b]) != cudaSuccess)
+      ok2 = 0;
+  }
+  if (agree_min(h, &ok2)) ok2 = 0;  // every rank has published its event handles (or none goes on)
+  for (int g = 0; g < G && ok2; ++g) {
+    if (g == r) continue;
+    for (int b = 0; b < 2 && ok2; ++b)
+      if (cudaIpcOpenEventHandle(&N->peer_ready[g][b], S->r[g].ready[b]) != cudaSuccess ||
+          cudaIpcOpenEventHandle(&N->peer_done[g][b], S->r[g].done[b]) != cudaSuccess)
+        ok2 = 0;
+  }
+  if (agree_min(h, &ok2)) ok2 = 0;
+  cudaGetLastError();  // a refused IPC call must not poison the next CK()
+  if (ok2) h->node = std::move(N);
+}
+}  // namespace
+
 int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[128]) {
   if (!h) return 1;
   if (nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks) return fail(h, "bad rank / nranks (1..16 ranks)");
@@ -2131,6 +2305,7 @@ int lowdin_it_comm_init(lowdin_it_handle h, int rank, int nranks, const char id[
   int rc = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
   if (rc) return fail(h, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
   h->rank = rank; h->nranks = nranks;
+  setup_node_link(h, id);
   return 0;
 }
 
