@@ -1172,7 +1172,7 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
       if (pipelined) CK(cudaEventRecord(h->ev_sh[bsel], h->stream));
       return 0;
     };
-    const bool dma = (G > 1 && h->node && h->exchange_dma && !h->lgroup);
+    bool dma = (G > 1 && h->node && h->exchange_dma && !h->lgroup);
     if (dma) {
       // the chunk buffers at their largest size of the pass, once (peers map them for the whole chunk loop), then the mappings
       NodeLink &N = *h->node;
@@ -1183,20 +1183,28 @@ int run_passes(lowdin_it_handle h, const Plan &pl, int occ_batch, int first_pass
         hmax = std::max(hmax, (size_t)pt.nslots * (size_t)std::max<int64_t>(wblk, 1));
       }
       NodeShm::Rank &me = N.shm->r[h->rank];
+      int64_t mapped_ok = 1;
       for (int b = 0; b < 2; ++b) {
         me.has[b] = 0;
         if (b == 1 && !pipelined) continue;
         CK(Hb[b]->ensure(hmax * sizeof(double)));
-        CK(cudaIpcGetMemHandle(&me.mem[b], Hb[b]->p));
-        me.has[b] = 1;
+        if (cudaIpcGetMemHandle(&me.mem[b], Hb[b]->p) == cudaSuccess) me.has[b] = 1; else mapped_ok = 0;
       }
       if (!N.barrier()) return fail(h, "node link: a rank did not reach the pass");
-      for (int g = 0; g < G; ++g) {
+      for (int g = 0; g < G && mapped_ok; ++g) {
         if (g == h->rank) continue;
-        for (int b = 0; b < 2; ++b)
-          if (N.shm->r[g].has[b]) CK(cudaIpcOpenMemHandle(&N.peer_mem[g][b], N.shm->r[g].mem[b], cudaIpcMemLazyEnablePeerAccess));
+        for (int b = 0; b < (pipelined ? 2 : 1) && mapped_ok; ++b)
+          if (!N.shm->r[g].has[b] || cudaIpcOpenMemHandle(&N.peer_mem[g][b], N.shm->r[g].mem[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) mapped_ok = 0;
       }
-      h->node_mapped = true;
+      cudaGetLastError();
+      if (agree_min(h, &mapped_ok)) return 1;
+      if (mapped_ok) h->node_mapped = true;
+      else {  // a buffer could not be exported or mapped somewhere: every rank goes back to ncclSend/ncclRecv, for good
+        N.unmap_all();
+        if (!N.barrier()) return fail(h, "node link: a rank did not reach the pass");
+        h->exchange_dma = 0;
+        dma = false;
+      }
     }
     cudaEvent_t ev_begin = h->chunk_ev[4 * chunks.size()], ev_end = h->chunk_ev[4 * chunks.size() + 1];
     CK(cudaEventRecord(ev_begin, h->stream));
