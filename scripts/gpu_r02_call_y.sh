@@ -4,8 +4,8 @@ TAG=${1:-r02y}; NG=${2:-8}
 mkdir -p gpurun_out
 O=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
-( timeout 300 $TR --master-port 29511 scripts/mgpu_check.py > $O/${TAG}_mgpu_check_g$NG.log 2>&1; echo "exit $?" >> $O/${TAG}_mgpu_check_g$NG.log ); grep -v "^W\|^\[W\|warn" $O/${TAG}_mgpu_check_g$NG.log | tail -6 | cut -c1-300
-( timeout 400 $TR --master-port 29512 bench.py --gpus $NG --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG}_bench_n1500_g${NG}.json 2> $O/${TAG}_bench_n1500_g${NG}.err; echo "exit $?" >> $O/${TAG}_bench_n1500_g${NG}.err )
+( [ "$SKIPCHECK" = "1" ] || timeout 300 $TR --master-port 29511 scripts/mgpu_check.py > $O/${TAG}_mgpu_check_g$NG.log 2>&1; echo "exit $?" >> $O/${TAG}_mgpu_check_g$NG.log ); grep -v "^W\|^\[W\|warn" $O/${TAG}_mgpu_check_g$NG.log | tail -6 | cut -c1-300
+( timeout 400 $TR --master-port 29512 bench.py --gpus $NG --steps ${STEPS:-3} --warmup 1 --no-cpu-baseline ${EXTRA} > $O/${TAG}_bench_n1500_g${NG}.json 2> $O/${TAG}_bench_n1500_g${NG}.err; echo "exit $?" >> $O/${TAG}_bench_n1500_g${NG}.err )
 python - <<PY
 import json
 try:
