@@ -2,7 +2,11 @@
 window of the scaling configurations: occupied batch, passes, third-quarter accumulators, chunk width, buffers per rank.
 No GPU needed; used to check that a sizing change still fits 180 GB before spending GPU time on it.
   python scripts/plan_model.py [free_GB]"""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from openlowdin_b200 import capi  # noqa: E402
 
 
 def ceil_div(a, b):
@@ -13,15 +17,13 @@ def model(N, G, free=178e9, ws=1 << 30):
     occ, virt = N // 10, N - N // 10
     nf, nf2, ns2, ld = occ, occ, virt, N + (N % 2)
     spf, per_out, M = virt, virt * occ * 8.0, N * (N + 1) // 2
-    out_need = max(min(4e9, spf * per_out * nf), spf * per_out)                      # pick_occ_batch
+    out_need = max(min(4e9, spf * per_out * nf), min(2, nf) * spf * per_out)          # pick_occ_batch
     avail = 0.92 * free - 2 * ws - out_need - (1 << 30)
     t3_per_f = spf * nf2 * ld * 8.0 / G
     hc_per_f = spf * 8.0 * min(M, 8 * N) * (3.0 / G if G > 1 else 1.0)
     qmax = int(max(1, min(nf, avail / (t3_per_f + hc_per_f))))
-    qb = ceil_div(nf, ceil_div(nf, qmax))
-    if 8 < qb < nf and ((qb + 7) & ~7) <= qmax:
-        qb = (qb + 7) & ~7
-    qb = min(qb, nf)
+    # the batch itself comes from the library's cost model (first + third quarter; a pure host function of the shared library)
+    qb = capi.occ_batch_model(nf, qmax, G, spf, nf2, N, N, M, M, avail, False)
     nslots = qb * virt                                                               # run_passes, first pass
     nmine = max((qb * (r + 1) // G - qb * r // G) * virt for r in range(G))
     t3 = nmine * nf2 * ld * 8
