@@ -92,3 +92,86 @@ def test_translation_and_rotation_invariance(O):
     tot = sum(O.eri_one(sh, 2 + i, 0, 2 + i, 11) for i in range(3))
     tot_m = sum(O.eri_one(moved, 2 + i, 0, 2 + i, 11) for i in range(3))
     assert abs(tot - tot_m) < 1e-13
+
+
+def _mp_reference(prims):
+    """(ab|cd) over NORMALISED primitive Cartesian Gaussians from 50-digit derivatives of the closed-form (ss|ss) integral:
+    x^n exp(-a x^2) is a combination of centre derivatives of exp(-a x^2) (n = 1: d/2a; n = 2: d2/4a^2 + 1/2a; n = 3: d3/8a^3 +
+    3 d/4a^2), so any class up to f follows from mixed partials of one analytic function -- no recurrences, no quadrature.
+    prims: four tuples (exponent, centre(3), (lx, ly, lz))."""
+    import itertools
+    import mpmath as mp
+    mp.mp.dps = 50
+    expo = [mp.mpf(p[0]) for p in prims]
+
+    def ssss(*c):   # 12 coordinates: A, B, C, D
+        A, B, Cc, D = (c[0:3], c[3:6], c[6:9], c[9:12])
+        a, b, cc, d = expo
+        p, q = a + b, cc + d
+        AB2 = sum((x - y) ** 2 for x, y in zip(A, B)); CD2 = sum((x - y) ** 2 for x, y in zip(Cc, D))
+        P = [(a * x + b * y) / p for x, y in zip(A, B)]; Q = [(cc * x + d * y) / q for x, y in zip(Cc, D)]
+        xx = p * q / (p + q) * sum((x - y) ** 2 for x, y in zip(P, Q))
+        f0 = mp.sqrt(mp.pi / xx) / 2 * mp.erf(mp.sqrt(xx)) if xx > mp.mpf("1e-30") else mp.mpf(1)
+        return 2 * mp.pi ** 2.5 / (p * q * mp.sqrt(p + q)) * mp.exp(-a * b / p * AB2 - cc * d / q * CD2) * f0
+
+    def terms(n, a):   # x^n g = sum_k coef_k d^k g / dA^k
+        return {0: [(0, mp.mpf(1))], 1: [(1, 1 / (2 * a))], 2: [(2, 1 / (4 * a * a)), (0, 1 / (2 * a))],
+                3: [(3, 1 / (8 * a ** 3)), (1, 3 / (4 * a * a))]}[n]
+    per_dim, point = [], []
+    for (a, centre, l), am in zip(prims, expo):
+        for d in range(3):
+            per_dim.append(terms(l[d], am)); point.append(mp.mpf(centre[d]))
+    total = mp.mpf(0)
+    for choice in itertools.product(*per_dim):
+        orders = tuple(k for k, _ in choice)
+        coef = mp.mpf(1)
+        for _, c in choice:
+            coef *= c
+        total += coef * (mp.diff(ssss, tuple(point), orders) if any(orders) else ssss(*point))
+
+    def dfact(n):
+        r = 1
+        while n > 1:
+            r *= n; n -= 2
+        return r
+    norm = mp.mpf(1)
+    for (a, _, l), am in zip(prims, expo):
+        L = sum(l)
+        norm *= (2 * am / mp.pi) ** mp.mpf("0.75") * (4 * am) ** (mp.mpf(L) / 2) / mp.sqrt(dfact(2 * l[0] - 1) * dfact(2 * l[1] - 1) * dfact(2 * l[2] - 1))
+    return float(total * norm)
+
+
+def _fn_index(l, comp):
+    """index of Cartesian component comp = (lx, ly, lz) inside a shell of angular momentum l (libint2 / CCA order)"""
+    k = 0
+    for lx in range(l, -1, -1):
+        for ly in range(l - lx, -1, -1):
+            if (lx, ly, l - lx - ly) == tuple(comp):
+                return k
+            k += 1
+    raise ValueError(comp)
+
+
+@pytest.mark.parametrize("case", [
+    ((3, (1, 1, 1)), (1, (0, 1, 0)), (2, (1, 0, 1)), (0, (0, 0, 0))),      # (f_xyz p_y | d_xz s)
+    ((3, (3, 0, 0)), (0, (0, 0, 0)), (0, (0, 0, 0)), (0, (0, 0, 0))),      # (f_xxx s | s s)
+    ((2, (2, 0, 0)), (2, (0, 2, 0)), (1, (0, 0, 1)), (1, (0, 0, 1))),      # (d_xx d_yy | p_z p_z)
+    ((3, (2, 1, 0)), (0, (0, 0, 0)), (3, (0, 1, 2)), (0, (0, 0, 0))),      # (f_xxy s | f_yzz s)
+    ((1, (1, 0, 0)), (2, (0, 1, 1)), (3, (0, 3, 0)), (0, (0, 0, 0))),      # (p_x d_yz | f_yyy s)
+])
+def test_high_angular_momentum_classes_against_analytic_derivatives(O, case):
+    """Every class up to f pinned WITHOUT any integral library: the oracle (Rys-form) against 50-digit mixed derivatives of the
+    closed-form (ss|ss) integral (mpmath), single primitives on four different centres.  (Checked once in the same way, too slow
+    to keep in the suite: (f_xyy f_yzz|s d_xy) and (p_x p_x|f_xxz f_yyy), 3 and 1 minutes of 50-digit differentiation.)"""
+    pytest.importorskip("mpmath")
+    expo = (0.9, 1.3, 0.7, 1.6)
+    centres = ((0.1, -0.2, 0.3), (0.7, 0.2, -0.4), (-0.5, 0.6, 0.1), (0.0, -0.9, 0.8))
+    shells, idx, off = [], [], 0
+    for (l, comp), a, c in zip(case, expo, centres):
+        shells.append((l, c, [a], [1.0]))
+        idx.append(off + _fn_index(l, comp))
+        off += (l + 1) * (l + 2) // 2
+    got = O.eri_one(shells, *idx)
+    ref = _mp_reference([(a, c, comp) for (l, comp), a, c in zip(case, expo, centres)])
+    assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (got, ref)
+    assert abs(ref) > 1e-6     # a non-trivial value
