@@ -43,3 +43,24 @@ def packed_to_full(packed, M):
     iu = np.triu_indices(M)
     sq[iu] = packed
     return sq + np.triu(sq, 1).T
+
+
+# Minimal-basis H2 at R = 1.4 a0 (Szabo & Ostlund, section 3.5.2 and eq. 6.77): overlap, MO two-electron integrals, orbital energies,
+# second-order (MP2) correlation energy K12^2 / (2 (eps1 - eps2)).
+H2_MO = {"S12": 0.6593, "J11": 0.6746, "J12": 0.6636, "J22": 0.6975, "K12": 0.1813, "eps": (-0.5782, 0.6703)}
+
+
+def h2_mo_coefficients(S):
+    """sigma_g, sigma_u of the minimal basis: (phi1 +- phi2) / sqrt(2 (1 +- S))"""
+    return np.array([[1 / np.sqrt(2 * (1 + S)), 1 / np.sqrt(2 * (1 - S))], [1 / np.sqrt(2 * (1 + S)), -1 / np.sqrt(2 * (1 - S))]])
+
+
+def sto3g_overlap(shell, R):
+    """<phi1|phi2> of two copies of one contracted s shell a distance R apart, unit-normalised"""
+    _, _, e, c = shell
+    e, c = np.array(e), np.array(c)
+    w = c * (2 * e / np.pi) ** 0.75
+    p = e[:, None] + e[None, :]
+    s12 = (w[:, None] * w[None, :] * (np.pi / p) ** 1.5 * np.exp(-e[:, None] * e[None, :] / p * R * R)).sum()
+    s11 = (w[:, None] * w[None, :] * (np.pi / p) ** 1.5).sum()
+    return s12 / s11

@@ -175,3 +175,24 @@ def test_high_angular_momentum_classes_against_analytic_derivatives(O, case):
     ref = _mp_reference([(a, c, comp) for (l, comp), a, c in zip(case, expo, centres)])
     assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (got, ref)
     assert abs(ref) > 1e-6     # a non-trivial value
+
+
+def test_h2_minimal_basis_chain_reproduces_the_textbook(O):
+    """basis -> AO integrals -> MO integrals -> MP2 energy on the CHECKER's side, against Szabo & Ostlund's minimal-basis H2:
+    the one real-molecule chain whose every number is published (the reference's own test energies need libint2 + an SCF)."""
+    from eri_cases import H2_MO, h2_mo_coefficients, sto3g_overlap
+    sh = h2_sto3g(O)
+    S = sto3g_overlap(sh[0], 1.4)
+    assert abs(S - H2_MO["S12"]) < 1e-4
+    Cm = h2_mo_coefficients(S)
+    packed = O.eri_packed_intra(sh)
+    win, sym = O.windows_c_intra("ALL", 2, 1)
+    p, q, r, s, v = O.transform_c_intra(Cm, packed, win, sym)
+    mo = {(a, b, c, d): x for a, b, c, d, x in zip(p, q, r, s, v)}
+    for key, name in (((1, 1, 1, 1), "J11"), ((1, 1, 2, 2), "J12"), ((2, 2, 2, 2), "J22"), ((1, 2, 1, 2), "K12")):
+        assert abs(mo[key] - H2_MO[name]) < 1e-4, (key, mo[key])
+    assert (1, 1, 1, 2) not in mo and (1, 2, 2, 2) not in mo          # zero by symmetry: below the 1e-10 output filter
+    ij, kl, vv = O.transform_e_intra(Cm, packed, O.windows_e_intra("MP2", 2, 1))
+    assert len(vv) == 1 and abs(vv[0] - H2_MO["K12"]) < 1e-4
+    e2 = O.mp2_intra_from_pairs(ij, kl, vv, 2, 1, np.array(H2_MO["eps"]))
+    assert abs(e2 - H2_MO["K12"] ** 2 / (2 * (H2_MO["eps"][0] - H2_MO["eps"][1]))) < 2e-5 and abs(e2 + 0.0132) < 1e-4

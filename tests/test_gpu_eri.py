@@ -162,3 +162,28 @@ def test_computed_ints_files_feed_the_file_to_file_transform(O, T, tmp_path):
     nmo = capi.host_transform_one_species(T, ctl, sp)
     rij, rkl, rv = O.transform_e_intra(Cm, packed, O.windows_e_intra("MP2", n, occ))
     assert abs(nmo - len(rv)) <= 2
+
+
+def test_h2_minimal_basis_chain_reproduces_the_textbook(O, T):
+    """The whole device chain on a real molecule whose every number is published (Szabo & Ostlund, minimal-basis H2, R = 1.4):
+    basis -> AO integrals (it_eri.cuh) -> MO integrals J11, J12, J22, K12 (transformer-C conventions, full window) -> (ia|jb) of
+    the MP2 window (transformer-E conventions) -> MP2 correlation energy -0.0132 Eh on the device."""
+    from eri_cases import H2_MO, h2_mo_coefficients, sto3g_overlap
+    sh = h2_sto3g(O)
+    Cm = h2_mo_coefficients(sto3g_overlap(sh[0], 1.4))
+    T.set_species(0, Cm)
+    T.set_basis(0, sh)
+    T.compute_ao(0, 0)
+    win, sym = O.windows_c_intra("ALL", 2, 1)
+    p, q, r, s, v = T.transform(0, 0, win, ol.CONV_C, symmetric=sym)
+    mo = {(a, b, c, d): x for a, b, c, d, x in zip(p, q, r, s, v)}
+    for key, name in (((1, 1, 1, 1), "J11"), ((1, 1, 2, 2), "J12"), ((2, 2, 2, 2), "J22"), ((1, 2, 1, 2), "K12")):
+        assert abs(mo[key] - H2_MO[name]) < 1e-4, (key, mo[key])
+    assert (1, 1, 1, 2) not in mo and (1, 2, 2, 2) not in mo
+    winE = O.windows_e_intra("MP2", 2, 1)
+    ij, kl, vv = T.transform(0, 0, winE, ol.CONV_E)
+    assert len(vv) == 1 and abs(vv[0] - H2_MO["K12"]) < 1e-4
+    e2 = T.transform_stream(0, 0, winE, ol.CONV_E, epsA=np.array(H2_MO["eps"]), lam=2.0)[3]
+    assert abs(e2 + 0.0132) < 1e-4
+    rij, rkl, rv = O.transform_e_intra(Cm, O.eri_packed_intra(sh), winE)
+    assert abs(e2 - O.mp2_intra_from_pairs(rij, rkl, rv, 2, 1, np.array(H2_MO["eps"]))) <= 1e-12
