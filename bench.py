@@ -728,6 +728,7 @@ def main():
                                        f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
                                        f"({npass} passes = the whole transform)",
                            "nbf": n, "occ": occ, "gen": args.gen, "occ_batch": qb, "passes_per_transform": npass,
+                           "transform_wall_s_at_this_rate": (2.0 * n * occ * (n + (n - occ)) * (n * (n + 1) // 2 + (n - occ) * occ)) / max(flops / dev_s, 1e-9),
                            "exchange": ("none (one GPU)" if world == 1 else "peer-to-peer DMA over cudaIpc-mapped chunk buffers" if exchange_dma
                                         else "grouped ncclSend/ncclRecv"),
                            "l2": "working set larger than L2 (each pass re-streams the third-quarter accumulators and chunk buffers, tens of GB)",
