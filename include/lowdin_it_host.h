@@ -155,6 +155,11 @@ int lowdin_host_plan_program(const lowdin_host_control *ctl, const lowdin_host_s
  * *ncalls = calls it made. */
 int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies,
                             int rank, int nranks, int64_t *nonzero, int *ncalls);
+/* The same loop for a ONE-PROCESS host driving several GPUs (the reference's program is one process): `handles` are the members of
+ * an in-process group (lowdin_it_comm_init_local); every call of the loop, in program order, runs on the whole group and writes
+ * its one moint.dat. */
+int lowdin_host_group_run_program(lowdin_it_handle *handles, int nhandles, const lowdin_host_control *ctl,
+                                  const lowdin_host_species *species, int nspecies, int64_t *nonzero, int *ncalls);
 
 #ifdef __cplusplus
 }

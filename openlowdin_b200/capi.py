@@ -467,7 +467,7 @@ HOST_SYMBOLS = [
     "lowdin_host_write_moint_pairs", "lowdin_host_atomic_to_molecular_one_species",
     "lowdin_host_atomic_to_molecular_two_species", "lowdin_host_plan_program", "lowdin_host_run_program",
     "lowdin_host_write_moint_d_intra", "lowdin_host_write_moint_d_inter", "lowdin_host_wfn_read", "lowdin_host_wfn_append",
-    "lowdin_host_wfn_load_species", "lowdin_host_group_atomic_to_molecular", "lowdin_host_write_computed_ints",
+    "lowdin_host_wfn_load_species", "lowdin_host_group_atomic_to_molecular", "lowdin_host_write_computed_ints", "lowdin_host_group_run_program",
 ]
 
 
@@ -533,6 +533,7 @@ def _host():
     L.lowdin_host_write_moint_pairs.argtypes = [C.c_char_p, C.c_int, _i64p, _i64p, _f64p, C.c_int64]
     L.lowdin_host_atomic_to_molecular_one_species.argtypes = [C.c_void_p, PC, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_atomic_to_molecular_two_species.argtypes = [C.c_void_p, PC, PS, PS, C.POINTER(C.c_int64)]
+    L.lowdin_host_group_run_program.argtypes = [C.POINTER(C.c_void_p), C.c_int, PC, PS, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L.lowdin_host_write_computed_ints.argtypes = [C.c_void_p, PC, PS, PS, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     L.lowdin_host_group_atomic_to_molecular.argtypes = [C.POINTER(C.c_void_p), C.c_int, PC, PS, PS, C.POINTER(C.c_int64)]
     L.lowdin_host_plan_program.argtypes = [PC, PS, C.c_int, C.c_int, C.POINTER(HostTask), C.c_int, C.POINTER(C.c_int)]
@@ -651,6 +652,15 @@ def host_run_program(T, ctl, species, rank=0, nranks=1):
     arr = _species_array(species)
     nz, nc = C.c_int64(), C.c_int()
     _hck(_host().lowdin_host_run_program(T.h if T is not None else None, C.byref(ctl), arr, len(species), rank, nranks, C.byref(nz), C.byref(nc)))
+    return nz.value, nc.value
+
+
+def host_group_run_program(transformers, ctl, species):
+    """The program's loop on an in-process group of GPUs (every call collective); returns (integrals written, calls made)."""
+    arr = _species_array(species)
+    hs = (C.c_void_p * len(transformers))(*[t.h for t in transformers])
+    nz, nc = C.c_int64(), C.c_int()
+    _hck(_host().lowdin_host_group_run_program(hs, len(transformers), C.byref(ctl), arr, len(species), C.byref(nz), C.byref(nc)))
     return nz.value, nc.value
 
 

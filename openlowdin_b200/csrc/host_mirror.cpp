@@ -756,8 +756,28 @@ int lowdin_host_plan_program(const lowdin_host_control *ctl, const lowdin_host_s
   return 0;
 }
 
+namespace {
+// the calls of the plan assigned to `rank` (program order) on one handle, or on the handles of an in-process group (every call collective)
+int run_program(lowdin_it_handle *hs, int nh, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies, int rank,
+                int nranks, int64_t *nonzero, int *ncalls);
+}  // namespace
+
 int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies,
                             int rank, int nranks, int64_t *nonzero, int *ncalls) {
+  return run_program(&h, 1, ctl, species, nspecies, rank, nranks, nonzero, ncalls);
+}
+
+// The program's loop for a ONE-PROCESS host driving several GPUs: every call of the loop, in program order, runs on the whole group
+// (the stored AO tensor sharded by rows, the transform collective, one moint.dat per call).
+int lowdin_host_group_run_program(lowdin_it_handle *handles, int nhandles, const lowdin_host_control *ctl, const lowdin_host_species *species,
+                                  int nspecies, int64_t *nonzero, int *ncalls) {
+  if (!handles || nhandles < 1) return hfail("null handles");
+  return run_program(handles, nhandles, ctl, species, nspecies, 0, 1, nonzero, ncalls);
+}
+
+namespace {
+int run_program(lowdin_it_handle *hs, int nh, const lowdin_host_control *ctl, const lowdin_host_species *species, int nspecies, int rank,
+                int nranks, int64_t *nonzero, int *ncalls) {
   if (rank < 0 || rank >= nranks) return hfail("bad rank");
   std::vector<lowdin_host_task> plan;
   if (plan_program(ctl, species, nspecies, nranks, plan)) return 1;
@@ -772,7 +792,7 @@ int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, 
       else printf("\n Integrals transformation for: %s\n\n", trimmed(a->name, 32).c_str());
     }
     int64_t n = 0;
-    if (run_and_write(&h, 1, ctl, a, b, &n)) return 1;
+    if (run_and_write(hs, nh, ctl, a, b, &n)) return 1;
     total += n;
     ++calls;
   }
@@ -780,5 +800,6 @@ int lowdin_host_run_program(lowdin_it_handle h, const lowdin_host_control *ctl, 
   if (ncalls) *ncalls = calls;
   return 0;
 }
+}  // namespace
 
 }  // extern "C"
