@@ -437,6 +437,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the device's PCI function), so that the pinned host
+    buffers it allocates afterwards -- the sink's ring that receives every MO integral -- sit on the GPU's NUMA node: with eight
+    ranks of one box delivering 41 GB each, buffers on the far socket make the slowest rank's copies cross the inter-socket link.
+    Returns a description, or None when nothing was done (no sysfs entry, one node, restricted cpuset)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} of {len(allowed)} CPUs, local to {bdf}"
+    except Exception:  # noqa: BLE001  (best effort: never fail the bench over placement)
+        pass
+    return None
+
+
 def cublas_fp64_peak(torch, dev, n=4096, iters=6):
     a = torch.rand(n, n, dtype=torch.float64, device=dev)
     b = torch.rand(n, n, dtype=torch.float64, device=dev)
@@ -475,6 +498,7 @@ def main():
     ap.add_argument("--frag-perm", type=int, default=-1, help="fragment-row permutation of the TMA kernels: 0 / 1 (-1 = library default)")
     ap.add_argument("--overlap", type=int, default=-1, help="N>1: all-to-all of chunk c under the first half of chunk c+1: 0 / 1 (-1 = library default)")
     ap.add_argument("--gemm-tall", type=int, default=-1, help="192 x 64 tiles for the second / fourth quarter when the rows are a multiple of 192 plus a few: 0 / 1 (-1 = library default)")
+    ap.add_argument("--numa-bind", type=int, default=-1, help="pin the process to the CPUs local to its GPU before allocating pinned buffers: 0 / 1 (-1 = when N > 1)")
     ap.add_argument("--exchange-dma", type=int, default=-1, help="N>1 on one node: all-to-all as peer-to-peer DMA (1) or ncclSend/ncclRecv (0); -1 = library default")
     ap.add_argument("--q3-two-cta", type=int, default=-1, help="third quarter: products with K <= this value as two 4-warp CTAs per SM (0 = off, -1 = library default)")
     ap.add_argument("--q3-red", type=int, default=-1, help="third-quarter accumulation by red.global.add.f64: 0 / 1 (-1 = library default)")
@@ -504,6 +528,8 @@ def main():
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # N > 1: NUMA-local pinned buffers (not at N = 1, where the cpu_baseline leg wants every host core)
+    host_affinity = bind_to_gpu_numa_node(torch, local) if (args.numa_bind == 1 or (args.numa_bind < 0 and world > 1)) else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -728,6 +754,7 @@ def main():
                                        f"random orthonormal C; step = one occupied-batch pass of {qb} occupied orbitals "
                                        f"({npass} passes = the whole transform)",
                            "nbf": n, "occ": occ, "gen": args.gen, "occ_batch": qb, "passes_per_transform": npass,
+                           "host_affinity": host_affinity,
                            "transform_wall_s_at_this_rate": (2.0 * n * occ * (n + (n - occ)) * (n * (n + 1) // 2 + (n - occ) * occ)) / max(flops / dev_s, 1e-9),
                            "exchange": ("none (one GPU)" if world == 1 else "peer-to-peer DMA over cudaIpc-mapped chunk buffers" if exchange_dma
                                         else "grouped ncclSend/ncclRecv"),
